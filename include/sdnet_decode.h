@@ -1,0 +1,113 @@
+/*
+ * sdnet_decode.h -- C ABI of the B200-native SDNet decoding path.
+ *
+ * The reference (laclouis5/StructureDetector) is pure Python and has no FFI of its own;
+ * these entry points are what a binding for its decoding path would call.  Each one
+ * names the reference code it replaces (paths relative to the reference repo root).
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes only; no C++/torch types cross the boundary;
+ *   - the caller owns every buffer (inputs, outputs, workspace); the library never
+ *     allocates or frees device memory and keeps no per-call state;
+ *   - stream-ordered and asynchronous: work is enqueued on `stream` (a cudaStream_t
+ *     passed as void*), nothing synchronises;
+ *   - re-entrant across host threads and streams given distinct workspaces;
+ *   - return value: 0 = OK; negative = argument error detected on the host before any
+ *     launch (SDNET_E_*); positive = a cudaError_t raised by a launch.
+ *   - there is no CPU fallback: on a machine without a CUDA device every launch
+ *     returns a positive cudaError_t.
+ */
+#ifndef SDNET_DECODE_H_
+#define SDNET_DECODE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDNET_ABI_VERSION 1
+
+/* element types of the four input tensors */
+#define SDNET_DTYPE_F32 0
+
+/* SdnetDecodeParams.flags */
+#define SDNET_FLAG_PRE_ACTIVATED 1u /* heat maps already sigmoid+NMS'd: decoders.py:211,226 (CoreMLDecoder) */
+#define SDNET_FLAG_NO_GROUPING 2u   /* skip part->anchor grouping: decoders.py:345-423 (KeypointDecoder) */
+#define SDNET_FLAG_EXACT_SELECT 4u  /* route every plane through the bounded-memory exact select (testing) */
+
+/* argument errors */
+#define SDNET_E_NULL -1      /* a required pointer is NULL */
+#define SDNET_E_SHAPE -2     /* non-positive dimension, H*W >= 2^24, K or P > H*W (torch.topk: "k out of range"),
+                                K or P > SDNET_MAX_TOPK, M+N > SDNET_MAX_CHANNELS */
+#define SDNET_E_STRIDE -3    /* innermost (w) stride is not 1 */
+#define SDNET_E_DTYPE -4     /* unsupported dtype */
+#define SDNET_E_WORKSPACE -5 /* workspace missing, misaligned (256 B) or smaller than sdnet_decode_workspace_bytes */
+#define SDNET_E_RADIUS -6    /* NMS window radius other than 2 (5x5, utils.py:442) or 1 (3x3) */
+#define SDNET_E_STRUCT -7    /* struct_size does not match this library's SdnetDecodeParams */
+
+#define SDNET_MAX_TOPK 1024
+#define SDNET_MAX_CHANNELS 255
+
+/* A strided NCHW view.  Strides are in ELEMENTS.  The decoder consumes the channel-slice
+ * views produced by the reference network (src/sdnet/model/network.py:79-84), which are
+ * not contiguous in the batch dimension, so b/c/h strides are free; stride_w must be 1. */
+typedef struct SdnetTensor4 {
+  const void* data;
+  int64_t stride_b, stride_c, stride_h, stride_w;
+} SdnetTensor4;
+
+typedef struct SdnetDecodeParams {
+  uint32_t struct_size; /* sizeof(SdnetDecodeParams) */
+  int32_t dtype;        /* SDNET_DTYPE_* */
+  int32_t B, M, N, H, W; /* batch, anchor classes, part kinds, map rows, map cols */
+  int32_t K, P;          /* max_objects, max_parts (decoders.py:25-26) */
+  int32_t radius;        /* NMS window radius; 2 = the reference's 5x5 (utils.py:442) */
+  uint32_t flags;        /* SDNET_FLAG_* */
+  float conf_f32;        /* (float)conf_thresh: `scores > conf` is an fp32 compare (decoders.py:78,83) */
+  float dist_abs_f32;    /* (float)(dist_thresh * min(W, H)) (decoders.py:100) */
+  SdnetTensor4 anchor_hm;  /* (B, M, H, W) logits */
+  SdnetTensor4 part_hm;    /* (B, N, H, W) logits */
+  SdnetTensor4 offsets;    /* (B, 2, H, W) */
+  SdnetTensor4 embeddings; /* (B, 2, H, W); may be NULL data with SDNET_FLAG_NO_GROUPING */
+  /* outputs, all contiguous, all device memory */
+  float* anchor_out;    /* (B, K, 4) x, y, score, class           decoders.py:55-57 */
+  float* part_out;      /* (B, P, 6) x, y, score, kind, ox, oy    decoders.py:72-75 */
+  int64_t* anchor_inds; /* (B, K) flat h*W+w index of each slot   utils.py:463 */
+  int64_t* part_inds;   /* (B, P) */
+  float* part_emb;      /* (B, P, 2) gathered embeddings, optional (NULL to skip)  decoders.py:66 */
+  int32_t* assign;      /* (B, P) anchor slot of each part, -1 when not grouped  decoders.py:99-100,108-112 */
+  int32_t* counts;      /* (B, 2) slots with score > conf: anchors, parts */
+  int32_t* diag;        /* optional (B*(M+N), 2): candidates emitted per plane, 1 if the exact select ran */
+  void* workspace;
+  size_t workspace_bytes;
+} SdnetDecodeParams;
+
+/* Library / ABI identification. */
+int sdnet_abi_version(void);
+const char* sdnet_error_string(int code);
+
+/* Scratch size for one in-flight decode of the given shape. */
+int sdnet_decode_workspace_bytes(int B, int M, int N, int H, int W, int K, int P, int dtype, size_t* out_bytes);
+
+/* The whole tensor half of Decoder.__call__ (src/sdnet/data/decoders.py:44-100 with
+ * src/sdnet/utils/utils.py:355-361 clamped_sigmoid, 441-443 nms, 447-467 topk,
+ * 347-351 transpose_and_gather, 422-437 hypot): heat maps -> packed detections. */
+int sdnet_decode_launch(const SdnetDecodeParams* params, void* stream);
+
+/* clamp(sigmoid(x), 1e-6, 1-1e-6) of a (B, C, H, W) view into a contiguous fp32 tensor:
+ * the `anchor_hm_sig` / `part_hm_sig` metadata maps (decoders.py:44,60,163-164). */
+int sdnet_activate_launch(const SdnetTensor4* in, int dtype, int B, int C, int H, int W, float* out, void* stream);
+
+/* Same as sdnet_decode_launch but the four input tensors live in (pinned) HOST memory:
+ * the heat-map planes are staged to `staging` (device, >= B*(M+N)*H*W*4 bytes) in
+ * chunks overlapped with the kernels, offsets/embeddings are only touched at the
+ * selected peaks.  Outputs stay on the device.  Uses `stream` plus one internal
+ * copy stream per call. */
+int sdnet_decode_host_launch(const SdnetDecodeParams* params, void* staging, size_t staging_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDNET_DECODE_H_ */

@@ -1,0 +1,134 @@
+"""ctypes binding of ``libsdnet_decode.so`` (C ABI declared in ``include/sdnet_decode.h``).
+
+There is deliberately no fallback: if the shared library is missing or does not export
+the expected ABI, importing the decode ops raises.  Build it with
+``python -m structuredetector_b200.build`` (or ``__graft_entry__.build()``).
+"""
+from __future__ import annotations
+
+import ctypes
+from pathlib import Path
+
+LIB_PATH = Path(__file__).resolve().parent / "csrc" / "libsdnet_decode.so"
+ABI_VERSION = 1
+
+FLAG_PRE_ACTIVATED = 1
+FLAG_NO_GROUPING = 2
+FLAG_EXACT_SELECT = 4
+DTYPE_F32 = 0
+MAX_TOPK = 1024
+MAX_CHANNELS = 255
+
+EXPORTS = (
+    "sdnet_abi_version",
+    "sdnet_error_string",
+    "sdnet_decode_workspace_bytes",
+    "sdnet_decode_launch",
+    "sdnet_activate_launch",
+    "sdnet_decode_host_launch",
+)
+
+
+class SdnetTensor4(ctypes.Structure):
+    _fields_ = [
+        ("data", ctypes.c_void_p),
+        ("stride_b", ctypes.c_int64),
+        ("stride_c", ctypes.c_int64),
+        ("stride_h", ctypes.c_int64),
+        ("stride_w", ctypes.c_int64),
+    ]
+
+
+class SdnetDecodeParams(ctypes.Structure):
+    _fields_ = [
+        ("struct_size", ctypes.c_uint32),
+        ("dtype", ctypes.c_int32),
+        ("B", ctypes.c_int32),
+        ("M", ctypes.c_int32),
+        ("N", ctypes.c_int32),
+        ("H", ctypes.c_int32),
+        ("W", ctypes.c_int32),
+        ("K", ctypes.c_int32),
+        ("P", ctypes.c_int32),
+        ("radius", ctypes.c_int32),
+        ("flags", ctypes.c_uint32),
+        ("conf_f32", ctypes.c_float),
+        ("dist_abs_f32", ctypes.c_float),
+        ("anchor_hm", SdnetTensor4),
+        ("part_hm", SdnetTensor4),
+        ("offsets", SdnetTensor4),
+        ("embeddings", SdnetTensor4),
+        ("anchor_out", ctypes.c_void_p),
+        ("part_out", ctypes.c_void_p),
+        ("anchor_inds", ctypes.c_void_p),
+        ("part_inds", ctypes.c_void_p),
+        ("part_emb", ctypes.c_void_p),
+        ("assign", ctypes.c_void_p),
+        ("counts", ctypes.c_void_p),
+        ("diag", ctypes.c_void_p),
+        ("workspace", ctypes.c_void_p),
+        ("workspace_bytes", ctypes.c_size_t),
+    ]
+
+
+class NativeLibraryError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """Load the decode library once; raise ``NativeLibraryError`` if it cannot be used."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise NativeLibraryError(
+            f"{LIB_PATH} is missing: build the CUDA extension first "
+            "(python -m structuredetector_b200.build). There is no CPU fallback."
+        )
+    lib = ctypes.CDLL(str(LIB_PATH))
+    missing = [name for name in EXPORTS if not hasattr(lib, name)]
+    if missing:
+        raise NativeLibraryError(f"{LIB_PATH} does not export {missing}")
+    lib.sdnet_abi_version.restype = ctypes.c_int
+    lib.sdnet_error_string.restype = ctypes.c_char_p
+    lib.sdnet_error_string.argtypes = [ctypes.c_int]
+    lib.sdnet_decode_workspace_bytes.restype = ctypes.c_int
+    lib.sdnet_decode_workspace_bytes.argtypes = [ctypes.c_int] * 8 + [ctypes.POINTER(ctypes.c_size_t)]
+    lib.sdnet_decode_launch.restype = ctypes.c_int
+    lib.sdnet_decode_launch.argtypes = [ctypes.POINTER(SdnetDecodeParams), ctypes.c_void_p]
+    lib.sdnet_activate_launch.restype = ctypes.c_int
+    lib.sdnet_activate_launch.argtypes = [ctypes.POINTER(SdnetTensor4), ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                          ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+    lib.sdnet_decode_host_launch.restype = ctypes.c_int
+    lib.sdnet_decode_host_launch.argtypes = [ctypes.POINTER(SdnetDecodeParams), ctypes.c_void_p, ctypes.c_size_t,
+                                             ctypes.c_void_p]
+    if lib.sdnet_abi_version() != ABI_VERSION:
+        raise NativeLibraryError(f"ABI mismatch: library {lib.sdnet_abi_version()} != binding {ABI_VERSION}")
+    _lib = lib
+    return lib
+
+
+def error_string(code: int) -> str:
+    return load().sdnet_error_string(int(code)).decode()
+
+
+def check(code: int, what: str):
+    """Map the C ABI's return convention onto Python exceptions."""
+    if code == 0:
+        return
+    msg = f"{what}: {error_string(code)} (code {code})"
+    if code == -2:
+        # mirrors torch.topk's failure for k > H*W in the reference (SURVEY 8b "Error conventions")
+        raise RuntimeError(msg)
+    if code < 0:
+        raise ValueError(msg)
+    raise RuntimeError(msg)
+
+
+def workspace_bytes(B, M, N, H, W, K, P, dtype=DTYPE_F32) -> int:
+    out = ctypes.c_size_t(0)
+    check(load().sdnet_decode_workspace_bytes(B, M, N, H, W, K, P, dtype, ctypes.byref(out)), "sdnet_decode_workspace_bytes")
+    return int(out.value)

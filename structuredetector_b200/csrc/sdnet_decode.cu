@@ -1,0 +1,1058 @@
+// sdnet_decode.cu -- B200 (sm_100a) kernels + C ABI for the SDNet decoding path.
+//
+// Replaces the tensor half of the reference decoder
+//   src/sdnet/data/decoders.py:44-100  (Decoder.__call__)
+//   src/sdnet/utils/utils.py:355-361   clamped_sigmoid
+//   src/sdnet/utils/utils.py:441-443   nms (5x5 max-pool equality)
+//   src/sdnet/utils/utils.py:447-467   topk (per-channel, then cross-channel)
+//   src/sdnet/utils/utils.py:347-351   transpose_and_gather
+//   src/sdnet/utils/utils.py:422-437   hypot
+// with three launches:
+//   1. peaks kernel   -- the only pass over the heat maps (HBM-bound).  One warp walks a
+//      128-column panel of one plane top to bottom with a register ring of 8 rows, finds
+//      the pixels that survive the reference's NMS and appends (score, index) records to a
+//      small per-plane candidate list, pruning everything that provably cannot reach the
+//      plane's top-K.
+//   2. exact-select kernel -- only for planes whose candidate list overflowed (huge exact
+//      plateaus): bounded-memory radix select straight from the heat map.
+//   3. tail kernel    -- one CTA per image: radix-select + sort of the candidates under the
+//      total order (score desc, class asc, index asc), zero-fill, offset/embedding gather,
+//      coordinate assembly, masking, nearest-anchor grouping.
+//
+// Numerics contract:
+//   * score  = min(max(1/(1+expf(-x)), 1e-6f), (float)(1-1e-6))   -- ATen's CUDA formula;
+//   * a pixel survives NMS iff score == max score over its window.  With S monotone
+//     non-decreasing in x (verified exhaustively on the device, tests/test_gpu_parity.py)
+//     this is  S(x) == S(window-max of x), so the stencil runs on raw logits and the exact
+//     sigmoid is evaluated only for the few pixels within a hair of their window maximum;
+//   * ties: (score desc, class asc, flat index asc) -- what torch.topk does on CUDA for k > 32;
+//   * grouping arithmetic uses explicitly rounded mul/add/sqrt (no FMA contraction) and the
+//     first minimum wins.
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "sdnet_decode.h"
+
+namespace {
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+
+constexpr int kThreads = 256;          // peaks kernel CTA
+constexpr int kWarps = kThreads / 32;
+constexpr int kPanelW = 128;           // columns per warp (32 lanes x 4)
+constexpr int kRing = 8;               // rows held in registers per lane
+constexpr int kBins = 128;             // per-warp logit histogram used for pruning
+constexpr float kBinLo = -16.0f;
+constexpr float kBinScale = 4.0f;      // bins of 0.25 logit
+constexpr float kNearTie = 2e-3f;      // logit margin inside which two scores may round equal (|x| <= 8)
+constexpr float kHiZone = 8.0f;        // above this, score spacing approaches 1 ulp: always check exactly
+constexpr float kLoZone = -13.0f;      // below this, scores approach the 1e-6 clamp: always check exactly
+constexpr float kSatX = 14.0f;         // |x| >= 14 is inside the clamp on both sides: S(x) == S(+-14)
+constexpr float kPreScale = 8.0f;      // pre-activated maps: histogram runs on 8*value
+constexpr float kClampLo = 1e-6f;
+constexpr float kClampHi = (float)(1.0 - 1e-6);
+constexpr float kFar = 1e6f;
+
+constexpr int kTailThreads = 256;
+constexpr int kSortN = 2048;           // tail sort buffer (>= SDNET_MAX_TOPK + boundary slack)
+
+struct View4 {
+  const float* data;
+  long long sb, sc, sh;
+};
+
+struct PeaksParams {
+  View4 anchor, part;
+  int B, M, N, H, W, K, P;
+  int strips, rows_per_strip, panels;
+  int units;
+  int cap;                 // records per plane list
+  int pre_activated;
+  u64* lists;              // [planes][cap]
+  int* counts;             // [planes] records emitted (may exceed cap)
+  u32* sched;              // [0] dynamic unit counter
+};
+
+// clamp(sigmoid(x)) bit-identical to ATen's CUDA kernels (UnarySpecialOpsKernel.cu sigmoid:
+// one / (one + std::exp(-a)); clamp: min(max(v, lo), hi)).
+__device__ __forceinline__ float activate(float x) {
+  float s = 1.0f / (1.0f + expf(-x));
+  return fminf(fmaxf(s, kClampLo), kClampHi);
+}
+
+__device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
+
+__device__ __forceinline__ float comp(const float4& v, int j) {
+  return j == 0 ? v.x : (j == 1 ? v.y : (j == 2 ? v.z : v.w));
+}
+
+// ---------------------------------------------------------------------------------------------
+// peaks kernel
+// ---------------------------------------------------------------------------------------------
+template <bool kAligned>
+__device__ __forceinline__ void load_row(const float* __restrict__ plane, long long sh, int row, int H, int W,
+                                         int col0, int lane, int panel_col0, float4& v, float2& hv) {
+  const float ninf = -CUDART_INF_F;
+  v = make_float4(ninf, ninf, ninf, ninf);
+  hv = make_float2(ninf, ninf);
+  if (row < 0 || row >= H) return;  // warp-uniform
+  const float* rp = plane + (long long)row * sh;
+  if (kAligned) {
+    if (col0 < W) v = __ldg(reinterpret_cast<const float4*>(rp + col0));
+    if (lane == 0 && panel_col0 > 0) hv = __ldg(reinterpret_cast<const float2*>(rp + panel_col0 - 2));
+    if (lane == 31 && panel_col0 + kPanelW < W) hv = __ldg(reinterpret_cast<const float2*>(rp + panel_col0 + kPanelW));
+  } else {
+    if (col0 + 0 < W) v.x = __ldg(rp + col0 + 0);
+    if (col0 + 1 < W) v.y = __ldg(rp + col0 + 1);
+    if (col0 + 2 < W) v.z = __ldg(rp + col0 + 2);
+    if (col0 + 3 < W) v.w = __ldg(rp + col0 + 3);
+    if (lane == 0 && panel_col0 > 0) {
+      hv.x = __ldg(rp + panel_col0 - 2);
+      hv.y = __ldg(rp + panel_col0 - 1);
+    }
+    if (lane == 31) {
+      if (panel_col0 + kPanelW < W) hv.x = __ldg(rp + panel_col0 + kPanelW);
+      if (panel_col0 + kPanelW + 1 < W) hv.y = __ldg(rp + panel_col0 + kPanelW + 1);
+    }
+  }
+}
+
+__device__ __forceinline__ int logit_bin(float x) {
+  int bin = __float2int_rd((x - kBinLo) * kBinScale);
+  bin = max(0, min(kBins - 1, bin));
+  // rounding guard: never count an element in a bin whose lower edge is above it
+  if (bin > 0 && x < kBinLo + (float)bin * (1.0f / kBinScale)) --bin;
+  return bin;
+}
+
+// order-preserving float <-> int (so atomicMin works on floats of either sign)
+__device__ __forceinline__ int ord_of(float x) {
+  const int b = __float_as_int(x);
+  return b ^ ((b >> 31) & 0x7fffffff);
+}
+__device__ __forceinline__ float ord_to_float(int o) { return __int_as_float(o ^ ((o >> 31) & 0x7fffffff)); }
+
+// Pruning floor of one warp-unit.  Let b be the highest bin such that the unit has already
+// recorded >= K candidates in bins >= b.  Every one of those has a (saturation-clamped) logit
+// >= minx[b], a lower flat index than anything the unit will see later, and therefore beats any
+// later pixel whose clamped logit is <= minx[b] under (score desc, index asc).  Returns that
+// minx[b] (in clamped-logit units), or -inf when fewer than K candidates were recorded.
+__device__ __forceinline__ float floor_value(const u32* hist, const int* minx, int lane, int K) {
+  const uint4 c = *reinterpret_cast<const uint4*>(hist + 4 * lane);
+  const u32 s = c.x + c.y + c.z + c.w;
+  u32 suf = s;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    u32 t = __shfl_down_sync(0xffffffffu, suf, d);
+    if (lane + d < 32) suf += t;
+  }
+  const u32 mask = __ballot_sync(0xffffffffu, suf >= (u32)K);
+  if (mask == 0) return -CUDART_INF_F;
+  const int L = 31 - __clz(mask);
+  float f = 0.f;
+  if (lane == L) {
+    u32 above = suf - s;
+    int b;
+    if (above + c.w >= (u32)K) b = 4 * L + 3;
+    else if (above + c.w + c.z >= (u32)K) b = 4 * L + 2;
+    else if (above + c.w + c.z + c.y >= (u32)K) b = 4 * L + 1;
+    else b = 4 * L;
+    f = ord_to_float(minx[b]);
+  }
+  return __shfl_sync(0xffffffffu, f, L);
+}
+
+template <bool kAligned, int R>
+__global__ void __launch_bounds__(kThreads, 3) sdnet_peaks_kernel(const __grid_constant__ PeaksParams p) {
+  __shared__ __align__(16) u32 s_hist[kWarps][kBins];
+  __shared__ __align__(16) int s_minx[kWarps][kBins];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  u32* hist = s_hist[warp];
+  int* minx = s_minx[warp];
+  const float xscale = p.pre_activated ? kPreScale : 1.0f;
+  const float satx = p.pre_activated ? CUDART_INF_F : kSatX;
+  const float ninf = -CUDART_INF_F;
+  const int C = p.M + p.N;
+
+  for (;;) {
+    u32 unit = 0;
+    if (lane == 0) unit = atomicAdd(p.sched, 1u);
+    unit = __shfl_sync(0xffffffffu, unit, 0);
+    if (unit >= (u32)p.units) break;
+    const int panel = unit % p.panels;
+    const int t1 = unit / p.panels;
+    const int strip = t1 % p.strips;
+    const int plane_id = t1 / p.strips;
+    const int b = plane_id / C, c = plane_id % C;
+    const bool is_anchor = c < p.M;
+    const View4& vw = is_anchor ? p.anchor : p.part;
+    const float* __restrict__ plane = vw.data + (long long)b * vw.sb + (long long)(is_anchor ? c : c - p.M) * vw.sc;
+    const long long sh = vw.sh;
+    const int K = is_anchor ? p.K : p.P;
+    const int H = p.H, W = p.W;
+    const int panel_col0 = panel * kPanelW;
+    const int col0 = panel_col0 + lane * 4;
+    const int r_begin = strip * p.rows_per_strip;
+    const int r_end = min(H, r_begin + p.rows_per_strip);
+    const int nrows = r_end - r_begin;
+    u64* __restrict__ list = p.lists + (size_t)plane_id * p.cap;
+    int* count_ptr = p.counts + plane_id;
+
+    // per-unit pruning state (warp-uniform)
+    float floorx = ninf;  // in input units; a pixel can still matter only if min(x, satx) > floorx
+    u32 emitted = 0;
+    *reinterpret_cast<uint4*>(hist + 4 * lane) = make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<int4*>(minx + 4 * lane) = make_int4(0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff);
+    __syncwarp();
+
+    float4 ring[kRing];
+    float2 hring[kRing];
+    // prologue: rows r_begin-R .. r_begin-R+kRing-2
+#pragma unroll
+    for (int q = 0; q < kRing - 1; ++q) {
+      const int row = r_begin - R + q;
+      if (row <= r_end - 1 + R)
+        load_row<kAligned>(plane, sh, row, H, W, col0, lane, panel_col0, ring[q], hring[q]);
+      else {
+        ring[q] = make_float4(ninf, ninf, ninf, ninf);
+        hring[q] = make_float2(ninf, ninf);
+      }
+    }
+
+    for (int t0 = 0; t0 < nrows; t0 += kRing) {
+#pragma unroll
+      for (int j = 0; j < kRing; ++j) {
+        const int t = t0 + j;
+        if (t < nrows) {  // warp-uniform
+          {  // prefetch the row that enters the ring kRing-1 steps ahead
+            const int row = r_begin - R + t + (kRing - 1);
+            const int slot = (j + kRing - 1) % kRing;
+            if (row <= r_end - 1 + R)
+              load_row<kAligned>(plane, sh, row, H, W, col0, lane, panel_col0, ring[slot], hring[slot]);
+            else {
+              ring[slot] = make_float4(ninf, ninf, ninf, ninf);
+              hring[slot] = make_float2(ninf, ninf);
+            }
+          }
+          const float4 ctr = ring[(j + R) % kRing];
+          const float m4 = fmaxf(fmaxf(ctr.x, ctr.y), fmaxf(ctr.z, ctr.w));
+          if (__any_sync(0xffffffffu, fminf(m4, satx) > floorx)) {
+            const int row = r_begin + t;
+            u32 ekey[4] = {0, 0, 0, 0};
+            if (!p.pre_activated) {
+              // vertical (2R+1)-max of own columns and of the halo pair
+              float4 v = ring[j % kRing];
+              float2 hvv = hring[j % kRing];
+#pragma unroll
+              for (int d = 1; d <= 2 * R; ++d) {
+                const float4 o = ring[(j + d) % kRing];
+                const float2 ho = hring[(j + d) % kRing];
+                v.x = fmaxf(v.x, o.x); v.y = fmaxf(v.y, o.y); v.z = fmaxf(v.z, o.z); v.w = fmaxf(v.w, o.w);
+                hvv.x = fmaxf(hvv.x, ho.x); hvv.y = fmaxf(hvv.y, ho.y);
+              }
+              float L2 = __shfl_up_sync(0xffffffffu, v.z, 1);
+              float L3 = __shfl_up_sync(0xffffffffu, v.w, 1);
+              float R0 = __shfl_down_sync(0xffffffffu, v.x, 1);
+              float R1 = __shfl_down_sync(0xffffffffu, v.y, 1);
+              if (lane == 0) { L2 = hvv.x; L3 = hvv.y; }
+              if (lane == 31) { R0 = hvv.x; R1 = hvv.y; }
+              float hmax[4];
+              if (R == 2) {
+                const float m12 = fmaxf(v.y, v.z);
+                hmax[0] = max3(fmaxf(L2, L3), v.x, m12);
+                hmax[1] = max3(fmaxf(L3, v.x), m12, v.w);
+                hmax[2] = max3(fmaxf(v.x, R0), m12, v.w);
+                hmax[3] = max3(fmaxf(R0, R1), m12, v.w);
+              } else {
+                hmax[0] = max3(L3, v.x, v.y);
+                hmax[1] = max3(v.x, v.y, v.z);
+                hmax[2] = max3(v.y, v.z, v.w);
+                hmax[3] = max3(v.z, v.w, R0);
+              }
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) {
+                const float x = comp(ctr, jj);
+                const float h = hmax[jj];
+                const bool inside = col0 + jj < W;
+                const bool near = (x >= h - kNearTie) || (h > kHiZone && x > kHiZone - 1.0f) || (h < kLoZone);
+                if (inside && fminf(x, satx) > floorx && near) {
+                  const float sx = activate(x);
+                  const bool peak = (x == h) || (sx == activate(h));
+                  if (peak) ekey[jj] = __float_as_uint(sx);
+                }
+              }
+            } else {
+              // pre-activated maps (CoreMLDecoder): every pixel is a candidate with its own value.
+              // Values are scores in [0, 1]; the order-preserving key below also handles negatives.
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) {
+                const float x = comp(ctr, jj);
+                if (col0 + jj < W && x > floorx) {
+                  const u32 bits = __float_as_uint(x);
+                  ekey[jj] = (bits & 0x80000000u) ? ~bits : (bits | 0x80000000u);
+                }
+              }
+            }
+            const u32 m0 = __ballot_sync(0xffffffffu, ekey[0] != 0);
+            const u32 m1 = __ballot_sync(0xffffffffu, ekey[1] != 0);
+            const u32 m2 = __ballot_sync(0xffffffffu, ekey[2] != 0);
+            const u32 m3 = __ballot_sync(0xffffffffu, ekey[3] != 0);
+            const u32 total = __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
+            if (total) {  // warp-uniform
+              int base = 0;
+              if (lane == 0) base = atomicAdd(count_ptr, (int)total);
+              base = __shfl_sync(0xffffffffu, base, 0);
+              const u32 lt = (1u << lane) - 1u;
+              // lane-major order inside the row: position = records of lower lanes + own earlier columns
+              int pos = base + __popc(m0 & lt) + __popc(m1 & lt) + __popc(m2 & lt) + __popc(m3 & lt);
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) {
+                if (ekey[jj]) {
+                  const u32 idx = (u32)(row * W + col0 + jj);
+                  if (pos < p.cap) list[pos] = ((u64)ekey[jj] << 32) | idx;
+                  ++pos;
+                  // clamped logit: the score is a monotone function of it, saturation included
+                  const float xe = fminf(fmaxf(comp(ctr, jj) * xscale, -satx), satx);
+                  const int bin = logit_bin(xe);
+                  atomicAdd(&hist[bin], 1u);
+                  atomicMin(&minx[bin], ord_of(xe));
+                }
+              }
+              emitted += total;
+              if (emitted >= (u32)K) {
+                __syncwarp();
+                // xscale is a power of two, so the division is exact
+                floorx = fmaxf(floorx, floor_value(hist, minx, lane, K) / xscale);
+              }
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// exact-select kernel: bounded-memory fallback for planes whose candidate list overflowed
+// (or for every plane under SDNET_FLAG_EXACT_SELECT).  One CTA per plane: a 3-level radix
+// select (11/11/10 bits) over the NMS'd scores recomputed straight from the heat map, then an
+// index-ordered emission pass that keeps every score above the K-th and the lowest-index
+// members of the K-th score's tie run.  Rewrites the plane's list with <= K records.
+// ---------------------------------------------------------------------------------------------
+constexpr int kExactThreads = 512;
+
+struct ExactParams {
+  View4 anchor, part;
+  int B, M, N, H, W, K, P;
+  int radius, cap, force, pre_activated;
+  u64* lists;
+  int* counts;
+  int* flags;
+};
+
+__device__ __forceinline__ u32 exact_key(const float* __restrict__ plane, long long sh, int H, int W, int R, int y,
+                                         int x, bool pre) {
+  const float v = __ldg(plane + (long long)y * sh + x);
+  if (pre) {
+    const u32 bits = __float_as_uint(v);
+    return (bits & 0x80000000u) ? ~bits : (bits | 0x80000000u);
+  }
+  float h = v;
+  for (int dy = -R; dy <= R; ++dy) {
+    const int yy = y + dy;
+    if (yy < 0 || yy >= H) continue;
+    const float* rp = plane + (long long)yy * sh;
+    for (int dx = -R; dx <= R; ++dx) {
+      const int xx = x + dx;
+      if (xx >= 0 && xx < W) h = fmaxf(h, __ldg(rp + xx));
+    }
+  }
+  const float sv = activate(v);
+  const bool peak = (v == h) || (sv == activate(h));
+  return peak ? __float_as_uint(sv) : 0u;
+}
+
+// digit (from the top) at which the cumulative count reaches `need`; bins = 2048
+__device__ void pick_digit(const u32* s_hist, int nbins, int need, int* s_out) {
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    const int per = nbins / 32;
+    u32 s = 0;
+    for (int q = 0; q < per; ++q) s += s_hist[lane * per + q];
+    u32 suf = s;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      u32 t = __shfl_down_sync(0xffffffffu, suf, d);
+      if (lane + d < 32) suf += t;
+    }
+    const u32 mask = __ballot_sync(0xffffffffu, suf >= (u32)need);
+    if (mask == 0) {
+      if (lane == 0) { s_out[0] = -1; s_out[1] = 0; }
+    } else {
+      const int L = 31 - __clz(mask);
+      if (lane == L) {
+        u32 above = suf - s;
+        int dsel = L * per;
+        for (int q = per - 1; q >= 0; --q) {
+          const u32 cq = s_hist[L * per + q];
+          if (above + cq >= (u32)need) { dsel = L * per + q; break; }
+          above += cq;
+        }
+        s_out[0] = dsel;
+        s_out[1] = (int)above;
+      }
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kExactThreads) sdnet_exact_select_kernel(const __grid_constant__ ExactParams p) {
+  __shared__ u32 s_hist[2048];
+  __shared__ int s_out[2];
+  __shared__ int s_warp[kExactThreads / 32][2];
+  __shared__ int s_base[2];
+  const int C = p.M + p.N;
+  const int plane_id = blockIdx.x;
+  const int emitted = p.counts[plane_id];
+  if (!p.force && emitted <= p.cap) return;
+  const int b = plane_id / C, c = plane_id % C;
+  const bool is_anchor = c < p.M;
+  const View4& vw = is_anchor ? p.anchor : p.part;
+  const float* __restrict__ plane = vw.data + (long long)b * vw.sb + (long long)(is_anchor ? c : c - p.M) * vw.sc;
+  const long long sh = vw.sh;
+  const int K = is_anchor ? p.K : p.P;
+  const int H = p.H, W = p.W, HW = H * W, R = p.radius;
+  const bool pre = p.pre_activated != 0;
+  const int tid = threadIdx.x;
+  u64* list = p.lists + (size_t)plane_id * p.cap;
+  // per-pixel key cache lives behind the K output records of this plane's list region
+  // (cap*8 bytes >= K*8 + H*W/8*... see plan_workspace): 1 bit per pixel "survives NMS".
+  u32* bitmap = reinterpret_cast<u32*>(list + K + 2);
+  const int words = (HW + 31) / 32;
+
+  // level 1 (top 11 bits) + NMS bitmap
+  for (int i = tid; i < 2048; i += blockDim.x) s_hist[i] = 0;
+  __syncthreads();
+  for (int base = 0; base < words * 32; base += blockDim.x) {
+    const int i = base + tid;
+    u32 key = 0;
+    if (i < HW) key = exact_key(plane, sh, H, W, R, i / W, i % W, pre);
+    const u32 m = __ballot_sync(0xffffffffu, key != 0);
+    if ((tid & 31) == 0 && (i >> 5) < words) bitmap[i >> 5] = m;
+    if (key) atomicAdd(&s_hist[key >> 21], 1u);
+  }
+  __syncthreads();
+  u32 prefix = 0;
+  int need = K;
+  bool all = false;
+  pick_digit(s_hist, 2048, need, s_out);
+  if (s_out[0] < 0) all = true;  // fewer than K survivors: keep them all
+  u32 thresh = 0;
+  if (!all) {
+    need -= s_out[1];
+    prefix = (u32)s_out[0];
+    __syncthreads();
+    // level 2 (next 11 bits)
+    for (int i = tid; i < 2048; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < HW; i += blockDim.x) {
+      if (!((bitmap[i >> 5] >> (i & 31)) & 1u)) continue;
+      const float v = __ldg(plane + (long long)(i / W) * sh + (i % W));
+      const u32 key = pre ? ((__float_as_uint(v) & 0x80000000u) ? ~__float_as_uint(v) : (__float_as_uint(v) | 0x80000000u))
+                          : __float_as_uint(activate(v));
+      if ((key >> 21) == prefix) atomicAdd(&s_hist[(key >> 10) & 0x7ffu], 1u);
+    }
+    __syncthreads();
+    pick_digit(s_hist, 2048, need, s_out);
+    need -= s_out[1];
+    prefix = (prefix << 11) | (u32)s_out[0];
+    __syncthreads();
+    // level 3 (last 10 bits)
+    for (int i = tid; i < 1024; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < HW; i += blockDim.x) {
+      if (!((bitmap[i >> 5] >> (i & 31)) & 1u)) continue;
+      const float v = __ldg(plane + (long long)(i / W) * sh + (i % W));
+      const u32 key = pre ? ((__float_as_uint(v) & 0x80000000u) ? ~__float_as_uint(v) : (__float_as_uint(v) | 0x80000000u))
+                          : __float_as_uint(activate(v));
+      if ((key >> 10) == prefix) atomicAdd(&s_hist[key & 0x3ffu], 1u);
+    }
+    __syncthreads();
+    pick_digit(s_hist, 1024, need, s_out);
+    need -= s_out[1];  // members of the K-th score's tie run still to take, lowest index first
+    thresh = (prefix << 10) | (u32)s_out[0];
+    __syncthreads();
+  }
+  // ordered emission
+  if (tid < 2) s_base[tid] = 0;  // [0] scores above the threshold so far, [1] tie-run members so far
+  __syncthreads();
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int base = 0; base < HW; base += blockDim.x) {
+    const int i = base + tid;
+    u32 key = 0;
+    if (i < HW && ((bitmap[i >> 5] >> (i & 31)) & 1u)) {
+      const float v = __ldg(plane + (long long)(i / W) * sh + (i % W));
+      key = pre ? ((__float_as_uint(v) & 0x80000000u) ? ~__float_as_uint(v) : (__float_as_uint(v) | 0x80000000u))
+                : __float_as_uint(activate(v));
+    }
+    const bool gt = key != 0 && (all || key > thresh);
+    const bool eq = key != 0 && !all && key == thresh;
+    const u32 mg = __ballot_sync(0xffffffffu, gt), me = __ballot_sync(0xffffffffu, eq);
+    if (lane == 0) { s_warp[warp][0] = __popc(mg); s_warp[warp][1] = __popc(me); }
+    __syncthreads();
+    int g_before = 0, e_before = 0;
+    for (int w = 0; w < warp; ++w) { g_before += s_warp[w][0]; e_before += s_warp[w][1]; }
+    const u32 lt = (1u << lane) - 1u;
+    const int e_rank = s_base[1] + e_before + __popc(me & lt);  // tie-run members with a lower index
+    const bool take_eq = eq && e_rank < need;
+    const int pos = s_base[0] + g_before + __popc(mg & lt) + min(e_rank, need);
+    if (gt || take_eq) list[pos] = ((u64)key << 32) | (u32)i;
+    __syncthreads();
+    if (tid == 0) {
+      int g = 0, e = 0;
+      for (int w = 0; w < kExactThreads / 32; ++w) { g += s_warp[w][0]; e += s_warp[w][1]; }
+      s_base[0] += g;  // scores above the threshold so far
+      s_base[1] += e;  // tie-run members so far
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    p.counts[plane_id] = s_base[0] + min(s_base[1], need);
+    p.flags[plane_id] = 1;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// tail kernel: select + sort + gather + group, one CTA per image
+// ---------------------------------------------------------------------------------------------
+struct TailParams {
+  View4 offsets, embeddings;
+  int B, M, N, H, W, K, P;
+  int cap;
+  int pre_activated, no_grouping;
+  float conf, dist_abs;
+  const u64* lists;
+  const int* counts;
+  float* anchor_out;
+  float* part_out;
+  long long* anchor_inds;
+  long long* part_inds;
+  float* part_emb;
+  int* assign;
+  int* out_counts;
+  int* diag;
+  const int* exact_flags;  // [planes] 1 if the exact select rewrote the list
+};
+
+__device__ __forceinline__ u64 make_comp(u64 rec, int c_local) {
+  // rec = key:32 | idx:32  ->  key:32 | (255-c):8 | (0xFFFFFF-idx):24 ; larger = earlier in the output
+  const u32 key = (u32)(rec >> 32);
+  const u32 idx = (u32)rec;
+  return ((u64)key << 32) | ((u64)(255u - (u32)c_local) << 24) | (u64)(0xFFFFFFu - idx);
+}
+
+__device__ void bitonic_sort_desc(u64* s, int n /* power of two */) {
+  for (int k = 2; k <= n; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const u64 a = s[i], b = s[ixj];
+          const bool desc = (i & k) == 0;
+          if (desc ? (a < b) : (a > b)) { s[i] = b; s[ixj] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// Select the `want` largest composites of planes [c0, c0+nc) of image b into s_sel (sorted
+// descending).  Returns the number selected (< want only when fewer candidates exist).
+__device__ int select_group(const TailParams& p, int b, int c0, int nc, int want, u64* s_sel, u32* s_hist,
+                            int* s_misc) {
+  const int C = p.M + p.N;
+  const int tid = threadIdx.x;
+  // total candidates
+  if (tid == 0) {
+    int tot = 0;
+    for (int c = 0; c < nc; ++c) tot += min(p.counts[(size_t)b * C + c0 + c], p.cap);
+    s_misc[0] = tot;
+    s_misc[1] = 0;  // collected
+  }
+  __syncthreads();
+  const int total = s_misc[0];
+  u64 prefix = 0;   // value of the top `bits` bits that boundary elements share
+  int bits = 0;
+  if (total > kSortN) {
+    int need = want;      // how many still have to come from the boundary bucket
+    int certain = 0;      // elements strictly above the boundary bucket
+    for (int level = 0; level < 8; ++level) {
+      const int shift = 56 - 8 * level;
+      for (int i = tid; i < 256; i += blockDim.x) s_hist[i] = 0;
+      __syncthreads();
+      for (int c = 0; c < nc; ++c) {
+        const int n = min(p.counts[(size_t)b * C + c0 + c], p.cap);
+        const u64* list = p.lists + ((size_t)b * C + c0 + c) * p.cap;
+        for (int i = tid; i < n; i += blockDim.x) {
+          const u64 v = make_comp(list[i], c);
+          if (bits == 0 || (v >> (64 - bits)) == prefix) atomicAdd(&s_hist[(u32)(v >> shift) & 0xffu], 1u);
+        }
+      }
+      __syncthreads();
+      if (tid < 32) {
+        // lane l owns digits 8l..8l+7; suffix-scan from the top
+        u32 loc[8], s = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { loc[q] = s_hist[8 * tid + q]; s += loc[q]; }
+        u32 suf = s;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          u32 t = __shfl_down_sync(0xffffffffu, suf, d);
+          if (tid + d < 32) suf += t;
+        }
+        const u32 mask = __ballot_sync(0xffffffffu, suf >= (u32)need);
+        const int L = 31 - __clz(mask);  // mask != 0 because the bucket holds >= need elements
+        if (tid == L) {
+          u32 above = suf - s;
+          int dsel = 8 * L;
+          for (int q = 7; q >= 0; --q) {
+            if (above + loc[q] >= (u32)need) { dsel = 8 * L + q; break; }
+            above += loc[q];
+          }
+          s_misc[2] = dsel;
+          s_misc[3] = (int)above;                 // elements in this bucket with a larger digit
+          s_misc[4] = (int)s_hist[dsel];          // size of the new boundary bucket
+        }
+      }
+      __syncthreads();
+      const int dsel = s_misc[2], above = s_misc[3], binc = s_misc[4];
+      certain += above;
+      need -= above;
+      prefix = (prefix << 8) | (u64)dsel;
+      bits += 8;
+      __syncthreads();
+      if (certain + binc <= kSortN) break;  // everything at or above the boundary bucket fits the sorter
+    }
+  }
+  // collect: all elements whose top `bits` bits are >= prefix
+  for (int c = 0; c < nc; ++c) {
+    const int n = min(p.counts[(size_t)b * C + c0 + c], p.cap);
+    const u64* list = p.lists + ((size_t)b * C + c0 + c) * p.cap;
+    for (int i = tid; i < n; i += blockDim.x) {
+      const u64 v = make_comp(list[i], c);
+      if (bits == 0 || (v >> (64 - bits)) >= prefix) {
+        const int slot = atomicAdd(&s_misc[1], 1);
+        if (slot < kSortN) s_sel[slot] = v;
+      }
+    }
+  }
+  __syncthreads();
+  const int got = min(s_misc[1], kSortN);
+  int n2 = 32;
+  while (n2 < got) n2 <<= 1;
+  for (int i = got + tid; i < n2; i += blockDim.x) s_sel[i] = 0;
+  __syncthreads();
+  bitonic_sort_desc(s_sel, n2);
+  return min(got, want);
+}
+
+// Slots [have, want) of a group are the zero-valued entries torch.topk pads with: under
+// (value desc, index asc) they are the lowest-index pixels of the group's first plane that
+// did not survive NMS.  All of them lie below index `want`.
+__device__ void zero_fill(const TailParams& p, int b, int c0, int have, int want, u64* s_sel, u32* s_bits) {
+  const int C = p.M + p.N;
+  const int tid = threadIdx.x;
+  const int words = (want + 31) / 32;
+  for (int i = tid; i < words; i += blockDim.x) s_bits[i] = 0;
+  __syncthreads();
+  const int n = min(p.counts[(size_t)b * C + c0], p.cap);
+  const u64* list = p.lists + ((size_t)b * C + c0) * p.cap;
+  for (int i = tid; i < n; i += blockDim.x) {
+    const u32 idx = (u32)list[i];
+    if (idx < (u32)want) atomicOr(&s_bits[idx >> 5], 1u << (idx & 31));
+  }
+  __syncthreads();
+  for (int s = have + tid; s < want; s += blockDim.x) {
+    int rank = s - have;  // rank-th non-peak index
+    int w = 0;
+    for (; w < words; ++w) {
+      const int z = 32 - __popc(s_bits[w]);
+      if (rank < z) break;
+      rank -= z;
+    }
+    const u32 free_mask = ~s_bits[w];
+    const u32 bit = __fns(free_mask, 0, rank + 1);
+    const u32 idx = (u32)(w * 32) + bit;
+    // key 0 (score 0.0), class 0
+    s_sel[s] = ((u64)255u << 24) | (u64)(0xFFFFFFu - idx);
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kTailThreads) sdnet_tail_kernel(const __grid_constant__ TailParams p) {
+  __shared__ u64 s_sel[kSortN];
+  __shared__ u32 s_hist[256];
+  __shared__ int s_misc[8];
+  __shared__ float s_ax[SDNET_MAX_TOPK], s_ay[SDNET_MAX_TOPK];
+  __shared__ int s_cnt[2];
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int W = p.W;
+  if (tid < 2) s_cnt[tid] = 0;
+
+  // ---- anchors
+  int have = select_group(p, b, 0, p.M, p.K, s_sel, s_hist, s_misc);
+  if (have < p.K) zero_fill(p, b, 0, have, p.K, s_sel, s_hist);
+  const float* offx = p.offsets.data + (long long)b * p.offsets.sb;
+  const float* offy = offx + p.offsets.sc;
+  const long long osh = p.offsets.sh;
+  int n_valid = 0;
+  for (int s = tid; s < p.K; s += blockDim.x) {
+    const u64 v = s_sel[s];
+    u32 key = (u32)(v >> 32);
+    const int cls = 255 - (int)((v >> 24) & 0xffu);
+    const u32 idx = 0xFFFFFFu - (u32)(v & 0xFFFFFFu);
+    const int yy = idx / W, xx = idx - yy * W;
+    float score;
+    if (p.pre_activated) {
+      u32 bits = (key == 0) ? 0u : ((key & 0x80000000u) ? (key & 0x7fffffffu) : ~key);
+      score = __uint_as_float(bits);
+    } else {
+      score = __uint_as_float(key);
+    }
+    const float x = __fadd_rn((float)xx, __ldg(offx + (long long)yy * osh + xx));
+    const float y = __fadd_rn((float)yy, __ldg(offy + (long long)yy * osh + xx));
+    reinterpret_cast<float4*>(p.anchor_out)[(size_t)b * p.K + s] = make_float4(x, y, score, (float)cls);
+    p.anchor_inds[(size_t)b * p.K + s] = (long long)idx;
+    const bool valid = score > p.conf;
+    s_ax[s] = valid ? x : kFar;
+    s_ay[s] = valid ? y : kFar;
+    n_valid += valid ? 1 : 0;
+  }
+  if (n_valid) atomicAdd(&s_cnt[0], n_valid);
+  __syncthreads();
+
+  // ---- parts
+  have = select_group(p, b, p.M, p.N, p.P, s_sel, s_hist, s_misc);
+  if (have < p.P) zero_fill(p, b, p.M, have, p.P, s_sel, s_hist);
+  const float* embx = p.embeddings.data ? p.embeddings.data + (long long)b * p.embeddings.sb : nullptr;
+  const float* emby = embx ? embx + p.embeddings.sc : nullptr;
+  const long long esh = p.embeddings.sh;
+  n_valid = 0;
+  for (int s = tid; s < p.P; s += blockDim.x) {
+    const u64 v = s_sel[s];
+    u32 key = (u32)(v >> 32);
+    const int cls = 255 - (int)((v >> 24) & 0xffu);
+    const u32 idx = 0xFFFFFFu - (u32)(v & 0xFFFFFFu);
+    const int yy = idx / W, xx = idx - yy * W;
+    float score;
+    if (p.pre_activated) {
+      u32 bits = (key == 0) ? 0u : ((key & 0x80000000u) ? (key & 0x7fffffffu) : ~key);
+      score = __uint_as_float(bits);
+    } else {
+      score = __uint_as_float(key);
+    }
+    const float x = __fadd_rn((float)xx, __ldg(offx + (long long)yy * osh + xx));
+    const float y = __fadd_rn((float)yy, __ldg(offy + (long long)yy * osh + xx));
+    float ex = 0.f, ey = 0.f;
+    if (embx) {
+      ex = __ldg(embx + (long long)yy * esh + xx);
+      ey = __ldg(emby + (long long)yy * esh + xx);
+    }
+    const float ox = __fadd_rn(x, ex), oy = __fadd_rn(y, ey);
+    float2* po = reinterpret_cast<float2*>(p.part_out + ((size_t)b * p.P + s) * 6);
+    po[0] = make_float2(x, y);
+    po[1] = make_float2(score, (float)cls);
+    po[2] = make_float2(ox, oy);
+    p.part_inds[(size_t)b * p.P + s] = (long long)idx;
+    if (p.part_emb) reinterpret_cast<float2*>(p.part_emb)[(size_t)b * p.P + s] = make_float2(ex, ey);
+    const bool valid = score > p.conf;
+    n_valid += valid ? 1 : 0;
+    int slot = -1;
+    if (!p.no_grouping) {
+      // masked parts sit at (-1e6, -1e6), masked anchors at (+1e6, +1e6): decoders.py:80-86
+      const float qx = valid ? ox : -kFar, qy = valid ? oy : -kFar;
+      float best = CUDART_INF_F;
+      int arg = 0;
+      for (int a = 0; a < p.K; ++a) {
+        const float dx = __fsub_rn(qx, s_ax[a]), dy = __fsub_rn(qy, s_ay[a]);
+        const float d = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+        if (d < best) { best = d; arg = a; }
+      }
+      slot = (best < p.dist_abs) ? arg : -1;
+    }
+    p.assign[(size_t)b * p.P + s] = slot;
+  }
+  if (n_valid) atomicAdd(&s_cnt[1], n_valid);
+  __syncthreads();
+  if (tid < 2) p.out_counts[(size_t)b * 2 + tid] = s_cnt[tid];
+  if (p.diag) {
+    const int C = p.M + p.N;
+    for (int c = tid; c < C; c += blockDim.x) {
+      p.diag[((size_t)b * C + c) * 2 + 0] = p.counts[(size_t)b * C + c];
+      p.diag[((size_t)b * C + c) * 2 + 1] = p.exact_flags[(size_t)b * C + c];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// metadata: clamped-sigmoid maps
+// ---------------------------------------------------------------------------------------------
+__global__ void sdnet_activate_kernel(View4 in, int C, int H, int W, size_t total, float* __restrict__ out) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W);
+    size_t t = i / W;
+    const int y = (int)(t % H);
+    t /= H;
+    const int c = (int)(t % C);
+    const long long b = (long long)(t / C);
+    out[i] = activate(__ldg(in.data + b * in.sb + (long long)c * in.sc + (long long)y * in.sh + x));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+struct Workspace {
+  size_t off_counts, off_flags, off_sched, off_lists, total;
+  int cap;
+};
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+Workspace plan_workspace(int B, int M, int N, int H, int W, int K, int P) {
+  Workspace ws;
+  const size_t planes = (size_t)B * (M + N);
+  const int kmax = K > P ? K : P;
+  ws.cap = (int)((size_t)H * W / 8 + 2 * (size_t)kmax + 1024);
+  size_t off = 0;
+  ws.off_counts = off; off = align_up(off + planes * sizeof(int), 256);
+  ws.off_flags = off;  off = align_up(off + planes * sizeof(int), 256);
+  ws.off_sched = off;  off = align_up(off + 64, 256);
+  ws.off_lists = off;  off = align_up(off + planes * (size_t)ws.cap * sizeof(u64), 256);
+  ws.total = off;
+  return ws;
+}
+
+int device_sm_count() {
+  static int cached = 0;
+  if (cached) return cached;
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) return 148;
+  cached = sms;
+  return sms;
+}
+
+int validate(const SdnetDecodeParams* p) {
+  if (!p) return SDNET_E_NULL;
+  if (p->struct_size != sizeof(SdnetDecodeParams)) return SDNET_E_STRUCT;
+  if (p->dtype != SDNET_DTYPE_F32) return SDNET_E_DTYPE;
+  if (p->B <= 0 || p->M <= 0 || p->N <= 0 || p->H <= 0 || p->W <= 0 || p->K <= 0 || p->P <= 0) return SDNET_E_SHAPE;
+  const long long hw = (long long)p->H * p->W;
+  if (hw >= (1ll << 24) || p->K > hw || p->P > hw) return SDNET_E_SHAPE;
+  if (p->K > SDNET_MAX_TOPK || p->P > SDNET_MAX_TOPK || p->M + p->N > SDNET_MAX_CHANNELS) return SDNET_E_SHAPE;
+  if (p->radius != 1 && p->radius != 2) return SDNET_E_RADIUS;
+  const bool no_group = (p->flags & SDNET_FLAG_NO_GROUPING) != 0;
+  if (!p->anchor_hm.data || !p->part_hm.data || !p->offsets.data || (!no_group && !p->embeddings.data)) return SDNET_E_NULL;
+  if (!p->anchor_out || !p->part_out || !p->anchor_inds || !p->part_inds || !p->assign || !p->counts) return SDNET_E_NULL;
+  if (p->anchor_hm.stride_w != 1 || p->part_hm.stride_w != 1 || p->offsets.stride_w != 1 ||
+      (p->embeddings.data && p->embeddings.stride_w != 1))
+    return SDNET_E_STRIDE;
+  const Workspace ws = plan_workspace(p->B, p->M, p->N, p->H, p->W, p->K, p->P);
+  if (!p->workspace || ((uintptr_t)p->workspace & 255) || p->workspace_bytes < ws.total) return SDNET_E_WORKSPACE;
+  return 0;
+}
+
+View4 to_view(const SdnetTensor4& t) {
+  View4 v;
+  v.data = static_cast<const float*>(t.data);
+  v.sb = t.stride_b; v.sc = t.stride_c; v.sh = t.stride_h;
+  return v;
+}
+
+bool view_aligned(const SdnetTensor4& t, int W) {
+  return ((uintptr_t)t.data % 16 == 0) && (t.stride_b % 4 == 0) && (t.stride_c % 4 == 0) && (t.stride_h % 4 == 0) &&
+         (W % 4 == 0);
+}
+
+int launch_decode(const SdnetDecodeParams* p, cudaStream_t stream) {
+  const Workspace ws = plan_workspace(p->B, p->M, p->N, p->H, p->W, p->K, p->P);
+  char* base = static_cast<char*>(p->workspace);
+  const int C = p->M + p->N;
+  const size_t planes = (size_t)p->B * C;
+  cudaError_t err = cudaMemsetAsync(base, 0, ws.off_lists, stream);
+  if (err != cudaSuccess) return (int)err;
+
+  PeaksParams pp;
+  pp.anchor = to_view(p->anchor_hm);
+  pp.part = to_view(p->part_hm);
+  pp.B = p->B; pp.M = p->M; pp.N = p->N; pp.H = p->H; pp.W = p->W; pp.K = p->K; pp.P = p->P;
+  pp.panels = (p->W + kPanelW - 1) / kPanelW;
+  const int sms = device_sm_count();
+  const int resident_warps = sms * 3 * kWarps;
+  // enough units for ~4 waves of resident warps, but strips of at least 32 rows
+  long long want_units = 4ll * resident_warps;
+  long long per_strip1 = (long long)planes * pp.panels;
+  int strips = (int)((want_units + per_strip1 - 1) / per_strip1);
+  const int max_strips = (p->H + 31) / 32;
+  if (strips > max_strips) strips = max_strips;
+  if (strips < 1) strips = 1;
+  pp.rows_per_strip = (p->H + strips - 1) / strips;
+  pp.strips = (p->H + pp.rows_per_strip - 1) / pp.rows_per_strip;
+  pp.units = (int)(planes * pp.strips * pp.panels);
+  pp.cap = ws.cap;
+  pp.pre_activated = (p->flags & SDNET_FLAG_PRE_ACTIVATED) ? 1 : 0;
+  pp.lists = reinterpret_cast<u64*>(base + ws.off_lists);
+  pp.counts = reinterpret_cast<int*>(base + ws.off_counts);
+  pp.sched = reinterpret_cast<u32*>(base + ws.off_sched);
+  const bool aligned = view_aligned(p->anchor_hm, p->W) && view_aligned(p->part_hm, p->W);
+  long long ctas = ((long long)pp.units + kWarps - 1) / kWarps;
+  if (ctas > (long long)sms * 3) ctas = (long long)sms * 3;
+  dim3 grid((unsigned)ctas), block(kThreads);
+  if (p->radius == 2) {
+    if (aligned) sdnet_peaks_kernel<true, 2><<<grid, block, 0, stream>>>(pp);
+    else sdnet_peaks_kernel<false, 2><<<grid, block, 0, stream>>>(pp);
+  } else {
+    if (aligned) sdnet_peaks_kernel<true, 1><<<grid, block, 0, stream>>>(pp);
+    else sdnet_peaks_kernel<false, 1><<<grid, block, 0, stream>>>(pp);
+  }
+  err = cudaGetLastError();
+  if (err != cudaSuccess) return (int)err;
+
+  {
+    ExactParams ep;
+    ep.anchor = pp.anchor; ep.part = pp.part;
+    ep.B = p->B; ep.M = p->M; ep.N = p->N; ep.H = p->H; ep.W = p->W; ep.K = p->K; ep.P = p->P;
+    ep.radius = p->radius; ep.cap = ws.cap;
+    ep.force = (p->flags & SDNET_FLAG_EXACT_SELECT) ? 1 : 0;
+    ep.pre_activated = pp.pre_activated;
+    ep.lists = pp.lists; ep.counts = pp.counts;
+    ep.flags = reinterpret_cast<int*>(base + ws.off_flags);
+    sdnet_exact_select_kernel<<<dim3((unsigned)planes), dim3(kExactThreads), 0, stream>>>(ep);
+    err = cudaGetLastError();
+    if (err != cudaSuccess) return (int)err;
+  }
+
+  TailParams tp;
+  tp.offsets = to_view(p->offsets);
+  tp.embeddings = to_view(p->embeddings);
+  tp.B = p->B; tp.M = p->M; tp.N = p->N; tp.H = p->H; tp.W = p->W; tp.K = p->K; tp.P = p->P;
+  tp.cap = ws.cap;
+  tp.pre_activated = pp.pre_activated;
+  tp.no_grouping = (p->flags & SDNET_FLAG_NO_GROUPING) ? 1 : 0;
+  tp.conf = p->conf_f32;
+  tp.dist_abs = p->dist_abs_f32;
+  tp.lists = pp.lists;
+  tp.counts = pp.counts;
+  tp.anchor_out = p->anchor_out;
+  tp.part_out = p->part_out;
+  tp.anchor_inds = reinterpret_cast<long long*>(p->anchor_inds);
+  tp.part_inds = reinterpret_cast<long long*>(p->part_inds);
+  tp.part_emb = p->part_emb;
+  tp.assign = p->assign;
+  tp.out_counts = p->counts;
+  tp.diag = p->diag;
+  tp.exact_flags = reinterpret_cast<const int*>(base + ws.off_flags);
+  sdnet_tail_kernel<<<dim3((unsigned)p->B), dim3(kTailThreads), 0, stream>>>(tp);
+  err = cudaGetLastError();
+  return (int)err;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sdnet_abi_version(void) { return SDNET_ABI_VERSION; }
+
+const char* sdnet_error_string(int code) {
+  switch (code) {
+    case 0: return "ok";
+    case SDNET_E_NULL: return "a required pointer is NULL";
+    case SDNET_E_SHAPE: return "bad shape (non-positive dim, H*W >= 2^24, k out of range, or above SDNET_MAX_*)";
+    case SDNET_E_STRIDE: return "innermost stride must be 1";
+    case SDNET_E_DTYPE: return "unsupported dtype";
+    case SDNET_E_WORKSPACE: return "workspace missing, misaligned or too small";
+    case SDNET_E_RADIUS: return "unsupported NMS radius";
+    case SDNET_E_STRUCT: return "SdnetDecodeParams.struct_size mismatch";
+    default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown error";
+  }
+}
+
+int sdnet_decode_workspace_bytes(int B, int M, int N, int H, int W, int K, int P, int dtype, size_t* out_bytes) {
+  if (!out_bytes) return SDNET_E_NULL;
+  if (dtype != SDNET_DTYPE_F32) return SDNET_E_DTYPE;
+  if (B <= 0 || M <= 0 || N <= 0 || H <= 0 || W <= 0 || K <= 0 || P <= 0) return SDNET_E_SHAPE;
+  if ((long long)H * W >= (1ll << 24)) return SDNET_E_SHAPE;
+  *out_bytes = plan_workspace(B, M, N, H, W, K, P).total;
+  return 0;
+}
+
+int sdnet_decode_launch(const SdnetDecodeParams* params, void* stream) {
+  const int rc = validate(params);
+  if (rc) return rc;
+  return launch_decode(params, static_cast<cudaStream_t>(stream));
+}
+
+int sdnet_activate_launch(const SdnetTensor4* in, int dtype, int B, int C, int H, int W, float* out, void* stream) {
+  if (!in || !in->data || !out) return SDNET_E_NULL;
+  if (dtype != SDNET_DTYPE_F32) return SDNET_E_DTYPE;
+  if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return SDNET_E_SHAPE;
+  if (in->stride_w != 1) return SDNET_E_STRIDE;
+  const size_t total = (size_t)B * C * H * W;
+  const int sms = device_sm_count();
+  size_t blocks = (total + 255) / 256;
+  if (blocks > (size_t)sms * 8) blocks = (size_t)sms * 8;
+  sdnet_activate_kernel<<<dim3((unsigned)blocks), dim3(256), 0, static_cast<cudaStream_t>(stream)>>>(
+      to_view(*in), C, H, W, total, out);
+  return (int)cudaGetLastError();
+}
+
+int sdnet_decode_host_launch(const SdnetDecodeParams* params, void* staging, size_t staging_bytes, void* stream_v) {
+  const int rc = validate(params);
+  if (rc) return rc;
+  if (!staging) return SDNET_E_NULL;
+  const SdnetDecodeParams& p = *params;
+  const size_t plane_bytes = (size_t)p.H * p.W * sizeof(float);
+  const size_t need = (size_t)p.B * (p.M + p.N) * plane_bytes;
+  if (staging_bytes < need || ((uintptr_t)staging & 255)) return SDNET_E_WORKSPACE;
+  if (p.anchor_hm.stride_h != p.W || p.part_hm.stride_h != p.W) return SDNET_E_STRIDE;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  // heat planes: host (strided per image) -> dense device staging [B][M+N][H][W]
+  char* dst = static_cast<char*>(staging);
+  const size_t img_bytes = (size_t)(p.M + p.N) * plane_bytes;
+  cudaError_t err;
+  if (p.anchor_hm.stride_c == (long long)p.H * p.W) {
+    err = cudaMemcpy2DAsync(dst, img_bytes, p.anchor_hm.data, (size_t)p.anchor_hm.stride_b * sizeof(float),
+                            (size_t)p.M * plane_bytes, p.B, cudaMemcpyHostToDevice, stream);
+  } else {
+    err = cudaErrorInvalidValue;
+  }
+  if (err != cudaSuccess) return (int)err;
+  if (p.part_hm.stride_c == (long long)p.H * p.W || p.N == 1) {
+    err = cudaMemcpy2DAsync(dst + (size_t)p.M * plane_bytes, img_bytes, p.part_hm.data,
+                            (size_t)p.part_hm.stride_b * sizeof(float), (size_t)p.N * plane_bytes, p.B,
+                            cudaMemcpyHostToDevice, stream);
+  } else {
+    err = cudaErrorInvalidValue;
+  }
+  if (err != cudaSuccess) return (int)err;
+  SdnetDecodeParams q = p;
+  q.anchor_hm.data = dst;
+  q.anchor_hm.stride_b = (long long)(p.M + p.N) * p.H * p.W;
+  q.anchor_hm.stride_c = (long long)p.H * p.W;
+  q.part_hm.data = dst + (size_t)p.M * plane_bytes;
+  q.part_hm.stride_b = q.anchor_hm.stride_b;
+  q.part_hm.stride_c = q.anchor_hm.stride_c;
+  // offsets / embeddings stay in pinned host memory: the tail kernel reads them through
+  // the unified address space only at the K + 2P selected pixels per image.
+  return launch_decode(&q, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,226 @@
+"""Host side of the decode op: torch tensors in, packed detection tensors out.
+
+``sdnet_b200::decode`` is a ``torch.library`` custom op whose implementation is one
+ctypes call into the ``extern "C"`` launcher ``sdnet_decode_launch`` on torch's current
+CUDA stream.  torch is used for device memory, streams and op registration only; all
+arithmetic happens in the hand-written sm_100a kernels.  There is no CPU or eager
+fallback: CPU tensors are rejected and a missing library raises at first use.
+
+Replaces (reference): src/sdnet/data/decoders.py:44-100 and the helpers it calls in
+src/sdnet/utils/utils.py:342-361,422-467.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+
+import torch
+
+from . import _native
+from ._native import FLAG_EXACT_SELECT, FLAG_NO_GROUPING, FLAG_PRE_ACTIVATED, SdnetDecodeParams, SdnetTensor4
+
+__all__ = ["decode_packed", "activate_maps", "DecodePlan", "PackedDetections", "gpu_launches_per_decode"]
+
+# kernels launched by one sdnet_decode_launch: peaks, exact-select, tail (+ one memset node)
+_KERNELS_PER_DECODE = 3
+
+
+def gpu_launches_per_decode() -> int:
+    return _KERNELS_PER_DECODE
+
+
+def _view4(t: torch.Tensor) -> SdnetTensor4:
+    sb, sc, sh, sw = t.stride()
+    return SdnetTensor4(t.data_ptr(), sb, sc, sh, sw)
+
+
+def _require_cuda_f32(name: str, t: torch.Tensor, allow_pinned_host: bool = False):
+    if t.dtype != torch.float32:
+        raise TypeError(
+            f"{name}: dtype {t.dtype} is not supported by the B200 decode path yet (fp32 only); "
+            "the reference computes the sigmoid in the input dtype, so a silent upcast would change results"
+        )
+    if t.dim() != 4:
+        raise ValueError(f"{name}: expected a (B, C, H, W) tensor, got shape {tuple(t.shape)}")
+    if not t.is_cuda and not (allow_pinned_host and t.is_pinned()):
+        raise RuntimeError(
+            f"{name} lives on {t.device}: the B200 decode path has no CPU fallback "
+            "(move the network outputs to a CUDA device)"
+        )
+
+
+@dataclass
+class PackedDetections:
+    """Device tensors produced by one decode (layouts: include/sdnet_decode.h)."""
+
+    anchor_out: torch.Tensor  # (B, K, 4) x, y, score, class
+    part_out: torch.Tensor  # (B, P, 6) x, y, score, kind, origin_x, origin_y
+    anchor_inds: torch.Tensor  # (B, K) int64
+    part_inds: torch.Tensor  # (B, P) int64
+    part_emb: torch.Tensor  # (B, P, 2)
+    assign: torch.Tensor  # (B, P) int32, -1 = not grouped
+    counts: torch.Tensor  # (B, 2) int32
+    diag: torch.Tensor  # (B*(M+N), 2) int32
+    blob: torch.Tensor | None = None  # the single allocation the fields above are views of
+
+    def as_dict(self) -> dict:
+        return {k: getattr(self, k) for k in
+                ("anchor_out", "part_out", "anchor_inds", "part_inds", "part_emb", "assign", "counts", "diag")}
+
+
+def _carve(blob: torch.Tensor, B: int, K: int, P: int, C: int) -> PackedDetections:
+    """Views of one uint8 allocation, 8-byte fields first so every view is aligned."""
+    off = 0
+
+    def take(nbytes, dtype, shape):
+        nonlocal off
+        view = blob[off : off + nbytes].view(dtype).view(shape)
+        off += (nbytes + 15) // 16 * 16
+        return view
+
+    a_inds = take(B * K * 8, torch.int64, (B, K))
+    p_inds = take(B * P * 8, torch.int64, (B, P))
+    a_out = take(B * K * 16, torch.float32, (B, K, 4))
+    p_out = take(B * P * 24, torch.float32, (B, P, 6))
+    p_emb = take(B * P * 8, torch.float32, (B, P, 2))
+    assign = take(B * P * 4, torch.int32, (B, P))
+    counts = take(B * 8, torch.int32, (B, 2))
+    diag = take(B * C * 8, torch.int32, (B * C, 2))
+    return PackedDetections(a_out, p_out, a_inds, p_inds, p_emb, assign, counts, diag, blob)
+
+
+def packed_nbytes(B: int, K: int, P: int, C: int) -> int:
+    sizes = (B * K * 8, B * P * 8, B * K * 16, B * P * 24, B * P * 8, B * P * 4, B * 8, B * C * 8)
+    return sum((s + 15) // 16 * 16 for s in sizes)
+
+
+class DecodePlan:
+    """Pre-sized workspace + output blob for one (device, shape, K, P): the low-overhead way
+    to call the C ABI repeatedly (bench loop, CUDA-graph capture, sharded decode)."""
+
+    def __init__(self, device, B, M, N, H, W, K, P):
+        self.shape = (B, M, N, H, W, K, P)
+        self.device = torch.device(device)
+        self.lib = _native.load()
+        self.workspace_bytes = _native.workspace_bytes(B, M, N, H, W, K, P)
+        self.workspace = torch.empty(self.workspace_bytes, dtype=torch.uint8, device=self.device)
+        self.out = _carve(torch.empty(packed_nbytes(B, K, P, M + N), dtype=torch.uint8, device=self.device),
+                          B, K, P, M + N)
+        self.params = SdnetDecodeParams()
+        p = self.params
+        p.struct_size = ctypes.sizeof(SdnetDecodeParams)
+        p.dtype = _native.DTYPE_F32
+        p.B, p.M, p.N, p.H, p.W, p.K, p.P = B, M, N, H, W, K, P
+        p.workspace = self.workspace.data_ptr()
+        p.workspace_bytes = self.workspace_bytes
+        self._bind_outputs(self.out)
+
+    def _bind_outputs(self, out: PackedDetections):
+        p = self.params
+        p.anchor_out, p.part_out = out.anchor_out.data_ptr(), out.part_out.data_ptr()
+        p.anchor_inds, p.part_inds = out.anchor_inds.data_ptr(), out.part_inds.data_ptr()
+        p.part_emb, p.assign = out.part_emb.data_ptr(), out.assign.data_ptr()
+        p.counts, p.diag = out.counts.data_ptr(), out.diag.data_ptr()
+
+    def _bind_inputs(self, anchor_hm, part_hm, offsets, embeddings, conf_f32, dist_abs_f32, radius, flags):
+        p = self.params
+        p.anchor_hm, p.part_hm, p.offsets = _view4(anchor_hm), _view4(part_hm), _view4(offsets)
+        p.embeddings = _view4(embeddings) if embeddings is not None else SdnetTensor4(None, 0, 0, 0, 1)
+        p.conf_f32, p.dist_abs_f32 = conf_f32, dist_abs_f32
+        p.radius, p.flags = radius, flags
+
+    def run(self, anchor_hm, part_hm, offsets, embeddings, conf_f32, dist_abs_f32, radius=2, flags=0,
+            stream: int | None = None) -> PackedDetections:
+        """Enqueue one decode on ``stream`` (default: torch's current stream). Asynchronous."""
+        self._bind_inputs(anchor_hm, part_hm, offsets, embeddings, conf_f32, dist_abs_f32, radius, flags)
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+        rc = self.lib.sdnet_decode_launch(ctypes.byref(self.params), ctypes.c_void_p(stream))
+        _native.check(rc, "sdnet_decode_launch")
+        return self.out
+
+    def run_host(self, anchor_hm, part_hm, offsets, embeddings, conf_f32, dist_abs_f32, staging: torch.Tensor,
+                 radius=2, flags=0, stream: int | None = None) -> PackedDetections:
+        """Same, with the four inputs in pinned HOST memory (``sdnet_decode_host_launch``)."""
+        self._bind_inputs(anchor_hm, part_hm, offsets, embeddings, conf_f32, dist_abs_f32, radius, flags)
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+        rc = self.lib.sdnet_decode_host_launch(ctypes.byref(self.params), ctypes.c_void_p(staging.data_ptr()),
+                                               ctypes.c_size_t(staging.numel() * staging.element_size()),
+                                               ctypes.c_void_p(stream))
+        _native.check(rc, "sdnet_decode_host_launch")
+        return self.out
+
+
+def _f32(value: float) -> float:
+    """Round a Python double to fp32 the way torch does when a tensor is compared with a scalar."""
+    return float(torch.tensor(value, dtype=torch.float32))
+
+
+# ------------------------------------------------------------------------------------ custom ops
+@torch.library.custom_op("sdnet_b200::decode", mutates_args=(), device_types="cuda")
+def _decode_op(anchor_hm: torch.Tensor, part_hm: torch.Tensor, offsets: torch.Tensor, embeddings: torch.Tensor,
+               max_objects: int, max_parts: int, conf_f32: float, dist_abs_f32: float, radius: int,
+               flags: int) -> torch.Tensor:
+    B, M, H, W = anchor_hm.shape
+    N = part_hm.shape[1]
+    with torch.cuda.device(anchor_hm.device):
+        plan = DecodePlan(anchor_hm.device, B, M, N, H, W, max_objects, max_parts)
+        plan.run(anchor_hm, part_hm, offsets, embeddings, conf_f32, dist_abs_f32, radius, flags)
+    return plan.out.blob
+
+
+@_decode_op.register_fake
+def _(anchor_hm, part_hm, offsets, embeddings, max_objects, max_parts, conf_f32, dist_abs_f32, radius, flags):
+    B, M = anchor_hm.shape[:2]
+    N = part_hm.shape[1]
+    return anchor_hm.new_empty(packed_nbytes(B, max_objects, max_parts, M + N), dtype=torch.uint8)
+
+
+@torch.library.custom_op("sdnet_b200::activate", mutates_args=(), device_types="cuda")
+def _activate_op(hm: torch.Tensor) -> torch.Tensor:
+    B, C, H, W = hm.shape
+    out = torch.empty((B, C, H, W), dtype=torch.float32, device=hm.device)
+    view = _view4(hm)
+    with torch.cuda.device(hm.device):
+        rc = _native.load().sdnet_activate_launch(ctypes.byref(view), _native.DTYPE_F32, B, C, H, W,
+                                                  ctypes.c_void_p(out.data_ptr()),
+                                                  ctypes.c_void_p(torch.cuda.current_stream(hm.device).cuda_stream))
+    _native.check(rc, "sdnet_activate_launch")
+    return out
+
+
+@_activate_op.register_fake
+def _(hm):
+    return hm.new_empty(hm.shape, dtype=torch.float32)
+
+
+def _unit_w_stride(t: torch.Tensor) -> torch.Tensor:
+    # a layout fix on the device, not a fallback: the kernels need the innermost stride to be 1
+    return t if t.stride(3) == 1 else t.contiguous()
+
+
+def decode_packed(outputs: dict, max_objects: int, max_parts: int, conf_thresh: float, dist_thresh: float, *,
+                  pre_activated: bool = False, group: bool = True, radius: int = 2,
+                  exact_select: bool = False) -> PackedDetections:
+    """Run the CUDA decode on the four network-output views and return packed device tensors."""
+    a_hm, p_hm, off = outputs["anchor_hm"], outputs["part_hm"], outputs["offsets"]
+    emb = outputs["embeddings"] if group or "embeddings" in outputs else None
+    for name, t in (("anchor_hm", a_hm), ("part_hm", p_hm), ("offsets", off)) + ((("embeddings", emb),) if emb is not None else ()):
+        _require_cuda_f32(name, t)
+    B, M, H, W = a_hm.shape
+    N = p_hm.shape[1]
+    if emb is None:
+        emb = off  # never read under NO_GROUPING without part_emb consumers; keeps the op signature tensor-only
+    flags = (FLAG_PRE_ACTIVATED if pre_activated else 0) | (0 if group else FLAG_NO_GROUPING) | (
+        FLAG_EXACT_SELECT if exact_select else 0)
+    a_hm, p_hm, off, emb = map(_unit_w_stride, (a_hm, p_hm, off, emb))
+    blob = _decode_op(a_hm, p_hm, off, emb, int(max_objects), int(max_parts), _f32(conf_thresh),
+                      _f32(float(dist_thresh) * min(W, H)), int(radius), int(flags))
+    return _carve(blob, B, int(max_objects), int(max_parts), M + N)
+
+
+def activate_maps(hm: torch.Tensor) -> torch.Tensor:
+    """``clamp(sigmoid(hm), 1e-6, 1-1e-6)`` as a contiguous fp32 tensor (reference utils.py:355-361)."""
+    _require_cuda_f32("heat map", hm)
+    return _activate_op(_unit_w_stride(hm))
