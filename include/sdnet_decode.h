@@ -96,6 +96,11 @@ int sdnet_decode_workspace_bytes(int B, int M, int N, int H, int W, int K, int P
  * 347-351 transpose_and_gather, 422-437 hypot): heat maps -> packed detections. */
 int sdnet_decode_launch(const SdnetDecodeParams* params, void* stream);
 
+/* Profiling variant (bench.py's roofline leg): same work, but records CUDA events between the
+ * three kernels on `stream`, WAITS for completion and returns the device time of each kernel in
+ * milliseconds: kernel_ms[0] = peaks, [1] = exact-select, [2] = tail.  Synchronous by design. */
+int sdnet_decode_launch_timed(const SdnetDecodeParams* params, void* stream, float* kernel_ms);
+
 /* clamp(sigmoid(x), 1e-6, 1-1e-6) of a (B, C, H, W) view into a contiguous fp32 tensor:
  * the `anchor_hm_sig` / `part_hm_sig` metadata maps (decoders.py:44,60,163-164). */
 int sdnet_activate_launch(const SdnetTensor4* in, int dtype, int B, int C, int H, int W, float* out, void* stream);

@@ -24,6 +24,7 @@ EXPORTS = (
     "sdnet_error_string",
     "sdnet_decode_workspace_bytes",
     "sdnet_decode_launch",
+    "sdnet_decode_launch_timed",
     "sdnet_activate_launch",
     "sdnet_decode_host_launch",
 )
@@ -99,6 +100,9 @@ def load() -> ctypes.CDLL:
     lib.sdnet_decode_workspace_bytes.argtypes = [ctypes.c_int] * 8 + [ctypes.POINTER(ctypes.c_size_t)]
     lib.sdnet_decode_launch.restype = ctypes.c_int
     lib.sdnet_decode_launch.argtypes = [ctypes.POINTER(SdnetDecodeParams), ctypes.c_void_p]
+    lib.sdnet_decode_launch_timed.restype = ctypes.c_int
+    lib.sdnet_decode_launch_timed.argtypes = [ctypes.POINTER(SdnetDecodeParams), ctypes.c_void_p,
+                                              ctypes.POINTER(ctypes.c_float)]
     lib.sdnet_activate_launch.restype = ctypes.c_int
     lib.sdnet_activate_launch.argtypes = [ctypes.POINTER(SdnetTensor4), ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                           ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]

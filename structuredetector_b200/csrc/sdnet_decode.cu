@@ -73,6 +73,8 @@ struct PeaksParams {
   u64* lists;              // [planes][cap]
   int* counts;             // [planes] records emitted (may exceed cap)
   u32* sched;              // [0] dynamic unit counter
+  u32* ghist;              // [planes][kBins] plane-wide logit histogram of recorded candidates
+  int* gfloor;             // [planes] highest bin b with >= K recorded candidates in bins >= b (0 = none)
 };
 
 // clamp(sigmoid(x)) bit-identical to ATen's CUDA kernels (UnarySpecialOpsKernel.cu sigmoid:
@@ -90,33 +92,83 @@ __device__ __forceinline__ float comp(const float4& v, int j) {
 
 // ---------------------------------------------------------------------------------------------
 // peaks kernel
+//
+// Work unit = (plane, row strip, 128-column panel), one warp per unit, units handed out by an
+// atomic counter.  Each warp streams its panel top to bottom through a private shared-memory
+// ring of kStages rows filled with cp.async (16 B per lane, straight from L2, no registers):
+//     row buffer (kPitch floats):  [pad pad hL hL | 128 panel columns | hR hR pad pad]
+// Per row the common case is: issue the copy of the row kStages-1 ahead, wait for the row two
+// below the centre, read the centre row (one LDS.128), and vote "does any pixel beat the
+// pruning floor?".  Only then is the 5x5 window maximum formed (vertical max from the ring,
+// neighbours' columns by shuffle, panel-edge columns from the halo slots) and the exact
+// sigmoid evaluated for the pixels within a hair of their window maximum.
 // ---------------------------------------------------------------------------------------------
+constexpr int kStages = 8;             // ring depth (power of two); kStages - 1 - 2R rows stay in flight
+constexpr int kPitch = 136;            // floats per ring row
+constexpr int kPeaksSmemPerWarp = kStages * kPitch * 4 + kBins * 8;
+constexpr int kPeaksSmem = kWarps * kPeaksSmemPerWarp;
+
+__device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(float* dst, const float* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src));
+}
+__device__ __forceinline__ void cp_async8(float* dst, const float* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src));
+}
+__device__ __forceinline__ void cp_async4(float* dst, const float* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Start the copy of one row of the panel into ring slot `dst` (or fill it with -inf when the row
+// lies outside the image: max_pool2d pads with -inf).  Always closes one cp.async group.
 template <bool kAligned>
-__device__ __forceinline__ void load_row(const float* __restrict__ plane, long long sh, int row, int H, int W,
-                                         int col0, int lane, int panel_col0, float4& v, float2& hv) {
+__device__ __forceinline__ void issue_row(float* dst, const float* __restrict__ plane, long long sh, int row, int H,
+                                          int W, int col0, int lane, int panel_col0, bool wanted) {
   const float ninf = -CUDART_INF_F;
-  v = make_float4(ninf, ninf, ninf, ninf);
-  hv = make_float2(ninf, ninf);
-  if (row < 0 || row >= H) return;  // warp-uniform
-  const float* rp = plane + (long long)row * sh;
-  if (kAligned) {
-    if (col0 < W) v = __ldg(reinterpret_cast<const float4*>(rp + col0));
-    if (lane == 0 && panel_col0 > 0) hv = __ldg(reinterpret_cast<const float2*>(rp + panel_col0 - 2));
-    if (lane == 31 && panel_col0 + kPanelW < W) hv = __ldg(reinterpret_cast<const float2*>(rp + panel_col0 + kPanelW));
-  } else {
-    if (col0 + 0 < W) v.x = __ldg(rp + col0 + 0);
-    if (col0 + 1 < W) v.y = __ldg(rp + col0 + 1);
-    if (col0 + 2 < W) v.z = __ldg(rp + col0 + 2);
-    if (col0 + 3 < W) v.w = __ldg(rp + col0 + 3);
-    if (lane == 0 && panel_col0 > 0) {
-      hv.x = __ldg(rp + panel_col0 - 2);
-      hv.y = __ldg(rp + panel_col0 - 1);
-    }
-    if (lane == 31) {
-      if (panel_col0 + kPanelW < W) hv.x = __ldg(rp + panel_col0 + kPanelW);
-      if (panel_col0 + kPanelW + 1 < W) hv.y = __ldg(rp + panel_col0 + kPanelW + 1);
+  if (wanted) {  // warp-uniform
+    float* own = dst + 4 + 4 * lane;
+    if (row >= 0 && row < H) {
+      const float* rp = plane + (long long)row * sh;
+      if (kAligned) {
+        if (col0 < W) cp_async16(own, rp + col0);
+        else *reinterpret_cast<float4*>(own) = make_float4(ninf, ninf, ninf, ninf);
+        if (lane == 0) {
+          if (panel_col0 > 0) cp_async8(dst + 2, rp + panel_col0 - 2);
+          else *reinterpret_cast<float2*>(dst + 2) = make_float2(ninf, ninf);
+        } else if (lane == 31) {
+          if (panel_col0 + kPanelW < W) cp_async8(dst + 4 + kPanelW, rp + panel_col0 + kPanelW);
+          else *reinterpret_cast<float2*>(dst + 4 + kPanelW) = make_float2(ninf, ninf);
+        }
+      } else {
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          if (col0 + jj < W) cp_async4(own + jj, rp + col0 + jj);
+          else own[jj] = ninf;
+        }
+        if (lane == 0) {
+#pragma unroll
+          for (int jj = 0; jj < 2; ++jj) {
+            if (panel_col0 - 2 + jj >= 0) cp_async4(dst + 2 + jj, rp + panel_col0 - 2 + jj);
+            else dst[2 + jj] = ninf;
+          }
+        } else if (lane == 31) {
+#pragma unroll
+          for (int jj = 0; jj < 2; ++jj) {
+            if (panel_col0 + kPanelW + jj < W) cp_async4(dst + 4 + kPanelW + jj, rp + panel_col0 + kPanelW + jj);
+            else dst[4 + kPanelW + jj] = ninf;
+          }
+        }
+      }
+    } else {
+      *reinterpret_cast<float4*>(own) = make_float4(ninf, ninf, ninf, ninf);
+      if (lane == 0) *reinterpret_cast<float2*>(dst + 2) = make_float2(ninf, ninf);
+      if (lane == 31) *reinterpret_cast<float2*>(dst + 4 + kPanelW) = make_float2(ninf, ninf);
     }
   }
+  cp_async_commit();
 }
 
 __device__ __forceinline__ int logit_bin(float x) {
@@ -134,13 +186,8 @@ __device__ __forceinline__ int ord_of(float x) {
 }
 __device__ __forceinline__ float ord_to_float(int o) { return __int_as_float(o ^ ((o >> 31) & 0x7fffffff)); }
 
-// Pruning floor of one warp-unit.  Let b be the highest bin such that the unit has already
-// recorded >= K candidates in bins >= b.  Every one of those has a (saturation-clamped) logit
-// >= minx[b], a lower flat index than anything the unit will see later, and therefore beats any
-// later pixel whose clamped logit is <= minx[b] under (score desc, index asc).  Returns that
-// minx[b] (in clamped-logit units), or -inf when fewer than K candidates were recorded.
-__device__ __forceinline__ float floor_value(const u32* hist, const int* minx, int lane, int K) {
-  const uint4 c = *reinterpret_cast<const uint4*>(hist + 4 * lane);
+// Highest bin b with (count in bins >= b) >= K given each lane's four bin counts; -1 if none.
+__device__ __forceinline__ int floor_bin_of(const uint4 c, int lane, int K) {
   const u32 s = c.x + c.y + c.z + c.w;
   u32 suf = s;
 #pragma unroll
@@ -149,33 +196,54 @@ __device__ __forceinline__ float floor_value(const u32* hist, const int* minx, i
     if (lane + d < 32) suf += t;
   }
   const u32 mask = __ballot_sync(0xffffffffu, suf >= (u32)K);
-  if (mask == 0) return -CUDART_INF_F;
+  if (mask == 0) return -1;
   const int L = 31 - __clz(mask);
-  float f = 0.f;
+  int b = 0;
   if (lane == L) {
     u32 above = suf - s;
-    int b;
     if (above + c.w >= (u32)K) b = 4 * L + 3;
     else if (above + c.w + c.z >= (u32)K) b = 4 * L + 2;
     else if (above + c.w + c.z + c.y >= (u32)K) b = 4 * L + 1;
     else b = 4 * L;
-    f = ord_to_float(minx[b]);
   }
-  return __shfl_sync(0xffffffffu, f, L);
+  return __shfl_sync(0xffffffffu, b, L);
+}
+
+// Warp-local pruning floor.  Let b be the highest bin such that this warp-unit has already
+// recorded >= K candidates in bins >= b.  Every one of those has a (saturation-clamped) logit
+// >= minx[b] and a lower flat index than anything the unit will see later, so it beats any
+// later pixel whose clamped logit is <= minx[b] under (score desc, index asc) -- equal scores
+// included.  Returns minx[b], or -inf when fewer than K candidates were recorded.
+__device__ __forceinline__ float local_floor(const u32* hist, const int* minx, int lane, int K) {
+  const int b = floor_bin_of(*reinterpret_cast<const uint4*>(hist + 4 * lane), lane, K);
+  if (b < 0) return -CUDART_INF_F;
+  return ord_to_float(minx[b]);
+}
+
+// Plane-wide floor shared between the warps working on one plane.  Unlike the warp-local floor
+// (which may drop equal scores because everything it counted has a lower index), this one needs
+// a strict score gap: a pixel is dropped only if its logit is below edge(b) - kNearTie with
+// edge(b) in [kLoZone, kHiZone], where S(x - kNearTie) < S(x) is verified exhaustively.
+__device__ __forceinline__ float shared_floor(int gbin, float xscale) {
+  if (gbin <= 0) return -CUDART_INF_F;
+  const float edge = kBinLo + (float)gbin * (1.0f / kBinScale);
+  if (xscale != 1.0f) return edge / xscale;  // pre-activated: keys are strictly monotone in the value
+  if (edge < kLoZone || edge > kHiZone) return -CUDART_INF_F;
+  return edge - kNearTie;
 }
 
 template <bool kAligned, int R>
-__global__ void __launch_bounds__(kThreads, 3) sdnet_peaks_kernel(const __grid_constant__ PeaksParams p) {
-  __shared__ __align__(16) u32 s_hist[kWarps][kBins];
-  __shared__ __align__(16) int s_minx[kWarps][kBins];
+__global__ void __launch_bounds__(kThreads, 4) sdnet_peaks_kernel(const __grid_constant__ PeaksParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  u32* hist = s_hist[warp];
-  int* minx = s_minx[warp];
+  float* ring = reinterpret_cast<float*>(smem_raw + (size_t)warp * kPeaksSmemPerWarp);
+  u32* hist = reinterpret_cast<u32*>(ring + kStages * kPitch);
+  int* minx = reinterpret_cast<int*>(hist + kBins);
   const float xscale = p.pre_activated ? kPreScale : 1.0f;
   const float satx = p.pre_activated ? CUDART_INF_F : kSatX;
-  const float ninf = -CUDART_INF_F;
   const int C = p.M + p.N;
+  constexpr int kPending = kStages - 1 - 2 * R;  // cp.async groups allowed in flight at the wait
 
   for (;;) {
     u32 unit = 0;
@@ -198,144 +266,155 @@ __global__ void __launch_bounds__(kThreads, 3) sdnet_peaks_kernel(const __grid_c
     const int r_begin = strip * p.rows_per_strip;
     const int r_end = min(H, r_begin + p.rows_per_strip);
     const int nrows = r_end - r_begin;
+    const int q_last = nrows - 1 + 2 * R;  // ring sequence number of the last row any centre row needs
     u64* __restrict__ list = p.lists + (size_t)plane_id * p.cap;
     int* count_ptr = p.counts + plane_id;
+    u32* ghist = p.ghist + (size_t)plane_id * kBins;
+    int* gfloor_ptr = p.gfloor + plane_id;
 
-    // per-unit pruning state (warp-uniform)
-    float floorx = ninf;  // in input units; a pixel can still matter only if min(x, satx) > floorx
+    // per-unit pruning state (warp-uniform).  Input units; a pixel can still matter only if
+    // min(x, satx) > floorx.
+    float floorx = shared_floor(__ldcg(gfloor_ptr), xscale);
     u32 emitted = 0;
+    __syncwarp();  // everyone is done with the previous unit's ring and histogram
     *reinterpret_cast<uint4*>(hist + 4 * lane) = make_uint4(0, 0, 0, 0);
     *reinterpret_cast<int4*>(minx + 4 * lane) = make_int4(0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff);
-    __syncwarp();
 
-    float4 ring[kRing];
-    float2 hring[kRing];
-    // prologue: rows r_begin-R .. r_begin-R+kRing-2
+    // ring sequence number q <-> image row r_begin - R + q, slot q % kStages
 #pragma unroll
-    for (int q = 0; q < kRing - 1; ++q) {
-      const int row = r_begin - R + q;
-      if (row <= r_end - 1 + R)
-        load_row<kAligned>(plane, sh, row, H, W, col0, lane, panel_col0, ring[q], hring[q]);
-      else {
-        ring[q] = make_float4(ninf, ninf, ninf, ninf);
-        hring[q] = make_float2(ninf, ninf);
+    for (int q = 0; q < kStages - 1; ++q)
+      issue_row<kAligned>(ring + q * kPitch, plane, sh, r_begin - R + q, H, W, col0, lane, panel_col0, q <= q_last);
+
+    for (int t = 0; t < nrows; ++t) {
+      {  // the slot of sequence number t-1 is free: every lane passed a warp-wide vote after reading it
+        const int q = t + kStages - 1;
+        issue_row<kAligned>(ring + (q & (kStages - 1)) * kPitch, plane, sh, r_begin - R + q, H, W, col0, lane,
+                            panel_col0, q <= q_last);
       }
-    }
-
-    for (int t0 = 0; t0 < nrows; t0 += kRing) {
+      cp_async_wait<kPending>();
+      __syncwarp();
+      const float* crow = ring + ((t + R) & (kStages - 1)) * kPitch + 4 + 4 * lane;
+      const float4 ctr = *reinterpret_cast<const float4*>(crow);
+      const float m4 = fmaxf(fmaxf(ctr.x, ctr.y), fmaxf(ctr.z, ctr.w));
+      if (__any_sync(0xffffffffu, fminf(m4, satx) > floorx)) {
+        const int row = r_begin + t;
+        u32 ekey0 = 0, ekey1 = 0, ekey2 = 0, ekey3 = 0;
+        if (!p.pre_activated) {
+          // vertical (2R+1)-max of own columns and of this lane's halo pair (lanes 0 / 31 only)
+          const int hoff = lane == 31 ? 4 + kPanelW : 2;
+          float4 v = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
+          float2 hvv = make_float2(-CUDART_INF_F, -CUDART_INF_F);
 #pragma unroll
-      for (int j = 0; j < kRing; ++j) {
-        const int t = t0 + j;
-        if (t < nrows) {  // warp-uniform
-          {  // prefetch the row that enters the ring kRing-1 steps ahead
-            const int row = r_begin - R + t + (kRing - 1);
-            const int slot = (j + kRing - 1) % kRing;
-            if (row <= r_end - 1 + R)
-              load_row<kAligned>(plane, sh, row, H, W, col0, lane, panel_col0, ring[slot], hring[slot]);
-            else {
-              ring[slot] = make_float4(ninf, ninf, ninf, ninf);
-              hring[slot] = make_float2(ninf, ninf);
+          for (int d = 0; d <= 2 * R; ++d) {
+            const float* rowp = ring + ((t + d) & (kStages - 1)) * kPitch;
+            const float4 o = *reinterpret_cast<const float4*>(rowp + 4 + 4 * lane);
+            const float2 ho = *reinterpret_cast<const float2*>(rowp + hoff);
+            v.x = fmaxf(v.x, o.x); v.y = fmaxf(v.y, o.y); v.z = fmaxf(v.z, o.z); v.w = fmaxf(v.w, o.w);
+            hvv.x = fmaxf(hvv.x, ho.x); hvv.y = fmaxf(hvv.y, ho.y);
+          }
+          float L2 = __shfl_up_sync(0xffffffffu, v.z, 1);
+          float L3 = __shfl_up_sync(0xffffffffu, v.w, 1);
+          float R0 = __shfl_down_sync(0xffffffffu, v.x, 1);
+          float R1 = __shfl_down_sync(0xffffffffu, v.y, 1);
+          if (lane == 0) { L2 = hvv.x; L3 = hvv.y; }
+          if (lane == 31) { R0 = hvv.x; R1 = hvv.y; }
+          float h0, h1, h2, h3;
+          if (R == 2) {
+            const float m12 = fmaxf(v.y, v.z);
+            h0 = max3(fmaxf(L2, L3), v.x, m12);
+            h1 = max3(fmaxf(L3, v.x), m12, v.w);
+            h2 = max3(fmaxf(v.x, R0), m12, v.w);
+            h3 = max3(fmaxf(R0, R1), m12, v.w);
+          } else {
+            h0 = max3(L3, v.x, v.y);
+            h1 = max3(v.x, v.y, v.z);
+            h2 = max3(v.y, v.z, v.w);
+            h3 = max3(v.z, v.w, R0);
+          }
+          // cheap per-pixel predicate: above the floor and within a hair of the window maximum
+          u32 cmask = 0;
+#define SDNET_NEAR(x, h) (((x) >= (h) - kNearTie) || ((h) > kHiZone && (x) > kHiZone - 1.0f) || ((h) < kLoZone))
+          if (col0 + 0 < W && fminf(ctr.x, satx) > floorx && SDNET_NEAR(ctr.x, h0)) cmask |= 1u;
+          if (col0 + 1 < W && fminf(ctr.y, satx) > floorx && SDNET_NEAR(ctr.y, h1)) cmask |= 2u;
+          if (col0 + 2 < W && fminf(ctr.z, satx) > floorx && SDNET_NEAR(ctr.z, h2)) cmask |= 4u;
+          if (col0 + 3 < W && fminf(ctr.w, satx) > floorx && SDNET_NEAR(ctr.w, h3)) cmask |= 8u;
+#undef SDNET_NEAR
+          // exact check, one pixel per lane per round, no divergence (idle lanes compute on 0)
+          while (__any_sync(0xffffffffu, cmask != 0)) {
+            const bool has = cmask != 0;
+            const int jj = has ? __ffs(cmask) - 1 : 0;
+            const float x = jj == 0 ? ctr.x : (jj == 1 ? ctr.y : (jj == 2 ? ctr.z : ctr.w));
+            const float h = jj == 0 ? h0 : (jj == 1 ? h1 : (jj == 2 ? h2 : h3));
+            const float sx = activate(has ? x : 0.0f);
+            bool peak = has && (x == h);
+            const bool second = has && !peak;
+            if (__any_sync(0xffffffffu, second)) peak = peak || (second && sx == activate(h));
+            const u32 key = peak ? __float_as_uint(sx) : 0u;
+            if (has) {
+              if (jj == 0) ekey0 = key; else if (jj == 1) ekey1 = key; else if (jj == 2) ekey2 = key; else ekey3 = key;
+            }
+            cmask &= cmask - 1;
+          }
+        } else {
+          // pre-activated maps (CoreMLDecoder): every pixel is a candidate with its own value.
+          // Values are scores in [0, 1]; the order-preserving key below also handles negatives.
+#define SDNET_PKEY(x) ((__float_as_uint(x) & 0x80000000u) ? ~__float_as_uint(x) : (__float_as_uint(x) | 0x80000000u))
+          if (col0 + 0 < W && ctr.x > floorx) ekey0 = SDNET_PKEY(ctr.x);
+          if (col0 + 1 < W && ctr.y > floorx) ekey1 = SDNET_PKEY(ctr.y);
+          if (col0 + 2 < W && ctr.z > floorx) ekey2 = SDNET_PKEY(ctr.z);
+          if (col0 + 3 < W && ctr.w > floorx) ekey3 = SDNET_PKEY(ctr.w);
+#undef SDNET_PKEY
+        }
+        const u32 m0 = __ballot_sync(0xffffffffu, ekey0 != 0);
+        const u32 m1 = __ballot_sync(0xffffffffu, ekey1 != 0);
+        const u32 m2 = __ballot_sync(0xffffffffu, ekey2 != 0);
+        const u32 m3 = __ballot_sync(0xffffffffu, ekey3 != 0);
+        const u32 total = __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
+        if (total) {  // warp-uniform
+          int base = 0;
+          if (lane == 0) base = atomicAdd(count_ptr, (int)total);
+          base = __shfl_sync(0xffffffffu, base, 0);
+          const u32 lt = (1u << lane) - 1u;
+          // lane-major order inside the row: position = records of lower lanes + own earlier columns
+          int pos = base + __popc(m0 & lt) + __popc(m1 & lt) + __popc(m2 & lt) + __popc(m3 & lt);
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const u32 key = jj == 0 ? ekey0 : (jj == 1 ? ekey1 : (jj == 2 ? ekey2 : ekey3));
+            if (key) {
+              const u32 idx = (u32)(row * W + col0 + jj);
+              if (pos < p.cap) list[pos] = ((u64)key << 32) | idx;
+              ++pos;
+              // clamped logit: the score is a monotone function of it, saturation included
+              const float xe = fminf(fmaxf(comp(ctr, jj) * xscale, -satx), satx);
+              const int bin = logit_bin(xe);
+              atomicAdd(&hist[bin], 1u);
+              atomicMin(&minx[bin], ord_of(xe));
+              atomicAdd(&ghist[bin], 1u);
             }
           }
-          const float4 ctr = ring[(j + R) % kRing];
-          const float m4 = fmaxf(fmaxf(ctr.x, ctr.y), fmaxf(ctr.z, ctr.w));
-          if (__any_sync(0xffffffffu, fminf(m4, satx) > floorx)) {
-            const int row = r_begin + t;
-            u32 ekey[4] = {0, 0, 0, 0};
-            if (!p.pre_activated) {
-              // vertical (2R+1)-max of own columns and of the halo pair
-              float4 v = ring[j % kRing];
-              float2 hvv = hring[j % kRing];
-#pragma unroll
-              for (int d = 1; d <= 2 * R; ++d) {
-                const float4 o = ring[(j + d) % kRing];
-                const float2 ho = hring[(j + d) % kRing];
-                v.x = fmaxf(v.x, o.x); v.y = fmaxf(v.y, o.y); v.z = fmaxf(v.z, o.z); v.w = fmaxf(v.w, o.w);
-                hvv.x = fmaxf(hvv.x, ho.x); hvv.y = fmaxf(hvv.y, ho.y);
-              }
-              float L2 = __shfl_up_sync(0xffffffffu, v.z, 1);
-              float L3 = __shfl_up_sync(0xffffffffu, v.w, 1);
-              float R0 = __shfl_down_sync(0xffffffffu, v.x, 1);
-              float R1 = __shfl_down_sync(0xffffffffu, v.y, 1);
-              if (lane == 0) { L2 = hvv.x; L3 = hvv.y; }
-              if (lane == 31) { R0 = hvv.x; R1 = hvv.y; }
-              float hmax[4];
-              if (R == 2) {
-                const float m12 = fmaxf(v.y, v.z);
-                hmax[0] = max3(fmaxf(L2, L3), v.x, m12);
-                hmax[1] = max3(fmaxf(L3, v.x), m12, v.w);
-                hmax[2] = max3(fmaxf(v.x, R0), m12, v.w);
-                hmax[3] = max3(fmaxf(R0, R1), m12, v.w);
-              } else {
-                hmax[0] = max3(L3, v.x, v.y);
-                hmax[1] = max3(v.x, v.y, v.z);
-                hmax[2] = max3(v.y, v.z, v.w);
-                hmax[3] = max3(v.z, v.w, R0);
-              }
-#pragma unroll
-              for (int jj = 0; jj < 4; ++jj) {
-                const float x = comp(ctr, jj);
-                const float h = hmax[jj];
-                const bool inside = col0 + jj < W;
-                const bool near = (x >= h - kNearTie) || (h > kHiZone && x > kHiZone - 1.0f) || (h < kLoZone);
-                if (inside && fminf(x, satx) > floorx && near) {
-                  const float sx = activate(x);
-                  const bool peak = (x == h) || (sx == activate(h));
-                  if (peak) ekey[jj] = __float_as_uint(sx);
-                }
-              }
-            } else {
-              // pre-activated maps (CoreMLDecoder): every pixel is a candidate with its own value.
-              // Values are scores in [0, 1]; the order-preserving key below also handles negatives.
-#pragma unroll
-              for (int jj = 0; jj < 4; ++jj) {
-                const float x = comp(ctr, jj);
-                if (col0 + jj < W && x > floorx) {
-                  const u32 bits = __float_as_uint(x);
-                  ekey[jj] = (bits & 0x80000000u) ? ~bits : (bits | 0x80000000u);
-                }
-              }
-            }
-            const u32 m0 = __ballot_sync(0xffffffffu, ekey[0] != 0);
-            const u32 m1 = __ballot_sync(0xffffffffu, ekey[1] != 0);
-            const u32 m2 = __ballot_sync(0xffffffffu, ekey[2] != 0);
-            const u32 m3 = __ballot_sync(0xffffffffu, ekey[3] != 0);
-            const u32 total = __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
-            if (total) {  // warp-uniform
-              int base = 0;
-              if (lane == 0) base = atomicAdd(count_ptr, (int)total);
-              base = __shfl_sync(0xffffffffu, base, 0);
-              const u32 lt = (1u << lane) - 1u;
-              // lane-major order inside the row: position = records of lower lanes + own earlier columns
-              int pos = base + __popc(m0 & lt) + __popc(m1 & lt) + __popc(m2 & lt) + __popc(m3 & lt);
-#pragma unroll
-              for (int jj = 0; jj < 4; ++jj) {
-                if (ekey[jj]) {
-                  const u32 idx = (u32)(row * W + col0 + jj);
-                  if (pos < p.cap) list[pos] = ((u64)ekey[jj] << 32) | idx;
-                  ++pos;
-                  // clamped logit: the score is a monotone function of it, saturation included
-                  const float xe = fminf(fmaxf(comp(ctr, jj) * xscale, -satx), satx);
-                  const int bin = logit_bin(xe);
-                  atomicAdd(&hist[bin], 1u);
-                  atomicMin(&minx[bin], ord_of(xe));
-                }
-              }
-              emitted += total;
-              if (emitted >= (u32)K) {
-                __syncwarp();
-                // xscale is a power of two, so the division is exact
-                floorx = fmaxf(floorx, floor_value(hist, minx, lane, K) / xscale);
-              }
-            }
+          emitted += total;
+          __syncwarp();
+          if (emitted >= (u32)K) {
+            // xscale is a power of two, so the division is exact
+            floorx = fmaxf(floorx, local_floor(hist, minx, lane, K) / xscale);
+          }
+          // publish / refresh the plane-wide floor
+          const uint4 gc = __ldcg(reinterpret_cast<const uint4*>(ghist + 4 * lane));
+          const int gb = floor_bin_of(gc, lane, K);
+          if (gb > 0) {
+            if (lane == 0) atomicMax(gfloor_ptr, gb);
+            floorx = fmaxf(floorx, shared_floor(gb, xscale));
           }
         }
       }
+      if ((t & 7) == 7) {
+        // every 8 rows: pick up the plane-wide floor other warps may have raised
+        floorx = fmaxf(floorx, shared_floor(__ldcg(gfloor_ptr), xscale));
+      }
     }
-    __syncwarp();
+    cp_async_wait<0>();
   }
 }
-
 
 // ---------------------------------------------------------------------------------------------
 // exact-select kernel: bounded-memory fallback for planes whose candidate list overflowed
@@ -820,7 +899,7 @@ __global__ void sdnet_activate_kernel(View4 in, int C, int H, int W, size_t tota
 // host side
 // ---------------------------------------------------------------------------------------------
 struct Workspace {
-  size_t off_counts, off_flags, off_sched, off_lists, total;
+  size_t off_counts, off_flags, off_sched, off_gfloor, off_ghist, off_lists, total;
   int cap;
 };
 
@@ -835,6 +914,8 @@ Workspace plan_workspace(int B, int M, int N, int H, int W, int K, int P) {
   ws.off_counts = off; off = align_up(off + planes * sizeof(int), 256);
   ws.off_flags = off;  off = align_up(off + planes * sizeof(int), 256);
   ws.off_sched = off;  off = align_up(off + 64, 256);
+  ws.off_gfloor = off; off = align_up(off + planes * sizeof(int), 256);
+  ws.off_ghist = off;  off = align_up(off + planes * kBins * sizeof(u32), 256);
   ws.off_lists = off;  off = align_up(off + planes * (size_t)ws.cap * sizeof(u64), 256);
   ws.total = off;
   return ws;
@@ -882,13 +963,23 @@ bool view_aligned(const SdnetTensor4& t, int W) {
          (W % 4 == 0);
 }
 
-int launch_decode(const SdnetDecodeParams* p, cudaStream_t stream) {
+constexpr int kPeaksCtasPerSm = 4;
+
+template <typename Kern>
+void launch_peaks(Kern kern, dim3 grid, dim3 block, cudaStream_t stream, const PeaksParams& pp) {
+  // > 48 KB of dynamic shared memory needs the opt-in (idempotent, cheap)
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kPeaksSmem);
+  kern<<<grid, block, kPeaksSmem, stream>>>(pp);
+}
+
+int launch_decode(const SdnetDecodeParams* p, cudaStream_t stream, cudaEvent_t* marks = nullptr) {
   const Workspace ws = plan_workspace(p->B, p->M, p->N, p->H, p->W, p->K, p->P);
   char* base = static_cast<char*>(p->workspace);
   const int C = p->M + p->N;
   const size_t planes = (size_t)p->B * C;
   cudaError_t err = cudaMemsetAsync(base, 0, ws.off_lists, stream);
   if (err != cudaSuccess) return (int)err;
+  if (marks) cudaEventRecord(marks[0], stream);
 
   PeaksParams pp;
   pp.anchor = to_view(p->anchor_hm);
@@ -896,7 +987,7 @@ int launch_decode(const SdnetDecodeParams* p, cudaStream_t stream) {
   pp.B = p->B; pp.M = p->M; pp.N = p->N; pp.H = p->H; pp.W = p->W; pp.K = p->K; pp.P = p->P;
   pp.panels = (p->W + kPanelW - 1) / kPanelW;
   const int sms = device_sm_count();
-  const int resident_warps = sms * 3 * kWarps;
+  const int resident_warps = sms * kPeaksCtasPerSm * kWarps;
   // enough units for ~4 waves of resident warps, but strips of at least 32 rows
   long long want_units = 4ll * resident_warps;
   long long per_strip1 = (long long)planes * pp.panels;
@@ -912,19 +1003,22 @@ int launch_decode(const SdnetDecodeParams* p, cudaStream_t stream) {
   pp.lists = reinterpret_cast<u64*>(base + ws.off_lists);
   pp.counts = reinterpret_cast<int*>(base + ws.off_counts);
   pp.sched = reinterpret_cast<u32*>(base + ws.off_sched);
+  pp.ghist = reinterpret_cast<u32*>(base + ws.off_ghist);
+  pp.gfloor = reinterpret_cast<int*>(base + ws.off_gfloor);
   const bool aligned = view_aligned(p->anchor_hm, p->W) && view_aligned(p->part_hm, p->W);
   long long ctas = ((long long)pp.units + kWarps - 1) / kWarps;
-  if (ctas > (long long)sms * 3) ctas = (long long)sms * 3;
+  if (ctas > (long long)sms * kPeaksCtasPerSm) ctas = (long long)sms * kPeaksCtasPerSm;
   dim3 grid((unsigned)ctas), block(kThreads);
   if (p->radius == 2) {
-    if (aligned) sdnet_peaks_kernel<true, 2><<<grid, block, 0, stream>>>(pp);
-    else sdnet_peaks_kernel<false, 2><<<grid, block, 0, stream>>>(pp);
+    if (aligned) launch_peaks(sdnet_peaks_kernel<true, 2>, grid, block, stream, pp);
+    else launch_peaks(sdnet_peaks_kernel<false, 2>, grid, block, stream, pp);
   } else {
-    if (aligned) sdnet_peaks_kernel<true, 1><<<grid, block, 0, stream>>>(pp);
-    else sdnet_peaks_kernel<false, 1><<<grid, block, 0, stream>>>(pp);
+    if (aligned) launch_peaks(sdnet_peaks_kernel<true, 1>, grid, block, stream, pp);
+    else launch_peaks(sdnet_peaks_kernel<false, 1>, grid, block, stream, pp);
   }
   err = cudaGetLastError();
   if (err != cudaSuccess) return (int)err;
+  if (marks) cudaEventRecord(marks[1], stream);
 
   {
     ExactParams ep;
@@ -938,6 +1032,7 @@ int launch_decode(const SdnetDecodeParams* p, cudaStream_t stream) {
     sdnet_exact_select_kernel<<<dim3((unsigned)planes), dim3(kExactThreads), 0, stream>>>(ep);
     err = cudaGetLastError();
     if (err != cudaSuccess) return (int)err;
+    if (marks) cudaEventRecord(marks[2], stream);
   }
 
   TailParams tp;
@@ -962,6 +1057,7 @@ int launch_decode(const SdnetDecodeParams* p, cudaStream_t stream) {
   tp.exact_flags = reinterpret_cast<const int*>(base + ws.off_flags);
   sdnet_tail_kernel<<<dim3((unsigned)p->B), dim3(kTailThreads), 0, stream>>>(tp);
   err = cudaGetLastError();
+  if (marks) cudaEventRecord(marks[3], stream);
   return (int)err;
 }
 
@@ -998,6 +1094,29 @@ int sdnet_decode_launch(const SdnetDecodeParams* params, void* stream) {
   const int rc = validate(params);
   if (rc) return rc;
   return launch_decode(params, static_cast<cudaStream_t>(stream));
+}
+
+int sdnet_decode_launch_timed(const SdnetDecodeParams* params, void* stream_v, float* kernel_ms) {
+  const int rc = validate(params);
+  if (rc) return rc;
+  if (!kernel_ms) return SDNET_E_NULL;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  cudaEvent_t marks[4];
+  for (int i = 0; i < 4; ++i) {
+    cudaError_t e = cudaEventCreate(&marks[i]);
+    if (e != cudaSuccess) return (int)e;
+  }
+  int out = launch_decode(params, stream, marks);
+  if (out == 0) {
+    cudaError_t e = cudaEventSynchronize(marks[3]);
+    if (e != cudaSuccess) out = (int)e;
+    for (int i = 0; i < 3 && out == 0; ++i) {
+      e = cudaEventElapsedTime(&kernel_ms[i], marks[i], marks[i + 1]);
+      if (e != cudaSuccess) out = (int)e;
+    }
+  }
+  for (int i = 0; i < 4; ++i) cudaEventDestroy(marks[i]);
+  return out;
 }
 
 int sdnet_activate_launch(const SdnetTensor4* in, int dtype, int B, int C, int H, int W, float* out, void* stream) {

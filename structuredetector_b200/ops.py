@@ -139,6 +139,15 @@ class DecodePlan:
         _native.check(rc, "sdnet_decode_launch")
         return self.out
 
+    def run_timed(self, anchor_hm, part_hm, offsets, embeddings, conf_f32, dist_abs_f32, radius=2, flags=0):
+        """Synchronous profiling run: returns (peaks_ms, exact_select_ms, tail_ms) device times."""
+        self._bind_inputs(anchor_hm, part_hm, offsets, embeddings, conf_f32, dist_abs_f32, radius, flags)
+        ms = (ctypes.c_float * 3)()
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        rc = self.lib.sdnet_decode_launch_timed(ctypes.byref(self.params), ctypes.c_void_p(stream), ms)
+        _native.check(rc, "sdnet_decode_launch_timed")
+        return tuple(float(x) for x in ms)
+
     def run_host(self, anchor_hm, part_hm, offsets, embeddings, conf_f32, dist_abs_f32, staging: torch.Tensor,
                  radius=2, flags=0, stream: int | None = None) -> PackedDetections:
         """Same, with the four inputs in pinned HOST memory (``sdnet_decode_host_launch``)."""
