@@ -42,7 +42,6 @@ typedef unsigned int u32;
 constexpr int kThreads = 256;          // peaks kernel CTA
 constexpr int kWarps = kThreads / 32;
 constexpr int kPanelW = 128;           // columns per warp (32 lanes x 4)
-constexpr int kRing = 8;               // rows held in registers per lane
 constexpr int kBins = 128;             // per-warp logit histogram used for pruning
 constexpr float kBinLo = -16.0f;
 constexpr float kBinScale = 4.0f;      // bins of 0.25 logit
@@ -105,69 +104,78 @@ __device__ __forceinline__ float comp(const float4& v, int j) {
 // ---------------------------------------------------------------------------------------------
 constexpr int kStages = 8;             // ring depth (power of two); kStages - 1 - 2R rows stay in flight
 constexpr int kPitch = 136;            // floats per ring row
-constexpr int kPeaksSmemPerWarp = kStages * kPitch * 4 + kBins * 8;
+constexpr int kPitchB = kPitch * 4;
+constexpr int kBuf = 64;               // per-warp candidate buffer (records), flushed at >= 32
+constexpr int kPeaksSmemPerWarp = kStages * kPitchB + kBins * 8 + kBuf * 8;
 constexpr int kPeaksSmem = kWarps * kPeaksSmemPerWarp;
 
 __device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void cp_async16(float* dst, const float* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src));
+// predicated cp.async: global -> shared, no register staging
+__device__ __forceinline__ void cp_async16_if(u32 dst, const void* src, bool pred) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p cp.async.cg.shared.global [%0], [%1], 16;\n\t}"
+               ::"r"(dst), "l"(src), "r"((int)pred));
 }
-__device__ __forceinline__ void cp_async8(float* dst, const float* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src));
+__device__ __forceinline__ void cp_async8_if(u32 dst, const void* src, bool pred) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p cp.async.ca.shared.global [%0], [%1], 8;\n\t}"
+               ::"r"(dst), "l"(src), "r"((int)pred));
 }
-__device__ __forceinline__ void cp_async4(float* dst, const float* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src));
+__device__ __forceinline__ void cp_async4_if(u32 dst, const void* src, bool pred) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p cp.async.ca.shared.global [%0], [%1], 4;\n\t}"
+               ::"r"(dst), "l"(src), "r"((int)pred));
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ float4 lds128(u32 addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float2 lds64(u32 addr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(u32 addr, float a) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %1, %1, %1};" ::"r"(addr), "f"(a) : "memory");
+}
+__device__ __forceinline__ void sts64(u32 addr, float a) {
+  asm volatile("st.shared.v2.f32 [%0], {%1, %1};" ::"r"(addr), "f"(a) : "memory");
+}
 
-// Start the copy of one row of the panel into ring slot `dst` (or fill it with -inf when the row
-// lies outside the image: max_pool2d pads with -inf).  Always closes one cp.async group.
+// Per-lane addressing of one warp-unit's ring traffic, set up once per unit.
+struct RowCopier {
+  const char* gown;   // this lane's 16 B of the next row to copy
+  const char* ghalo;  // lane 0: the two columns left of the panel; lane 31: the two right of it
+  long long pitch;    // bytes between rows in global memory
+  u32 s_own, s_halo;  // shared-memory byte addresses inside ring slot 0
+  u32 own_ok;         // aligned: 0/1; unaligned: bit j = column col0+j is inside the image
+  u32 halo_ok;        // aligned: 0/1; unaligned: bit j = halo column j is inside the image
+};
+
+// Start the copy of the next row into ring slot `slot` (or fill it with -inf when the row lies
+// outside the image: max_pool2d pads with -inf).  Always closes one cp.async group.
 template <bool kAligned>
-__device__ __forceinline__ void issue_row(float* dst, const float* __restrict__ plane, long long sh, int row, int H,
-                                          int W, int col0, int lane, int panel_col0, bool wanted) {
-  const float ninf = -CUDART_INF_F;
+__device__ __forceinline__ void issue_row(RowCopier& rc, int slot, bool wanted, bool row_inside, int lane) {
   if (wanted) {  // warp-uniform
-    float* own = dst + 4 + 4 * lane;
-    if (row >= 0 && row < H) {
-      const float* rp = plane + (long long)row * sh;
+    const u32 so = rc.s_own + slot * kPitchB, sh = rc.s_halo + slot * kPitchB;
+    if (row_inside) {  // warp-uniform
       if (kAligned) {
-        if (col0 < W) cp_async16(own, rp + col0);
-        else *reinterpret_cast<float4*>(own) = make_float4(ninf, ninf, ninf, ninf);
-        if (lane == 0) {
-          if (panel_col0 > 0) cp_async8(dst + 2, rp + panel_col0 - 2);
-          else *reinterpret_cast<float2*>(dst + 2) = make_float2(ninf, ninf);
-        } else if (lane == 31) {
-          if (panel_col0 + kPanelW < W) cp_async8(dst + 4 + kPanelW, rp + panel_col0 + kPanelW);
-          else *reinterpret_cast<float2*>(dst + 4 + kPanelW) = make_float2(ninf, ninf);
-        }
+        cp_async16_if(so, rc.gown, rc.own_ok != 0);
+        cp_async8_if(sh, rc.ghalo, rc.halo_ok != 0);
       } else {
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          if (col0 + jj < W) cp_async4(own + jj, rp + col0 + jj);
-          else own[jj] = ninf;
-        }
-        if (lane == 0) {
+        for (int jj = 0; jj < 4; ++jj) cp_async4_if(so + 4 * jj, rc.gown + 4 * jj, (rc.own_ok >> jj) & 1u);
 #pragma unroll
-          for (int jj = 0; jj < 2; ++jj) {
-            if (panel_col0 - 2 + jj >= 0) cp_async4(dst + 2 + jj, rp + panel_col0 - 2 + jj);
-            else dst[2 + jj] = ninf;
-          }
-        } else if (lane == 31) {
-#pragma unroll
-          for (int jj = 0; jj < 2; ++jj) {
-            if (panel_col0 + kPanelW + jj < W) cp_async4(dst + 4 + kPanelW + jj, rp + panel_col0 + kPanelW + jj);
-            else dst[4 + kPanelW + jj] = ninf;
-          }
-        }
+        for (int jj = 0; jj < 2; ++jj) cp_async4_if(sh + 4 * jj, rc.ghalo + 4 * jj, (rc.halo_ok >> jj) & 1u);
       }
     } else {
-      *reinterpret_cast<float4*>(own) = make_float4(ninf, ninf, ninf, ninf);
-      if (lane == 0) *reinterpret_cast<float2*>(dst + 2) = make_float2(ninf, ninf);
-      if (lane == 31) *reinterpret_cast<float2*>(dst + 4 + kPanelW) = make_float2(ninf, ninf);
+      sts128(so, -CUDART_INF_F);
+      if (lane == 0 || lane == 31) sts64(sh, -CUDART_INF_F);
     }
   }
+  rc.gown += rc.pitch;
+  rc.ghalo += rc.pitch;
   cp_async_commit();
 }
 
@@ -232,18 +240,79 @@ __device__ __forceinline__ float shared_floor(int gbin, float xscale) {
   return edge - kNearTie;
 }
 
+// Flush the warp's candidate buffer: evaluate the exact score of up to 64 buffered pixels (all
+// lanes busy), append (score, index) records to the plane's list with one atomic, feed the
+// warp-local and plane-wide histograms and raise the pruning floor.
+struct UnitState {
+  float floorx;   // input units; a pixel can still matter only if min(x, satx) > floorx
+  u32 emitted;    // records this unit has appended so far
+  int nbuf;       // records waiting in the shared-memory buffer
+};
+
+__device__ __forceinline__ void flush_candidates(UnitState& st, const u64* buf, u32* hist, int* minx, u32* ghist,
+                                                 int* gfloor_ptr, int* count_ptr, u64* __restrict__ list, int cap,
+                                                 int K, int lane, bool pre, float xscale, float satx) {
+  const int n = st.nbuf;  // warp-uniform, 1..kBuf
+  int base = 0;
+  if (lane == 0) base = atomicAdd(count_ptr, n);
+  base = __shfl_sync(0xffffffffu, base, 0);
+#pragma unroll
+  for (int half = 0; half < kBuf / 32; ++half) {
+    const int i = half * 32 + lane;
+    if (half * 32 < n) {  // warp-uniform
+      const bool valid = i < n;
+      const u64 rec = valid ? buf[i] : 0ull;
+      const float x = __uint_as_float((u32)(rec >> 32));
+      u32 key;
+      if (pre) {
+        const u32 bits = __float_as_uint(x);
+        key = (bits & 0x80000000u) ? ~bits : (bits | 0x80000000u);
+      } else {
+        key = __float_as_uint(activate(x));
+      }
+      if (valid) {
+        if (base + i < cap) list[base + i] = ((u64)key << 32) | (u32)rec;
+        // clamped logit: the score is a monotone function of it, saturation included
+        const float xe = fminf(fmaxf(x * xscale, -satx), satx);
+        const int bin = logit_bin(xe);
+        atomicAdd(&hist[bin], 1u);
+        atomicMin(&minx[bin], ord_of(xe));
+        atomicAdd(&ghist[bin], 1u);
+      }
+    }
+  }
+  st.emitted += n;
+  st.nbuf = 0;
+  __syncwarp();
+  // xscale is a power of two, so the division is exact
+  if (st.emitted >= (u32)K) st.floorx = fmaxf(st.floorx, local_floor(hist, minx, lane, K) / xscale);
+  // publish / refresh the plane-wide floor
+  const uint4 gc = __ldcg(reinterpret_cast<const uint4*>(ghist + 4 * lane));
+  const int gb = floor_bin_of(gc, lane, K);
+  if (gb > 0) {
+    if (lane == 0) atomicMax(gfloor_ptr, gb);
+    st.floorx = fmaxf(st.floorx, shared_floor(gb, xscale));
+  }
+}
+
 template <bool kAligned, int R>
 __global__ void __launch_bounds__(kThreads, 4) sdnet_peaks_kernel(const __grid_constant__ PeaksParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  float* ring = reinterpret_cast<float*>(smem_raw + (size_t)warp * kPeaksSmemPerWarp);
-  u32* hist = reinterpret_cast<u32*>(ring + kStages * kPitch);
+  unsigned char* wbase = smem_raw + (size_t)warp * kPeaksSmemPerWarp;
+  const u32 ring_s = smem_u32(wbase);
+  u32* hist = reinterpret_cast<u32*>(wbase + kStages * kPitchB);
   int* minx = reinterpret_cast<int*>(hist + kBins);
-  const float xscale = p.pre_activated ? kPreScale : 1.0f;
-  const float satx = p.pre_activated ? CUDART_INF_F : kSatX;
+  u64* buf = reinterpret_cast<u64*>(minx + kBins);
+  const bool pre = p.pre_activated != 0;
+  const float xscale = pre ? kPreScale : 1.0f;
+  const float satx = pre ? CUDART_INF_F : kSatX;
   const int C = p.M + p.N;
+  const int H = p.H, W = p.W;
   constexpr int kPending = kStages - 1 - 2 * R;  // cp.async groups allowed in flight at the wait
+  const u32 s_own0 = ring_s + (4 + 4 * lane) * 4;
+  const u32 s_halo0 = ring_s + (lane == 31 ? 4 + kPanelW : 2) * 4;
 
   for (;;) {
     u32 unit = 0;
@@ -258,9 +327,7 @@ __global__ void __launch_bounds__(kThreads, 4) sdnet_peaks_kernel(const __grid_c
     const bool is_anchor = c < p.M;
     const View4& vw = is_anchor ? p.anchor : p.part;
     const float* __restrict__ plane = vw.data + (long long)b * vw.sb + (long long)(is_anchor ? c : c - p.M) * vw.sc;
-    const long long sh = vw.sh;
     const int K = is_anchor ? p.K : p.P;
-    const int H = p.H, W = p.W;
     const int panel_col0 = panel * kPanelW;
     const int col0 = panel_col0 + lane * 4;
     const int r_begin = strip * p.rows_per_strip;
@@ -272,43 +339,66 @@ __global__ void __launch_bounds__(kThreads, 4) sdnet_peaks_kernel(const __grid_c
     u32* ghist = p.ghist + (size_t)plane_id * kBins;
     int* gfloor_ptr = p.gfloor + plane_id;
 
-    // per-unit pruning state (warp-uniform).  Input units; a pixel can still matter only if
-    // min(x, satx) > floorx.
-    float floorx = shared_floor(__ldcg(gfloor_ptr), xscale);
-    u32 emitted = 0;
-    __syncwarp();  // everyone is done with the previous unit's ring and histogram
+    UnitState st;
+    st.floorx = shared_floor(__ldcg(gfloor_ptr), xscale);
+    st.emitted = 0;
+    st.nbuf = 0;
+
+    RowCopier rc;
+    const int halo_col = lane == 31 ? panel_col0 + kPanelW : panel_col0 - 2;
+    rc.pitch = vw.sh * 4;
+    rc.gown = reinterpret_cast<const char*>(plane + (long long)(r_begin - R) * vw.sh + col0);
+    rc.ghalo = reinterpret_cast<const char*>(plane + (long long)(r_begin - R) * vw.sh + halo_col);
+    rc.s_own = s_own0;
+    rc.s_halo = s_halo0;
+    if (kAligned) {
+      rc.own_ok = col0 < W ? 1u : 0u;
+      rc.halo_ok = ((lane == 0 && panel_col0 > 0) || (lane == 31 && panel_col0 + kPanelW < W)) ? 1u : 0u;
+    } else {
+      rc.own_ok = 0;
+      for (int jj = 0; jj < 4; ++jj) rc.own_ok |= (col0 + jj < W ? 1u : 0u) << jj;
+      rc.halo_ok = 0;
+      if (lane == 0 || lane == 31)
+        for (int jj = 0; jj < 2; ++jj) rc.halo_ok |= ((halo_col + jj >= 0 && halo_col + jj < W) ? 1u : 0u) << jj;
+    }
+
+    __syncwarp();  // everyone is done with the previous unit's ring, histogram and buffer
     *reinterpret_cast<uint4*>(hist + 4 * lane) = make_uint4(0, 0, 0, 0);
     *reinterpret_cast<int4*>(minx + 4 * lane) = make_int4(0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff);
+    // columns outside the image never receive a copy: park -inf there once for the whole unit
+#pragma unroll
+    for (int sl = 0; sl < kStages; ++sl) {
+      sts128(s_own0 + sl * kPitchB, -CUDART_INF_F);
+      if (lane == 0 || lane == 31) sts64(s_halo0 + sl * kPitchB, -CUDART_INF_F);
+    }
+    __syncwarp();
 
     // ring sequence number q <-> image row r_begin - R + q, slot q % kStages
 #pragma unroll
     for (int q = 0; q < kStages - 1; ++q)
-      issue_row<kAligned>(ring + q * kPitch, plane, sh, r_begin - R + q, H, W, col0, lane, panel_col0, q <= q_last);
+      issue_row<kAligned>(rc, q, q <= q_last, (unsigned)(r_begin - R + q) < (unsigned)H, lane);
 
     for (int t = 0; t < nrows; ++t) {
       {  // the slot of sequence number t-1 is free: every lane passed a warp-wide vote after reading it
         const int q = t + kStages - 1;
-        issue_row<kAligned>(ring + (q & (kStages - 1)) * kPitch, plane, sh, r_begin - R + q, H, W, col0, lane,
-                            panel_col0, q <= q_last);
+        issue_row<kAligned>(rc, q & (kStages - 1), q <= q_last, (unsigned)(r_begin - R + q) < (unsigned)H, lane);
       }
       cp_async_wait<kPending>();
       __syncwarp();
-      const float* crow = ring + ((t + R) & (kStages - 1)) * kPitch + 4 + 4 * lane;
-      const float4 ctr = *reinterpret_cast<const float4*>(crow);
+      const float4 ctr = lds128(s_own0 + ((t + R) & (kStages - 1)) * kPitchB);
       const float m4 = fmaxf(fmaxf(ctr.x, ctr.y), fmaxf(ctr.z, ctr.w));
-      if (__any_sync(0xffffffffu, fminf(m4, satx) > floorx)) {
-        const int row = r_begin + t;
-        u32 ekey0 = 0, ekey1 = 0, ekey2 = 0, ekey3 = 0;
-        if (!p.pre_activated) {
+      if (__any_sync(0xffffffffu, fminf(m4, satx) > st.floorx)) {
+        const float floorx = st.floorx;
+        u32 cmask = 0;  // bit j: pixel col0+j goes to the candidate buffer
+        if (!pre) {
           // vertical (2R+1)-max of own columns and of this lane's halo pair (lanes 0 / 31 only)
-          const int hoff = lane == 31 ? 4 + kPanelW : 2;
           float4 v = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
           float2 hvv = make_float2(-CUDART_INF_F, -CUDART_INF_F);
 #pragma unroll
           for (int d = 0; d <= 2 * R; ++d) {
-            const float* rowp = ring + ((t + d) & (kStages - 1)) * kPitch;
-            const float4 o = *reinterpret_cast<const float4*>(rowp + 4 + 4 * lane);
-            const float2 ho = *reinterpret_cast<const float2*>(rowp + hoff);
+            const u32 so = ((t + d) & (kStages - 1)) * kPitchB;
+            const float4 o = lds128(s_own0 + so);
+            const float2 ho = lds64(s_halo0 + so);
             v.x = fmaxf(v.x, o.x); v.y = fmaxf(v.y, o.y); v.z = fmaxf(v.z, o.z); v.w = fmaxf(v.w, o.w);
             hvv.x = fmaxf(hvv.x, ho.x); hvv.y = fmaxf(hvv.y, ho.y);
           }
@@ -331,88 +421,66 @@ __global__ void __launch_bounds__(kThreads, 4) sdnet_peaks_kernel(const __grid_c
             h2 = max3(v.y, v.z, v.w);
             h3 = max3(v.z, v.w, R0);
           }
-          // cheap per-pixel predicate: above the floor and within a hair of the window maximum
-          u32 cmask = 0;
-#define SDNET_NEAR(x, h) (((x) >= (h) - kNearTie) || ((h) > kHiZone && (x) > kHiZone - 1.0f) || ((h) < kLoZone))
-          if (col0 + 0 < W && fminf(ctr.x, satx) > floorx && SDNET_NEAR(ctr.x, h0)) cmask |= 1u;
-          if (col0 + 1 < W && fminf(ctr.y, satx) > floorx && SDNET_NEAR(ctr.y, h1)) cmask |= 2u;
-          if (col0 + 2 < W && fminf(ctr.z, satx) > floorx && SDNET_NEAR(ctr.z, h2)) cmask |= 4u;
-          if (col0 + 3 < W && fminf(ctr.w, satx) > floorx && SDNET_NEAR(ctr.w, h3)) cmask |= 8u;
-#undef SDNET_NEAR
-          // exact check, one pixel per lane per round, no divergence (idle lanes compute on 0)
-          while (__any_sync(0xffffffffu, cmask != 0)) {
-            const bool has = cmask != 0;
-            const int jj = has ? __ffs(cmask) - 1 : 0;
+          // bit j   : pixel equals its window maximum -> certainly survives NMS
+          // bit 4+j : pixel is below the maximum but so close that the two scores may round equal
+          u32 amb = 0;
+#define SDNET_CLASSIFY(x, h, j)                                                                        \
+  if (col0 + j < W && fminf(x, satx) > floorx) {                                                       \
+    if ((x) == (h)) cmask |= 1u << j;                                                                  \
+    else if (((x) >= (h) - kNearTie) || ((h) > kHiZone && (x) > kHiZone - 1.0f) || ((h) < kLoZone))     \
+      amb |= 1u << j;                                                                                  \
+  }
+          SDNET_CLASSIFY(ctr.x, h0, 0)
+          SDNET_CLASSIFY(ctr.y, h1, 1)
+          SDNET_CLASSIFY(ctr.z, h2, 2)
+          SDNET_CLASSIFY(ctr.w, h3, 3)
+#undef SDNET_CLASSIFY
+          // rare: resolve the ambiguous pixels with the exact score function, one per lane per round
+          while (__any_sync(0xffffffffu, amb != 0)) {
+            const bool has = amb != 0;
+            const int jj = has ? __ffs(amb) - 1 : 0;
             const float x = jj == 0 ? ctr.x : (jj == 1 ? ctr.y : (jj == 2 ? ctr.z : ctr.w));
             const float h = jj == 0 ? h0 : (jj == 1 ? h1 : (jj == 2 ? h2 : h3));
-            const float sx = activate(has ? x : 0.0f);
-            bool peak = has && (x == h);
-            const bool second = has && !peak;
-            if (__any_sync(0xffffffffu, second)) peak = peak || (second && sx == activate(h));
-            const u32 key = peak ? __float_as_uint(sx) : 0u;
-            if (has) {
-              if (jj == 0) ekey0 = key; else if (jj == 1) ekey1 = key; else if (jj == 2) ekey2 = key; else ekey3 = key;
-            }
-            cmask &= cmask - 1;
+            if (has && activate(x) == activate(h)) cmask |= 1u << jj;
+            amb &= amb - 1;
           }
         } else {
-          // pre-activated maps (CoreMLDecoder): every pixel is a candidate with its own value.
-          // Values are scores in [0, 1]; the order-preserving key below also handles negatives.
-#define SDNET_PKEY(x) ((__float_as_uint(x) & 0x80000000u) ? ~__float_as_uint(x) : (__float_as_uint(x) | 0x80000000u))
-          if (col0 + 0 < W && ctr.x > floorx) ekey0 = SDNET_PKEY(ctr.x);
-          if (col0 + 1 < W && ctr.y > floorx) ekey1 = SDNET_PKEY(ctr.y);
-          if (col0 + 2 < W && ctr.z > floorx) ekey2 = SDNET_PKEY(ctr.z);
-          if (col0 + 3 < W && ctr.w > floorx) ekey3 = SDNET_PKEY(ctr.w);
-#undef SDNET_PKEY
+          // pre-activated maps (CoreMLDecoder): every pixel above the floor is a candidate
+          if (col0 + 0 < W && ctr.x > floorx) cmask |= 1u;
+          if (col0 + 1 < W && ctr.y > floorx) cmask |= 2u;
+          if (col0 + 2 < W && ctr.z > floorx) cmask |= 4u;
+          if (col0 + 3 < W && ctr.w > floorx) cmask |= 8u;
         }
-        const u32 m0 = __ballot_sync(0xffffffffu, ekey0 != 0);
-        const u32 m1 = __ballot_sync(0xffffffffu, ekey1 != 0);
-        const u32 m2 = __ballot_sync(0xffffffffu, ekey2 != 0);
-        const u32 m3 = __ballot_sync(0xffffffffu, ekey3 != 0);
-        const u32 total = __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
-        if (total) {  // warp-uniform
-          int base = 0;
-          if (lane == 0) base = atomicAdd(count_ptr, (int)total);
-          base = __shfl_sync(0xffffffffu, base, 0);
-          const u32 lt = (1u << lane) - 1u;
-          // lane-major order inside the row: position = records of lower lanes + own earlier columns
-          int pos = base + __popc(m0 & lt) + __popc(m1 & lt) + __popc(m2 & lt) + __popc(m3 & lt);
+        // append (logit, index) to the warp's buffer, one column at a time
+        const u32 idx0 = (u32)((r_begin + t) * W + col0);
 #pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {
-            const u32 key = jj == 0 ? ekey0 : (jj == 1 ? ekey1 : (jj == 2 ? ekey2 : ekey3));
-            if (key) {
-              const u32 idx = (u32)(row * W + col0 + jj);
-              if (pos < p.cap) list[pos] = ((u64)key << 32) | idx;
-              ++pos;
-              // clamped logit: the score is a monotone function of it, saturation included
-              const float xe = fminf(fmaxf(comp(ctr, jj) * xscale, -satx), satx);
-              const int bin = logit_bin(xe);
-              atomicAdd(&hist[bin], 1u);
-              atomicMin(&minx[bin], ord_of(xe));
-              atomicAdd(&ghist[bin], 1u);
+        for (int jj = 0; jj < 4; ++jj) {
+          const bool mine = (cmask >> jj) & 1u;
+          const u32 m = __ballot_sync(0xffffffffu, mine);
+          if (m) {  // warp-uniform
+            if (st.nbuf > kBuf - 32) {
+              __syncwarp();
+              flush_candidates(st, buf, hist, minx, ghist, gfloor_ptr, count_ptr, list, p.cap, K, lane, pre, xscale, satx);
             }
+            if (mine) buf[st.nbuf + __popc(m & ((1u << lane) - 1u))] = ((u64)__float_as_uint(comp(ctr, jj)) << 32) | (idx0 + jj);
+            st.nbuf += __popc(m);
           }
-          emitted += total;
+        }
+        if (st.nbuf >= 32) {
           __syncwarp();
-          if (emitted >= (u32)K) {
-            // xscale is a power of two, so the division is exact
-            floorx = fmaxf(floorx, local_floor(hist, minx, lane, K) / xscale);
-          }
-          // publish / refresh the plane-wide floor
-          const uint4 gc = __ldcg(reinterpret_cast<const uint4*>(ghist + 4 * lane));
-          const int gb = floor_bin_of(gc, lane, K);
-          if (gb > 0) {
-            if (lane == 0) atomicMax(gfloor_ptr, gb);
-            floorx = fmaxf(floorx, shared_floor(gb, xscale));
-          }
+          flush_candidates(st, buf, hist, minx, ghist, gfloor_ptr, count_ptr, list, p.cap, K, lane, pre, xscale, satx);
         }
       }
       if ((t & 7) == 7) {
         // every 8 rows: pick up the plane-wide floor other warps may have raised
-        floorx = fmaxf(floorx, shared_floor(__ldcg(gfloor_ptr), xscale));
+        st.floorx = fmaxf(st.floorx, shared_floor(__ldcg(gfloor_ptr), xscale));
       }
     }
     cp_async_wait<0>();
+    if (st.nbuf) {
+      __syncwarp();
+      flush_candidates(st, buf, hist, minx, ghist, gfloor_ptr, count_ptr, list, p.cap, K, lane, pre, xscale, satx);
+    }
   }
 }
 
