@@ -36,6 +36,7 @@ extern "C" {
 #define SDNET_FLAG_PRE_ACTIVATED 1u /* heat maps already sigmoid+NMS'd: decoders.py:211,226 (CoreMLDecoder) */
 #define SDNET_FLAG_NO_GROUPING 2u   /* skip part->anchor grouping: decoders.py:345-423 (KeypointDecoder) */
 #define SDNET_FLAG_EXACT_SELECT 4u  /* route every plane through the bounded-memory exact select (testing) */
+#define SDNET_FLAG_WARP_KERNEL 8u   /* use the any-alignment per-warp peaks kernel even when the TMA one applies (testing) */
 
 /* argument errors */
 #define SDNET_E_NULL -1      /* a required pointer is NULL */

@@ -15,6 +15,7 @@ ABI_VERSION = 1
 FLAG_PRE_ACTIVATED = 1
 FLAG_NO_GROUPING = 2
 FLAG_EXACT_SELECT = 4
+FLAG_WARP_KERNEL = 8
 DTYPE_F32 = 0
 MAX_TOPK = 1024
 MAX_CHANNELS = 255

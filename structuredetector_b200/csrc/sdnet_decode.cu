@@ -31,6 +31,7 @@
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "sdnet_decode.h"
 
@@ -106,7 +107,7 @@ constexpr int kStages = 8;             // ring depth (power of two); kStages - 1
 constexpr int kPitch = 136;            // floats per ring row
 constexpr int kPitchB = kPitch * 4;
 constexpr int kBuf = 64;               // per-warp candidate buffer (records), flushed at >= 32
-constexpr int kPeaksSmemPerWarp = kStages * kPitchB + kBins * 8 + kBuf * 8;
+constexpr int kPeaksSmemPerWarp = kStages * kPitchB + kBins * 8 + kBuf * 8 + kStages * 8;
 constexpr int kPeaksSmem = kWarps * kPeaksSmemPerWarp;
 
 __device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
@@ -143,41 +144,90 @@ __device__ __forceinline__ void sts64(u32 addr, float a) {
   asm volatile("st.shared.v2.f32 [%0], {%1, %1};" ::"r"(addr), "f"(a) : "memory");
 }
 
-// Per-lane addressing of one warp-unit's ring traffic, set up once per unit.
-struct RowCopier {
-  const char* gown;   // this lane's 16 B of the next row to copy
-  const char* ghalo;  // lane 0: the two columns left of the panel; lane 31: the two right of it
-  long long pitch;    // bytes between rows in global memory
-  u32 s_own, s_halo;  // shared-memory byte addresses inside ring slot 0
-  u32 own_ok;         // aligned: 0/1; unaligned: bit j = column col0+j is inside the image
-  u32 halo_ok;        // aligned: 0/1; unaligned: bit j = halo column j is inside the image
-};
-
-// Start the copy of the next row into ring slot `slot` (or fill it with -inf when the row lies
-// outside the image: max_pool2d pads with -inf).  Always closes one cp.async group.
-template <bool kAligned>
-__device__ __forceinline__ void issue_row(RowCopier& rc, int slot, bool wanted, bool row_inside, int lane) {
-  if (wanted) {  // warp-uniform
-    const u32 so = rc.s_own + slot * kPitchB, sh = rc.s_halo + slot * kPitchB;
-    if (row_inside) {  // warp-uniform
-      if (kAligned) {
-        cp_async16_if(so, rc.gown, rc.own_ok != 0);
-        cp_async8_if(sh, rc.ghalo, rc.halo_ok != 0);
-      } else {
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) cp_async4_if(so + 4 * jj, rc.gown + 4 * jj, (rc.own_ok >> jj) & 1u);
-#pragma unroll
-        for (int jj = 0; jj < 2; ++jj) cp_async4_if(sh + 4 * jj, rc.ghalo + 4 * jj, (rc.halo_ok >> jj) & 1u);
-      }
-    } else {
-      sts128(so, -CUDART_INF_F);
-      if (lane == 0 || lane == 31) sts64(sh, -CUDART_INF_F);
-    }
-  }
-  rc.gown += rc.pitch;
-  rc.ghalo += rc.pitch;
-  cp_async_commit();
+// ---- mbarrier + 1-D bulk copy (TMA unit; SASS: UBLKCP, SYNCS) ---------------------------------
+__device__ __forceinline__ void mbar_init(u32 bar, u32 count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(u32 bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(u32 bar, u32 bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u32 bar, u32 parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@!p bra WAIT_LOOP;\n\t}"
+      ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_g2s(u32 dst, const void* src, u32 bytes, u32 bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// Feeds one warp's ring in the fallback kernel: every lane copies its own four columns with
+// 4-byte cp.async (any alignment).  Ring sequence number q of a unit <-> image row row0 + q.
+template <bool kBulk>
+struct RowFeed;
+
+template <>
+struct RowFeed<false> {
+  u32 ring_s, base;
+  const char* gown;
+  const char* ghalo;
+  long long pitch;
+  u32 s_own, s_halo, own_ok, halo_ok;
+  int row0, H, q_last;
+
+  __device__ __forceinline__ void init(u32 ring, u32, int lane) {
+    ring_s = ring; base = 0;
+    s_own = ring + (4 + 4 * lane) * 4;
+    s_halo = ring + (lane == 31 ? 4 + kPanelW : 2) * 4;
+  }
+  __device__ __forceinline__ void begin_unit(const float* plane, long long sh, int r0, int H_, int W, int panel_col0,
+                                             int q_last_, int lane) {
+    row0 = r0; H = H_; q_last = q_last_;
+    const int col0 = panel_col0 + 4 * lane;
+    const int halo_col = lane == 31 ? panel_col0 + kPanelW : panel_col0 - 2;
+    pitch = sh * 4;
+    gown = reinterpret_cast<const char*>(plane + (long long)r0 * sh + col0);
+    ghalo = reinterpret_cast<const char*>(plane + (long long)r0 * sh + halo_col);
+    own_ok = 0;
+    for (int jj = 0; jj < 4; ++jj) own_ok |= (col0 + jj < W ? 1u : 0u) << jj;
+    halo_ok = 0;
+    if (lane == 0 || lane == 31)
+      for (int jj = 0; jj < 2; ++jj) halo_ok |= ((halo_col + jj >= 0 && halo_col + jj < W) ? 1u : 0u) << jj;
+    for (int i = lane; i < kStages * kPitch / 4; i += 32) sts128(ring_s + 16 * i, -CUDART_INF_F);
+    __syncwarp();
+  }
+  __device__ __forceinline__ u32 slot_addr(int q) const { return ring_s + (q & (kStages - 1)) * kPitchB; }
+  __device__ __forceinline__ void issue(int q, int lane) {
+    if (q <= q_last) {
+      const u32 so = s_own + (q & (kStages - 1)) * kPitchB, sh = s_halo + (q & (kStages - 1)) * kPitchB;
+      if ((unsigned)(row0 + q) < (unsigned)H) {
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) cp_async4_if(so + 4 * jj, gown + 4 * jj, (own_ok >> jj) & 1u);
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) cp_async4_if(sh + 4 * jj, ghalo + 4 * jj, (halo_ok >> jj) & 1u);
+      } else {
+        sts128(so, -CUDART_INF_F);
+        if (lane == 0 || lane == 31) sts64(sh, -CUDART_INF_F);
+      }
+    }
+    gown += pitch;
+    ghalo += pitch;
+    cp_async_commit();
+  }
+  // cp.async groups complete in order: allowing kStages-1-2R groups in flight means the row
+  // two below the centre has landed
+  template <int R>
+  __device__ __forceinline__ void wait_step() const { cp_async_wait<kStages - 1 - 2 * R>(); }
+  __device__ __forceinline__ void end_unit() { cp_async_wait<0>(); }
+};
 
 __device__ __forceinline__ int logit_bin(float x) {
   int bin = __float2int_rd((x - kBinLo) * kBinScale);
@@ -244,7 +294,7 @@ __device__ __forceinline__ float shared_floor(int gbin, float xscale) {
 // lanes busy), append (score, index) records to the plane's list with one atomic, feed the
 // warp-local and plane-wide histograms and raise the pruning floor.
 struct UnitState {
-  float floorx;   // input units; a pixel can still matter only if min(x, satx) > floorx
+  float floorx;   // input units; a pixel can still matter only if x > floorx
   u32 emitted;    // records this unit has appended so far
   int nbuf;       // records waiting in the shared-memory buffer
 };
@@ -293,6 +343,65 @@ __device__ __forceinline__ void flush_candidates(UnitState& st, const u64* buf, 
     if (lane == 0) atomicMax(gfloor_ptr, gb);
     st.floorx = fmaxf(st.floorx, shared_floor(gb, xscale));
   }
+  // a floor at the saturation clamp means "nothing can beat what we have": every x >= satx has
+  // the same score as the K recorded ones and a higher index
+  if (st.floorx >= satx) st.floorx = CUDART_INF_F;
+}
+
+// Which of a lane's four pixels survive NMS, given their window maxima h0..h3 (logit space).
+//   x == h            -> certainly survives;
+//   x <  h but so close that the two scores may round equal -> settled with the exact score.
+// Columns outside the image hold -inf and never pass x > floorx.
+template <int R>
+__device__ __forceinline__ u32 classify_row(const float4 ctr, float h0, float h1, float h2, float h3, float floorx) {
+  u32 cmask = 0, amb = 0;
+#define SDNET_CLASSIFY(x, h, j)                                                                        \
+  if ((x) > floorx) {                                                                                  \
+    if ((x) == (h)) cmask |= 1u << j;                                                                  \
+    else if (((x) >= (h) - kNearTie) || ((h) > kHiZone && (x) > kHiZone - 1.0f) || ((h) < kLoZone))     \
+      amb |= 1u << j;                                                                                  \
+  }
+  SDNET_CLASSIFY(ctr.x, h0, 0)
+  SDNET_CLASSIFY(ctr.y, h1, 1)
+  SDNET_CLASSIFY(ctr.z, h2, 2)
+  SDNET_CLASSIFY(ctr.w, h3, 3)
+#undef SDNET_CLASSIFY
+  // rare: resolve the ambiguous pixels with the exact score function, one per lane per round
+  while (__any_sync(0xffffffffu, amb != 0)) {
+    const bool has = amb != 0;
+    const int jj = has ? __ffs(amb) - 1 : 0;
+    const float x = jj == 0 ? ctr.x : (jj == 1 ? ctr.y : (jj == 2 ? ctr.z : ctr.w));
+    const float h = jj == 0 ? h0 : (jj == 1 ? h1 : (jj == 2 ? h2 : h3));
+    if (has && activate(x) == activate(h)) cmask |= 1u << jj;
+    amb &= amb - 1;
+  }
+  return cmask;
+}
+
+// Append the selected pixels of one row as (logit, index) records to the warp's buffer, one
+// column at a time, flushing when it fills up.
+__device__ __forceinline__ void append_row(UnitState& st, u32 cmask, const float4 ctr, u32 idx0, u64* buf, u32* hist,
+                                           int* minx, u32* ghist, int* gfloor_ptr, int* count_ptr,
+                                           u64* __restrict__ list, int cap, int K, int lane, bool pre, float xscale,
+                                           float satx) {
+  if (!__any_sync(0xffffffffu, cmask != 0)) return;
+#pragma unroll
+  for (int jj = 0; jj < 4; ++jj) {
+    const bool mine = (cmask >> jj) & 1u;
+    const u32 m = __ballot_sync(0xffffffffu, mine);
+    if (m) {  // warp-uniform
+      if (st.nbuf > kBuf - 32) {
+        __syncwarp();
+        flush_candidates(st, buf, hist, minx, ghist, gfloor_ptr, count_ptr, list, cap, K, lane, pre, xscale, satx);
+      }
+      if (mine) buf[st.nbuf + __popc(m & ((1u << lane) - 1u))] = ((u64)__float_as_uint(comp(ctr, jj)) << 32) | (idx0 + jj);
+      st.nbuf += __popc(m);
+    }
+  }
+  if (st.nbuf >= 32) {
+    __syncwarp();
+    flush_candidates(st, buf, hist, minx, ghist, gfloor_ptr, count_ptr, list, cap, K, lane, pre, xscale, satx);
+  }
 }
 
 template <bool kAligned, int R>
@@ -305,14 +414,16 @@ __global__ void __launch_bounds__(kThreads, 4) sdnet_peaks_kernel(const __grid_c
   u32* hist = reinterpret_cast<u32*>(wbase + kStages * kPitchB);
   int* minx = reinterpret_cast<int*>(hist + kBins);
   u64* buf = reinterpret_cast<u64*>(minx + kBins);
+  const u32 bars_s = smem_u32(buf + kBuf);
   const bool pre = p.pre_activated != 0;
   const float xscale = pre ? kPreScale : 1.0f;
   const float satx = pre ? CUDART_INF_F : kSatX;
   const int C = p.M + p.N;
   const int H = p.H, W = p.W;
-  constexpr int kPending = kStages - 1 - 2 * R;  // cp.async groups allowed in flight at the wait
-  const u32 s_own0 = ring_s + (4 + 4 * lane) * 4;
-  const u32 s_halo0 = ring_s + (lane == 31 ? 4 + kPanelW : 2) * 4;
+  const u32 own_off = (4 + 4 * lane) * 4;                      // this lane's four columns inside a ring row
+  const u32 halo_off = (lane == 31 ? 4 + kPanelW : 2) * 4;     // the two columns beyond the panel edge
+  RowFeed<false> feed;
+  feed.init(ring_s, bars_s, lane);
 
   for (;;) {
     u32 unit = 0;
@@ -344,50 +455,21 @@ __global__ void __launch_bounds__(kThreads, 4) sdnet_peaks_kernel(const __grid_c
     st.emitted = 0;
     st.nbuf = 0;
 
-    RowCopier rc;
-    const int halo_col = lane == 31 ? panel_col0 + kPanelW : panel_col0 - 2;
-    rc.pitch = vw.sh * 4;
-    rc.gown = reinterpret_cast<const char*>(plane + (long long)(r_begin - R) * vw.sh + col0);
-    rc.ghalo = reinterpret_cast<const char*>(plane + (long long)(r_begin - R) * vw.sh + halo_col);
-    rc.s_own = s_own0;
-    rc.s_halo = s_halo0;
-    if (kAligned) {
-      rc.own_ok = col0 < W ? 1u : 0u;
-      rc.halo_ok = ((lane == 0 && panel_col0 > 0) || (lane == 31 && panel_col0 + kPanelW < W)) ? 1u : 0u;
-    } else {
-      rc.own_ok = 0;
-      for (int jj = 0; jj < 4; ++jj) rc.own_ok |= (col0 + jj < W ? 1u : 0u) << jj;
-      rc.halo_ok = 0;
-      if (lane == 0 || lane == 31)
-        for (int jj = 0; jj < 2; ++jj) rc.halo_ok |= ((halo_col + jj >= 0 && halo_col + jj < W) ? 1u : 0u) << jj;
-    }
-
     __syncwarp();  // everyone is done with the previous unit's ring, histogram and buffer
     *reinterpret_cast<uint4*>(hist + 4 * lane) = make_uint4(0, 0, 0, 0);
     *reinterpret_cast<int4*>(minx + 4 * lane) = make_int4(0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff);
-    // columns outside the image never receive a copy: park -inf there once for the whole unit
+    feed.begin_unit(plane, vw.sh, r_begin - R, H, W, panel_col0, q_last, lane);
 #pragma unroll
-    for (int sl = 0; sl < kStages; ++sl) {
-      sts128(s_own0 + sl * kPitchB, -CUDART_INF_F);
-      if (lane == 0 || lane == 31) sts64(s_halo0 + sl * kPitchB, -CUDART_INF_F);
-    }
-    __syncwarp();
-
-    // ring sequence number q <-> image row r_begin - R + q, slot q % kStages
-#pragma unroll
-    for (int q = 0; q < kStages - 1; ++q)
-      issue_row<kAligned>(rc, q, q <= q_last, (unsigned)(r_begin - R + q) < (unsigned)H, lane);
+    for (int q = 0; q < kStages - 1; ++q) feed.issue(q, lane);
 
     for (int t = 0; t < nrows; ++t) {
-      {  // the slot of sequence number t-1 is free: every lane passed a warp-wide vote after reading it
-        const int q = t + kStages - 1;
-        issue_row<kAligned>(rc, q & (kStages - 1), q <= q_last, (unsigned)(r_begin - R + q) < (unsigned)H, lane);
-      }
-      cp_async_wait<kPending>();
+      // the slot of sequence number t-1 is free: every lane passed a warp-wide vote after reading it
+      feed.issue(t + kStages - 1, lane);
+      feed.template wait_step<R>();
       __syncwarp();
-      const float4 ctr = lds128(s_own0 + ((t + R) & (kStages - 1)) * kPitchB);
+      const float4 ctr = lds128(feed.slot_addr(t + R) + own_off);
       const float m4 = fmaxf(fmaxf(ctr.x, ctr.y), fmaxf(ctr.z, ctr.w));
-      if (__any_sync(0xffffffffu, fminf(m4, satx) > st.floorx)) {
+      if (__any_sync(0xffffffffu, m4 > st.floorx)) {
         const float floorx = st.floorx;
         u32 cmask = 0;  // bit j: pixel col0+j goes to the candidate buffer
         if (!pre) {
@@ -396,9 +478,9 @@ __global__ void __launch_bounds__(kThreads, 4) sdnet_peaks_kernel(const __grid_c
           float2 hvv = make_float2(-CUDART_INF_F, -CUDART_INF_F);
 #pragma unroll
           for (int d = 0; d <= 2 * R; ++d) {
-            const u32 so = ((t + d) & (kStages - 1)) * kPitchB;
-            const float4 o = lds128(s_own0 + so);
-            const float2 ho = lds64(s_halo0 + so);
+            const u32 so = feed.slot_addr(t + d);
+            const float4 o = lds128(so + own_off);
+            const float2 ho = lds64(so + halo_off);
             v.x = fmaxf(v.x, o.x); v.y = fmaxf(v.y, o.y); v.z = fmaxf(v.z, o.z); v.w = fmaxf(v.w, o.w);
             hvv.x = fmaxf(hvv.x, ho.x); hvv.y = fmaxf(hvv.y, ho.y);
           }
@@ -421,62 +503,282 @@ __global__ void __launch_bounds__(kThreads, 4) sdnet_peaks_kernel(const __grid_c
             h2 = max3(v.y, v.z, v.w);
             h3 = max3(v.z, v.w, R0);
           }
-          // bit j   : pixel equals its window maximum -> certainly survives NMS
-          // bit 4+j : pixel is below the maximum but so close that the two scores may round equal
-          u32 amb = 0;
-#define SDNET_CLASSIFY(x, h, j)                                                                        \
-  if (col0 + j < W && fminf(x, satx) > floorx) {                                                       \
-    if ((x) == (h)) cmask |= 1u << j;                                                                  \
-    else if (((x) >= (h) - kNearTie) || ((h) > kHiZone && (x) > kHiZone - 1.0f) || ((h) < kLoZone))     \
-      amb |= 1u << j;                                                                                  \
-  }
-          SDNET_CLASSIFY(ctr.x, h0, 0)
-          SDNET_CLASSIFY(ctr.y, h1, 1)
-          SDNET_CLASSIFY(ctr.z, h2, 2)
-          SDNET_CLASSIFY(ctr.w, h3, 3)
-#undef SDNET_CLASSIFY
-          // rare: resolve the ambiguous pixels with the exact score function, one per lane per round
-          while (__any_sync(0xffffffffu, amb != 0)) {
-            const bool has = amb != 0;
-            const int jj = has ? __ffs(amb) - 1 : 0;
-            const float x = jj == 0 ? ctr.x : (jj == 1 ? ctr.y : (jj == 2 ? ctr.z : ctr.w));
-            const float h = jj == 0 ? h0 : (jj == 1 ? h1 : (jj == 2 ? h2 : h3));
-            if (has && activate(x) == activate(h)) cmask |= 1u << jj;
-            amb &= amb - 1;
-          }
+          cmask = classify_row<R>(ctr, h0, h1, h2, h3, floorx);
         } else {
           // pre-activated maps (CoreMLDecoder): every pixel above the floor is a candidate
-          if (col0 + 0 < W && ctr.x > floorx) cmask |= 1u;
-          if (col0 + 1 < W && ctr.y > floorx) cmask |= 2u;
-          if (col0 + 2 < W && ctr.z > floorx) cmask |= 4u;
-          if (col0 + 3 < W && ctr.w > floorx) cmask |= 8u;
+          if (ctr.x > floorx) cmask |= 1u;
+          if (ctr.y > floorx) cmask |= 2u;
+          if (ctr.z > floorx) cmask |= 4u;
+          if (ctr.w > floorx) cmask |= 8u;
         }
-        // append (logit, index) to the warp's buffer, one column at a time
-        const u32 idx0 = (u32)((r_begin + t) * W + col0);
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          const bool mine = (cmask >> jj) & 1u;
-          const u32 m = __ballot_sync(0xffffffffu, mine);
-          if (m) {  // warp-uniform
-            if (st.nbuf > kBuf - 32) {
-              __syncwarp();
-              flush_candidates(st, buf, hist, minx, ghist, gfloor_ptr, count_ptr, list, p.cap, K, lane, pre, xscale, satx);
-            }
-            if (mine) buf[st.nbuf + __popc(m & ((1u << lane) - 1u))] = ((u64)__float_as_uint(comp(ctr, jj)) << 32) | (idx0 + jj);
-            st.nbuf += __popc(m);
-          }
-        }
-        if (st.nbuf >= 32) {
-          __syncwarp();
-          flush_candidates(st, buf, hist, minx, ghist, gfloor_ptr, count_ptr, list, p.cap, K, lane, pre, xscale, satx);
-        }
+        append_row(st, cmask, ctr, (u32)((r_begin + t) * W + col0), buf, hist, minx, ghist, gfloor_ptr, count_ptr, list,
+                   p.cap, K, lane, pre, xscale, satx);
       }
       if ((t & 7) == 7) {
         // every 8 rows: pick up the plane-wide floor other warps may have raised
         st.floorx = fmaxf(st.floorx, shared_floor(__ldcg(gfloor_ptr), xscale));
       }
     }
-    cp_async_wait<0>();
+    feed.end_unit();
+    if (st.nbuf) {
+      __syncwarp();
+      flush_candidates(st, buf, hist, minx, ghist, gfloor_ptr, count_ptr, list, p.cap, K, lane, pre, xscale, satx);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// peaks kernel, warp-specialised form (the fast path; needs 16 B-aligned rows and W <= 896)
+//
+// CTA = NC consumer warps + 1 producer warp, working on one (plane, row strip) unit at a time.
+// The producer streams whole image rows (W*4 contiguous bytes) into a shared-memory ring with
+// 1-D bulk copies (TMA unit, SASS UBLKCP), four rows per mbarrier ("group"); consumer warp w
+// owns columns [128 w, 128 w + 128) of every row.  Ring row layout (floats):
+//     [4 x -inf | W columns | -inf up to 128 NC + 8]
+// so the horizontal neighbours of any pixel -- including across warps and beyond the image
+// edge -- are plain shared-memory reads.  Per group of four output rows a consumer waits on
+// one barrier, reads its four centre rows (4 x LDS.128), takes the max of the 16 values and
+// votes "does anything here beat the pruning floor?"; only then does it look at single rows.
+// ---------------------------------------------------------------------------------------------
+constexpr int kGroupRows = 4;
+constexpr int kMaxConsumers = 7;
+
+struct CtaGeom {
+  int nc;       // consumer warps
+  int rpb;      // ring row pitch in bytes
+  int ng;       // ring groups
+  int smem;     // dynamic shared memory per CTA
+};
+
+__host__ __device__ inline CtaGeom cta_geometry(int W, int ng) {
+  CtaGeom g;
+  g.nc = (W + kPanelW - 1) / kPanelW;
+  g.rpb = (kPanelW * g.nc + 8) * 4;
+  g.ng = ng;
+  g.smem = ng * kGroupRows * g.rpb + 2 * ng * 8 + g.nc * (kBins * 8 + kBuf * 8);
+  return g;
+}
+
+// window maxima of a lane's four pixels for output row t, straight from the ring
+// (ring rows are contiguous in shared memory, so ring row q of a unit whose first group has running
+// number n lives at row (4 n + q) mod (4 NG): `rowbase` = 4 n, `rowmask` = 4 NG - 1)
+template <int R>
+__device__ __forceinline__ void window_max(u32 ring_own, u32 rowbase, u32 rowmask, int rpb, int t, float& h0,
+                                           float& h1, float& h2, float& h3) {
+  const float ninf = -CUDART_INF_F;
+  float v0 = ninf, v1 = ninf, v2 = ninf, v3 = ninf, v4 = ninf, v5 = ninf, v6 = ninf, v7 = ninf;  // cols c-2 .. c+5
+#pragma unroll
+  for (int d = 0; d <= 2 * R; ++d) {
+    const u32 a = ring_own + ((rowbase + (u32)(t + d)) & rowmask) * rpb;
+    const float4 o = lds128(a);
+    const float2 l = lds64(a - 8);
+    const float2 r = lds64(a + 16);
+    v0 = fmaxf(v0, l.x); v1 = fmaxf(v1, l.y);
+    v2 = fmaxf(v2, o.x); v3 = fmaxf(v3, o.y); v4 = fmaxf(v4, o.z); v5 = fmaxf(v5, o.w);
+    v6 = fmaxf(v6, r.x); v7 = fmaxf(v7, r.y);
+  }
+  if (R == 2) {
+    const float m34 = fmaxf(v3, v4);
+    h0 = max3(fmaxf(v0, v1), v2, m34);
+    h1 = max3(fmaxf(v1, v2), m34, v5);
+    h2 = max3(fmaxf(v2, v6), m34, v5);
+    h3 = max3(fmaxf(v6, v7), m34, v5);
+  } else {
+    h0 = max3(v1, v2, v3);
+    h1 = max3(v2, v3, v4);
+    h2 = max3(v3, v4, v5);
+    h3 = max3(v4, v5, v6);
+  }
+}
+
+template <int R, int NG>
+__global__ void __launch_bounds__((kMaxConsumers + 1) * 32) sdnet_peaks_cta_kernel(const __grid_constant__ PeaksParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  static_assert((NG & (NG - 1)) == 0, "ring groups must be a power of two");
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int nc = (int)(blockDim.x >> 5) - 1;
+  const int rpb = (kPanelW * nc + 8) * 4;
+  const u32 ring_s = smem_u32(smem_raw);
+  const u32 full_s = ring_s + NG * kGroupRows * rpb;
+  const u32 empty_s = full_s + NG * 8;
+  unsigned char* wstate = smem_raw + NG * kGroupRows * rpb + 2 * NG * 8;
+  const int C = p.M + p.N;
+  const int H = p.H, W = p.W;
+
+  // one-time setup: barriers, ring parked at -inf (everything a copy never overwrites must read
+  // as max_pool2d's -inf padding)
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NG; ++i) {
+      mbar_init(full_s + 8 * i, 1);
+      mbar_init(empty_s + 8 * i, (u32)nc);
+    }
+    mbar_fence_init();
+  }
+  for (int i = threadIdx.x; i < NG * kGroupRows * rpb / 16; i += blockDim.x) sts128(ring_s + 16 * i, -CUDART_INF_F);
+  fence_proxy_async();
+  __syncthreads();
+
+  if (warp == nc) {
+    // ================================ producer warp ================================
+    const u32 row_bytes = (u32)W * 4;
+    u32 n = 0;  // running group number: slot n % NG, phase (n / NG) & 1
+    for (u32 unit = blockIdx.x; unit < (u32)p.units; unit += gridDim.x) {
+      const int strip = unit % p.strips;
+      const int plane_id = unit / p.strips;
+      const int b = plane_id / C, c = plane_id % C;
+      const bool is_anchor = c < p.M;
+      const View4& vw = is_anchor ? p.anchor : p.part;
+      const float* plane = vw.data + (long long)b * vw.sb + (long long)(is_anchor ? c : c - p.M) * vw.sc;
+      const int r_begin = strip * p.rows_per_strip;
+      const int r_end = min(H, r_begin + p.rows_per_strip);
+      const int q_count = r_end - r_begin + 2 * R;      // ring rows of this unit: image rows r_begin-R ..
+      const int groups = (q_count + kGroupRows - 1) / kGroupRows;
+      const long long pitch = vw.sh * 4;
+      const char* src0 = reinterpret_cast<const char*>(plane) + (long long)(r_begin - R) * pitch;
+      for (int j = 0; j < groups; ++j, ++n) {
+        const u32 slot = n & (NG - 1);
+        mbar_wait(empty_s + 8 * slot, ((n / NG) & 1u) ^ 1u);  // consumers are done with this slot
+        u32 valid = 0, fill = 0;
+#pragma unroll
+        for (int i = 0; i < kGroupRows; ++i) {
+          const int q = j * kGroupRows + i;
+          if (q < q_count) {
+            if ((unsigned)(r_begin - R + q) < (unsigned)H) valid |= 1u << i;
+            else fill |= 1u << i;
+          }
+        }
+        if (fill) {  // rows above / below the image: -inf
+#pragma unroll
+          for (int i = 0; i < kGroupRows; ++i)
+            if ((fill >> i) & 1u)
+              for (int k = lane; k < rpb / 16; k += 32) sts128(ring_s + (slot * kGroupRows + i) * rpb + 16 * k, -CUDART_INF_F);
+          fence_proxy_async();
+          __syncwarp();
+        }
+        if (lane == 0) {
+          const u32 bar = full_s + 8 * slot;
+          if (valid) {
+            mbar_arrive_expect_tx(bar, (u32)__popc(valid) * row_bytes);
+#pragma unroll
+            for (int i = 0; i < kGroupRows; ++i)
+              if ((valid >> i) & 1u)
+                bulk_g2s(ring_s + (slot * kGroupRows + i) * rpb + 16, src0 + (long long)(j * kGroupRows + i) * pitch,
+                         row_bytes, bar);
+          } else {
+            mbar_arrive(bar);
+          }
+        }
+        __syncwarp();
+      }
+    }
+    return;
+  }
+
+  // ================================== consumer warps ==================================
+  u32* hist = reinterpret_cast<u32*>(wstate + (size_t)warp * (kBins * 8 + kBuf * 8));
+  int* minx = reinterpret_cast<int*>(hist + kBins);
+  u64* buf = reinterpret_cast<u64*>(minx + kBins);
+  const bool pre = p.pre_activated != 0;
+  const float xscale = pre ? kPreScale : 1.0f;
+  const float satx = pre ? CUDART_INF_F : kSatX;
+  const int col0 = kPanelW * warp + 4 * lane;
+  const u32 own_off = (u32)(4 + col0) * 4;
+  u32 n = 0;
+  for (u32 unit = blockIdx.x; unit < (u32)p.units; unit += gridDim.x) {
+    const int strip = unit % p.strips;
+    const int plane_id = unit / p.strips;
+    const int c = plane_id % C;
+    const int K = c < p.M ? p.K : p.P;
+    const int r_begin = strip * p.rows_per_strip;
+    const int r_end = min(H, r_begin + p.rows_per_strip);
+    const int nrows = r_end - r_begin;
+    const int groups = (nrows + 2 * R + kGroupRows - 1) / kGroupRows;
+    const int groups_out = (nrows + kGroupRows - 1) / kGroupRows;
+    u64* __restrict__ list = p.lists + (size_t)plane_id * p.cap;
+    int* count_ptr = p.counts + plane_id;
+    u32* ghist = p.ghist + (size_t)plane_id * kBins;
+    int* gfloor_ptr = p.gfloor + plane_id;
+
+    UnitState st;
+    st.floorx = shared_floor(__ldcg(gfloor_ptr), xscale);
+    st.emitted = 0;
+    st.nbuf = 0;
+    __syncwarp();
+    *reinterpret_cast<uint4*>(hist + 4 * lane) = make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<int4*>(minx + 4 * lane) = make_int4(0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff);
+    __syncwarp();
+
+    const u32 ring_own = ring_s + own_off;
+    const u32 rowbase = n * kGroupRows;
+    mbar_wait(full_s + 8 * (n & (NG - 1)), (n / NG) & 1u);
+    for (int g = 0; g < groups_out; ++g) {
+      const u32 n0 = n + g, n1 = n0 + 1;
+      if (g + 1 < groups) mbar_wait(full_s + 8 * (n1 & (NG - 1)), (n1 / NG) & 1u);
+      const int gfloor_next = __ldcg(gfloor_ptr);  // consumed at the end of the group: latency hidden
+      const u32 gb0 = ring_s + (n0 & (NG - 1)) * kGroupRows * rpb + own_off;
+      const u32 gb1 = ring_s + (n1 & (NG - 1)) * kGroupRows * rpb + own_off;
+      const int t0 = g * kGroupRows;
+      // centre row of output row t0+i is ring row t0+i+R
+      float4 c0, c1, c2, c3;
+      if (R == 2) {
+        c0 = lds128(gb0 + 2 * rpb); c1 = lds128(gb0 + 3 * rpb);
+      } else {
+        c0 = lds128(gb0 + 1 * rpb); c1 = lds128(gb0 + 2 * rpb);
+      }
+      if (t0 + 3 < nrows) {
+        if (R == 2) { c2 = lds128(gb1); c3 = lds128(gb1 + rpb); }
+        else { c2 = lds128(gb0 + 3 * rpb); c3 = lds128(gb1); }
+      } else {
+        // last, partial group: rows past the strip do not exist
+        const float4 none = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
+        if (t0 + 1 >= nrows) c1 = none;
+        c2 = none; c3 = none;
+        if (t0 + 2 < nrows) c2 = (R == 2) ? lds128(gb1) : lds128(gb0 + 3 * rpb);
+      }
+      const float m0 = fmaxf(fmaxf(c0.x, c0.y), fmaxf(c0.z, c0.w));
+      const float m1 = fmaxf(fmaxf(c1.x, c1.y), fmaxf(c1.z, c1.w));
+      const float m2 = fmaxf(fmaxf(c2.x, c2.y), fmaxf(c2.z, c2.w));
+      const float m3 = fmaxf(fmaxf(c3.x, c3.y), fmaxf(c3.z, c3.w));
+      if (__any_sync(0xffffffffu, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) > st.floorx)) {
+        // something in these four rows beats the floor: visit only the rows that do (kept as a
+        // real loop so the row code exists once -- it is large and instruction-cache bound)
+        u32 rowmask4 = (__any_sync(0xffffffffu, m0 > st.floorx) ? 1u : 0u) | (__any_sync(0xffffffffu, m1 > st.floorx) ? 2u : 0u) |
+                       (__any_sync(0xffffffffu, m2 > st.floorx) ? 4u : 0u) | (__any_sync(0xffffffffu, m3 > st.floorx) ? 8u : 0u);
+#pragma unroll 1
+        while (rowmask4) {
+          const int i = __ffs(rowmask4) - 1;
+          rowmask4 &= rowmask4 - 1;
+          const int t = t0 + i;
+          const float4 ctr = lds128(ring_own + ((rowbase + (u32)(t + R)) & (NG * kGroupRows - 1)) * rpb);
+          const float floorx = st.floorx;
+          const float mi = fmaxf(fmaxf(ctr.x, ctr.y), fmaxf(ctr.z, ctr.w));
+          if (!__any_sync(0xffffffffu, mi > floorx)) continue;  // an earlier row of the group raised the floor
+          u32 cmask = 0;
+          if (!pre) {
+            float h0, h1, h2, h3;
+            window_max<R>(ring_own, rowbase, NG * kGroupRows - 1, rpb, t, h0, h1, h2, h3);
+            cmask = classify_row<R>(ctr, h0, h1, h2, h3, floorx);
+          } else {
+            if (ctr.x > floorx) cmask |= 1u;
+            if (ctr.y > floorx) cmask |= 2u;
+            if (ctr.z > floorx) cmask |= 4u;
+            if (ctr.w > floorx) cmask |= 8u;
+          }
+          append_row(st, cmask, ctr, (u32)((r_begin + t) * W + col0), buf, hist, minx, ghist, gfloor_ptr, count_ptr,
+                     list, p.cap, K, lane, pre, xscale, satx);
+        }
+      }
+      // every lane's reads of group n0 are consumed (the votes above): hand the slot back
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty_s + 8 * (n0 & (NG - 1)));
+      st.floorx = fmaxf(st.floorx, shared_floor(gfloor_next, xscale));
+    }
+    if (groups > groups_out) {  // a trailing group that only held the bottom halo rows
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty_s + 8 * ((n + groups_out) & (NG - 1)));
+    }
+    n += (u32)groups;
     if (st.nbuf) {
       __syncwarp();
       flush_candidates(st, buf, hist, minx, ghist, gfloor_ptr, count_ptr, list, p.cap, K, lane, pre, xscale, satx);
@@ -1053,19 +1355,6 @@ int launch_decode(const SdnetDecodeParams* p, cudaStream_t stream, cudaEvent_t* 
   pp.anchor = to_view(p->anchor_hm);
   pp.part = to_view(p->part_hm);
   pp.B = p->B; pp.M = p->M; pp.N = p->N; pp.H = p->H; pp.W = p->W; pp.K = p->K; pp.P = p->P;
-  pp.panels = (p->W + kPanelW - 1) / kPanelW;
-  const int sms = device_sm_count();
-  const int resident_warps = sms * kPeaksCtasPerSm * kWarps;
-  // enough units for ~4 waves of resident warps, but strips of at least 32 rows
-  long long want_units = 4ll * resident_warps;
-  long long per_strip1 = (long long)planes * pp.panels;
-  int strips = (int)((want_units + per_strip1 - 1) / per_strip1);
-  const int max_strips = (p->H + 31) / 32;
-  if (strips > max_strips) strips = max_strips;
-  if (strips < 1) strips = 1;
-  pp.rows_per_strip = (p->H + strips - 1) / strips;
-  pp.strips = (p->H + pp.rows_per_strip - 1) / pp.rows_per_strip;
-  pp.units = (int)(planes * pp.strips * pp.panels);
   pp.cap = ws.cap;
   pp.pre_activated = (p->flags & SDNET_FLAG_PRE_ACTIVATED) ? 1 : 0;
   pp.lists = reinterpret_cast<u64*>(base + ws.off_lists);
@@ -1073,16 +1362,53 @@ int launch_decode(const SdnetDecodeParams* p, cudaStream_t stream, cudaEvent_t* 
   pp.sched = reinterpret_cast<u32*>(base + ws.off_sched);
   pp.ghist = reinterpret_cast<u32*>(base + ws.off_ghist);
   pp.gfloor = reinterpret_cast<int*>(base + ws.off_gfloor);
+  const int sms = device_sm_count();
   const bool aligned = view_aligned(p->anchor_hm, p->W) && view_aligned(p->part_hm, p->W);
-  long long ctas = ((long long)pp.units + kWarps - 1) / kWarps;
-  if (ctas > (long long)sms * kPeaksCtasPerSm) ctas = (long long)sms * kPeaksCtasPerSm;
-  dim3 grid((unsigned)ctas), block(kThreads);
-  if (p->radius == 2) {
-    if (aligned) launch_peaks(sdnet_peaks_kernel<true, 2>, grid, block, stream, pp);
-    else launch_peaks(sdnet_peaks_kernel<false, 2>, grid, block, stream, pp);
+  const bool use_cta = aligned && p->W <= kPanelW * kMaxConsumers && !(p->flags & SDNET_FLAG_WARP_KERNEL);
+  auto pick_strips = [&](long long units_per_strip1, long long want_units) {
+    int strips = (int)((want_units + units_per_strip1 - 1) / units_per_strip1);
+    const int max_strips = (p->H + 31) / 32;  // strips of at least 32 rows
+    if (strips > max_strips) strips = max_strips;
+    if (strips < 1) strips = 1;
+    pp.rows_per_strip = (p->H + strips - 1) / strips;
+    pp.strips = (p->H + pp.rows_per_strip - 1) / pp.rows_per_strip;
+  };
+  if (use_cta) {
+    static const int ring_groups = [] {  // tuning knob, read once: SDNET_RING_GROUPS = 4 | 8
+      const char* e = getenv("SDNET_RING_GROUPS");
+      return (e && atoi(e) == 8) ? 8 : 4;
+    }();
+    const CtaGeom geom = cta_geometry(p->W, ring_groups);
+    auto kern = ring_groups == 8
+                    ? (p->radius == 2 ? sdnet_peaks_cta_kernel<2, 8> : sdnet_peaks_cta_kernel<1, 8>)
+                    : (p->radius == 2 ? sdnet_peaks_cta_kernel<2, 4> : sdnet_peaks_cta_kernel<1, 4>);
+    const int threads = (geom.nc + 1) * 32;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, geom.smem);
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, geom.smem) != cudaSuccess || per_sm < 1)
+      per_sm = 1;
+    pp.panels = 1;
+    const long long resident = (long long)sms * per_sm;
+    pick_strips((long long)planes, 3 * resident);
+    pp.units = (int)(planes * pp.strips);
+    long long ctas = pp.units < resident ? pp.units : resident;
+    kern<<<dim3((unsigned)ctas), dim3(threads), geom.smem, stream>>>(pp);
   } else {
-    if (aligned) launch_peaks(sdnet_peaks_kernel<true, 1>, grid, block, stream, pp);
-    else launch_peaks(sdnet_peaks_kernel<false, 1>, grid, block, stream, pp);
+    pp.panels = (p->W + kPanelW - 1) / kPanelW;
+    const int resident_warps = sms * kPeaksCtasPerSm * kWarps;
+    pick_strips((long long)planes * pp.panels, 4ll * resident_warps);
+    pp.units = (int)(planes * pp.strips * pp.panels);
+    long long ctas = ((long long)pp.units + kWarps - 1) / kWarps;
+    if (ctas > (long long)sms * kPeaksCtasPerSm) ctas = (long long)sms * kPeaksCtasPerSm;
+    dim3 grid((unsigned)ctas), block(kThreads);
+    if (p->radius == 2) {
+      if (aligned) launch_peaks(sdnet_peaks_kernel<true, 2>, grid, block, stream, pp);
+      else launch_peaks(sdnet_peaks_kernel<false, 2>, grid, block, stream, pp);
+    } else {
+      if (aligned) launch_peaks(sdnet_peaks_kernel<true, 1>, grid, block, stream, pp);
+      else launch_peaks(sdnet_peaks_kernel<false, 1>, grid, block, stream, pp);
+    }
   }
   err = cudaGetLastError();
   if (err != cudaSuccess) return (int)err;

@@ -17,7 +17,8 @@ from dataclasses import dataclass
 import torch
 
 from . import _native
-from ._native import FLAG_EXACT_SELECT, FLAG_NO_GROUPING, FLAG_PRE_ACTIVATED, SdnetDecodeParams, SdnetTensor4
+from ._native import (FLAG_EXACT_SELECT, FLAG_NO_GROUPING, FLAG_PRE_ACTIVATED, FLAG_WARP_KERNEL, SdnetDecodeParams,
+                      SdnetTensor4)
 
 __all__ = ["decode_packed", "activate_maps", "DecodePlan", "PackedDetections", "gpu_launches_per_decode"]
 
@@ -211,7 +212,7 @@ def _unit_w_stride(t: torch.Tensor) -> torch.Tensor:
 
 def decode_packed(outputs: dict, max_objects: int, max_parts: int, conf_thresh: float, dist_thresh: float, *,
                   pre_activated: bool = False, group: bool = True, radius: int = 2,
-                  exact_select: bool = False) -> PackedDetections:
+                  exact_select: bool = False, warp_kernel: bool = False) -> PackedDetections:
     """Run the CUDA decode on the four network-output views and return packed device tensors."""
     a_hm, p_hm, off = outputs["anchor_hm"], outputs["part_hm"], outputs["offsets"]
     emb = outputs["embeddings"] if group or "embeddings" in outputs else None
@@ -222,7 +223,7 @@ def decode_packed(outputs: dict, max_objects: int, max_parts: int, conf_thresh: 
     if emb is None:
         emb = off  # never read under NO_GROUPING without part_emb consumers; keeps the op signature tensor-only
     flags = (FLAG_PRE_ACTIVATED if pre_activated else 0) | (0 if group else FLAG_NO_GROUPING) | (
-        FLAG_EXACT_SELECT if exact_select else 0)
+        FLAG_EXACT_SELECT if exact_select else 0) | (FLAG_WARP_KERNEL if warp_kernel else 0)
     a_hm, p_hm, off, emb = map(_unit_w_stride, (a_hm, p_hm, off, emb))
     blob = _decode_op(a_hm, p_hm, off, emb, int(max_objects), int(max_parts), _f32(conf_thresh),
                       _f32(float(dist_thresh) * min(W, H)), int(radius), int(flags))

@@ -16,13 +16,13 @@ from tests.helpers import assert_packed_equal, np_inputs, packed_np, torch_sigmo
 pytestmark = pytest.mark.gpu
 
 
-def _decode_both(cfg, raw_cpu, device, *, exact_select=False, radius=2, conf=None, dist=None):
+def _decode_both(cfg, raw_cpu, device, *, exact_select=False, radius=2, conf=None, dist=None, warp_kernel=False):
     conf = cfg.conf_threshold if conf is None else conf
     dist = cfg.dist_thresh if dist is None else dist
     outs_cpu = split_outputs(raw_cpu, cfg.labels, cfg.parts)
     outs_gpu = split_outputs(raw_cpu.to(device), cfg.labels, cfg.parts)
     got = ops.decode_packed(outs_gpu, cfg.max_objects, cfg.max_parts, conf, dist, exact_select=exact_select,
-                            radius=radius)
+                            radius=radius, warp_kernel=warp_kernel)
     torch.cuda.synchronize()
     want = O.decode_packed(*np_inputs(outs_cpu), cfg.max_objects, cfg.max_parts, conf, dist,
                            sigmoid_fn=torch_sigmoid_fn(device), radius=radius)
@@ -91,11 +91,12 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("warp_kernel", [False, True], ids=["tma", "warp"])
 @pytest.mark.parametrize("name,mode,batch", CASES)
-def test_decode_matches_oracle(cuda_device, name, mode, batch):
+def test_decode_matches_oracle(cuda_device, name, mode, batch, warp_kernel):
     cfg = CONFIGS[name]
     raw = make_raw(cfg, mode, batch=batch)
-    got, want = _decode_both(cfg, raw, cuda_device)
+    got, want = _decode_both(cfg, raw, cuda_device, warp_kernel=warp_kernel)
     assert_packed_equal(got, want, what=f"{name}/{mode}")
     assert int(got["diag"][:, 1].sum()) == 0 or mode == "ties"
 
@@ -110,7 +111,9 @@ def test_exact_select_path_matches_oracle(cuda_device, name, mode, batch):
 
 
 @pytest.mark.parametrize("h,w,k,p", [(5, 5, 25, 25), (7, 9, 10, 63), (37, 53, 40, 20), (64, 130, 100, 100),
-                                     (33, 257, 64, 64), (200, 4, 50, 50), (1, 300, 30, 30), (300, 1, 30, 30)])
+                                     (33, 257, 64, 64), (200, 4, 50, 50), (1, 300, 30, 30), (300, 1, 30, 30),
+                                     (3, 128, 20, 20), (41, 132, 60, 60), (70, 896, 100, 100), (40, 900, 100, 100),
+                                     (35, 1028, 100, 100), (9, 8, 72, 10)])
 @pytest.mark.parametrize("mode", ["noise", "ties"])
 def test_odd_shapes(cuda_device, h, w, k, p, mode):
     cfg = DecodeConfig("odd", 2, 3, 2, h, w, k, p, cfg_id=9)
@@ -119,10 +122,12 @@ def test_odd_shapes(cuda_device, h, w, k, p, mode):
     assert_packed_equal(got, want, what=f"odd {h}x{w}/{mode}")
 
 
-def test_radius_one(cuda_device):
-    cfg = CONFIGS["cfg1"]
+@pytest.mark.parametrize("warp_kernel", [False, True], ids=["tma", "warp"])
+@pytest.mark.parametrize("name", ["cfg1", "cfg3"])
+def test_radius_one(cuda_device, name, warp_kernel):
+    cfg = CONFIGS[name]
     raw = make_raw(cfg, "noise", batch=2)
-    got, want = _decode_both(cfg, raw, cuda_device, radius=1)
+    got, want = _decode_both(cfg, raw, cuda_device, radius=1, warp_kernel=warp_kernel)
     assert_packed_equal(got, want, what="radius 1")
 
 

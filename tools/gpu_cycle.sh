@@ -2,7 +2,7 @@
 # One GPU-box cycle: parity tests, short bench at two shard sizes and both modes, one ncu capture.
 # usage (under gpurun): bash tools/gpu_cycle.sh <tag> [ncu]
 tag=${1:-x}
-python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+python -m pytest tests -m gpu -x -q --durations=5 2>&1 | tail -14
 for gb in 1024 128; do
   python bench.py --steps 30 --warmup 5 --no-e2e --no-cpu-baseline --global-batch $gb > gpurun_out/b_${tag}_$gb.json 2> gpurun_out/b_${tag}_$gb.err
   python - <<PY
