@@ -261,6 +261,7 @@ def main():
     # ---- sanity: the timed path produced real detections (and every rank agrees after the gather)
     counts = plan.out.counts.sum(dim=0).tolist()
     diag_overflow = int(plan.out.diag[:, 1].sum())
+    cand_mean = float(plan.out.diag[:, 0].float().mean())
 
     # ---- roofline leg: device time of each kernel (events between the launches), averaged
     reps = 20
@@ -367,7 +368,8 @@ def main():
             "gpu_launches": ops.gpu_launches_per_decode() * args.steps,
             "clocks": clocks.summary(),
             "detections": {"anchors_above_conf": counts[0], "parts_above_conf": counts[1],
-                           "planes_via_exact_select": diag_overflow},
+                           "planes_via_exact_select": diag_overflow,
+                           "candidates_per_plane_mean": cand_mean},
         }
         print(json.dumps(line), flush=True)
     if world > 1:

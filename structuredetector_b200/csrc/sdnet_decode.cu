@@ -46,6 +46,8 @@ constexpr int kPanelW = 128;           // columns per warp (32 lanes x 4)
 constexpr int kBins = 128;             // per-warp logit histogram used for pruning
 constexpr float kBinLo = -16.0f;
 constexpr float kBinScale = 4.0f;      // bins of 0.25 logit
+constexpr int kFineBins = 256;         // shared (CTA-wide / plane-wide) histograms: bins of 0.125 logit
+constexpr float kFineScale = 8.0f;
 constexpr float kNearTie = 2e-3f;      // logit margin inside which two scores may round equal (|x| <= 8)
 constexpr float kHiZone = 8.0f;        // above this, score spacing approaches 1 ulp: always check exactly
 constexpr float kLoZone = -13.0f;      // below this, scores approach the 1e-6 clamp: always check exactly
@@ -73,8 +75,9 @@ struct PeaksParams {
   u64* lists;              // [planes][cap]
   int* counts;             // [planes] records emitted (may exceed cap)
   u32* sched;              // [0] dynamic unit counter
-  u32* ghist;              // [planes][kBins] plane-wide logit histogram of recorded candidates
-  int* gfloor;             // [planes] highest bin b with >= K recorded candidates in bins >= b (0 = none)
+  u32* ghist;              // [planes][kFineBins] plane-wide logit histogram of recorded candidates
+  int* gfloor;             // [planes] highest fine bin b with >= K recorded candidates in bins >= b (0 = none)
+  int l2_prefetch_groups;  // warp-specialised kernel: L2 prefetch distance in 4-row groups (0 = off)
 };
 
 // clamp(sigmoid(x)) bit-identical to ATen's CUDA kernels (UnarySpecialOpsKernel.cu sigmoid:
@@ -159,11 +162,14 @@ __device__ __forceinline__ void mbar_wait(u32 bar, u32 parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n"
       "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
       "@!p bra WAIT_LOOP;\n\t}"
-      ::"r"(bar), "r"(parity) : "memory");
+      ::"r"(bar), "r"(parity), "r"(1000u) : "memory");  // suspend-time hint (ns): sleep instead of spinning
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, u32 bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void bulk_g2s(u32 dst, const void* src, u32 bytes, u32 bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
@@ -278,17 +284,60 @@ __device__ __forceinline__ float local_floor(const u32* hist, const int* minx, i
   return ord_to_float(minx[b]);
 }
 
-// Plane-wide floor shared between the warps working on one plane.  Unlike the warp-local floor
-// (which may drop equal scores because everything it counted has a lower index), this one needs
-// a strict score gap: a pixel is dropped only if its logit is below edge(b) - kNearTie with
-// edge(b) in [kLoZone, kHiZone], where S(x - kNearTie) < S(x) is verified exhaustively.
-__device__ __forceinline__ float shared_floor(int gbin, float xscale) {
-  if (gbin <= 0) return -CUDART_INF_F;
-  const float edge = kBinLo + (float)gbin * (1.0f / kBinScale);
+__device__ __forceinline__ int fine_bin(float x) {
+  int bin = __float2int_rd((x - kBinLo) * kFineScale);
+  bin = max(0, min(kFineBins - 1, bin));
+  if (bin > 0 && x < kBinLo + (float)bin * (1.0f / kFineScale)) --bin;  // rounding guard, as in logit_bin
+  return bin;
+}
+
+// Highest fine bin b with (count in bins >= b) >= K; lane l owns bins 8l..8l+7.  -1 if none.
+__device__ __forceinline__ int floor_bin_fine(const uint4 lo, const uint4 hi, int lane, int K) {
+  const u32 cnt[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+  u32 s = 0;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) s += cnt[q];
+  u32 suf = s;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    u32 t = __shfl_down_sync(0xffffffffu, suf, d);
+    if (lane + d < 32) suf += t;
+  }
+  const u32 mask = __ballot_sync(0xffffffffu, suf >= (u32)K);
+  if (mask == 0) return -1;
+  const int L = 31 - __clz(mask);
+  int b = 8 * L;
+  if (lane == L) {
+    u32 above = suf - s;
+#pragma unroll
+    for (int q = 7; q >= 0; --q) {
+      if (above + cnt[q] >= (u32)K) { b = 8 * L + q; break; }
+      above += cnt[q];
+    }
+  }
+  return __shfl_sync(0xffffffffu, b, L);
+}
+
+// Floor shared between warps working on the same plane (CTA-wide in shared memory, plane-wide in
+// global memory).  Unlike the warp-local floor (which may drop equal scores because everything
+// it counted has a lower index), a shared floor needs a strict score gap: a pixel is dropped
+// only if its logit is below edge(b) - kNearTie with edge(b) in [kLoZone, kHiZone], where
+// S(x - kNearTie) < S(x) is verified exhaustively (tests/test_gpu_parity.py).
+__device__ __forceinline__ float shared_floor(int fbin, float xscale) {
+  if (fbin <= 0) return -CUDART_INF_F;
+  const float edge = kBinLo + (float)fbin * (1.0f / kFineScale);
   if (xscale != 1.0f) return edge / xscale;  // pre-activated: keys are strictly monotone in the value
   if (edge < kLoZone || edge > kHiZone) return -CUDART_INF_F;
   return edge - kNearTie;
 }
+
+// Where a warp publishes / picks up shared floors.
+struct SharedFloors {
+  u32* cta_hist;   // shared memory [kFineBins], or nullptr
+  int* cta_floor;  // shared memory, or nullptr
+  u32* ghist;      // global [kFineBins], or nullptr when the CTA covers the whole plane
+  int* gfloor;     // global
+};
 
 // Flush the warp's candidate buffer: evaluate the exact score of up to 64 buffered pixels (all
 // lanes busy), append (score, index) records to the plane's list with one atomic, feed the
@@ -299,9 +348,9 @@ struct UnitState {
   int nbuf;       // records waiting in the shared-memory buffer
 };
 
-__device__ __forceinline__ void flush_candidates(UnitState& st, const u64* buf, u32* hist, int* minx, u32* ghist,
-                                                 int* gfloor_ptr, int* count_ptr, u64* __restrict__ list, int cap,
-                                                 int K, int lane, bool pre, float xscale, float satx) {
+__device__ __forceinline__ void flush_candidates(UnitState& st, const u64* buf, u32* hist, int* minx,
+                                                 const SharedFloors& sf, int* count_ptr, u64* __restrict__ list,
+                                                 int cap, int K, int lane, bool pre, float xscale, float satx) {
   const int n = st.nbuf;  // warp-uniform, 1..kBuf
   int base = 0;
   if (lane == 0) base = atomicAdd(count_ptr, n);
@@ -327,7 +376,9 @@ __device__ __forceinline__ void flush_candidates(UnitState& st, const u64* buf, 
         const int bin = logit_bin(xe);
         atomicAdd(&hist[bin], 1u);
         atomicMin(&minx[bin], ord_of(xe));
-        atomicAdd(&ghist[bin], 1u);
+        const int fb = fine_bin(xe);
+        if (sf.cta_hist) atomicAdd(&sf.cta_hist[fb], 1u);
+        if (sf.ghist) atomicAdd(&sf.ghist[fb], 1u);
       }
     }
   }
@@ -336,12 +387,29 @@ __device__ __forceinline__ void flush_candidates(UnitState& st, const u64* buf, 
   __syncwarp();
   // xscale is a power of two, so the division is exact
   if (st.emitted >= (u32)K) st.floorx = fmaxf(st.floorx, local_floor(hist, minx, lane, K) / xscale);
-  // publish / refresh the plane-wide floor
-  const uint4 gc = __ldcg(reinterpret_cast<const uint4*>(ghist + 4 * lane));
-  const int gb = floor_bin_of(gc, lane, K);
-  if (gb > 0) {
-    if (lane == 0) atomicMax(gfloor_ptr, gb);
-    st.floorx = fmaxf(st.floorx, shared_floor(gb, xscale));
+  // publish / refresh the shared floors
+  if (sf.cta_hist) {
+    const u32 ha = smem_u32(sf.cta_hist + 8 * lane);
+    uint4 lo, hi;
+    asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(lo.x), "=r"(lo.y), "=r"(lo.z), "=r"(lo.w) : "r"(ha));
+    asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(hi.x), "=r"(hi.y), "=r"(hi.z), "=r"(hi.w) : "r"(ha + 16));
+    const int b = floor_bin_fine(lo, hi, lane, K);
+    if (b > 0) {
+      if (lane == 0) atomicMax(sf.cta_floor, b);
+      st.floorx = fmaxf(st.floorx, shared_floor(b, xscale));
+    }
+  }
+  if (sf.ghist) {
+    const uint4 lo = __ldcg(reinterpret_cast<const uint4*>(sf.ghist + 8 * lane));
+    const uint4 hi = __ldcg(reinterpret_cast<const uint4*>(sf.ghist + 8 * lane + 4));
+    const int gb = floor_bin_fine(lo, hi, lane, K);
+    if (gb > 0) {
+      if (lane == 0) {
+        atomicMax(sf.gfloor, gb);
+        if (sf.cta_floor) atomicMax(sf.cta_floor, gb);
+      }
+      st.floorx = fmaxf(st.floorx, shared_floor(gb, xscale));
+    }
   }
   // a floor at the saturation clamp means "nothing can beat what we have": every x >= satx has
   // the same score as the K recorded ones and a higher index
@@ -381,7 +449,7 @@ __device__ __forceinline__ u32 classify_row(const float4 ctr, float h0, float h1
 // Append the selected pixels of one row as (logit, index) records to the warp's buffer, one
 // column at a time, flushing when it fills up.
 __device__ __forceinline__ void append_row(UnitState& st, u32 cmask, const float4 ctr, u32 idx0, u64* buf, u32* hist,
-                                           int* minx, u32* ghist, int* gfloor_ptr, int* count_ptr,
+                                           int* minx, const SharedFloors& sf, int* count_ptr,
                                            u64* __restrict__ list, int cap, int K, int lane, bool pre, float xscale,
                                            float satx) {
   if (!__any_sync(0xffffffffu, cmask != 0)) return;
@@ -392,7 +460,7 @@ __device__ __forceinline__ void append_row(UnitState& st, u32 cmask, const float
     if (m) {  // warp-uniform
       if (st.nbuf > kBuf - 32) {
         __syncwarp();
-        flush_candidates(st, buf, hist, minx, ghist, gfloor_ptr, count_ptr, list, cap, K, lane, pre, xscale, satx);
+        flush_candidates(st, buf, hist, minx, sf, count_ptr, list, cap, K, lane, pre, xscale, satx);
       }
       if (mine) buf[st.nbuf + __popc(m & ((1u << lane) - 1u))] = ((u64)__float_as_uint(comp(ctr, jj)) << 32) | (idx0 + jj);
       st.nbuf += __popc(m);
@@ -400,7 +468,7 @@ __device__ __forceinline__ void append_row(UnitState& st, u32 cmask, const float
   }
   if (st.nbuf >= 32) {
     __syncwarp();
-    flush_candidates(st, buf, hist, minx, ghist, gfloor_ptr, count_ptr, list, cap, K, lane, pre, xscale, satx);
+    flush_candidates(st, buf, hist, minx, sf, count_ptr, list, cap, K, lane, pre, xscale, satx);
   }
 }
 
@@ -447,8 +515,11 @@ __global__ void __launch_bounds__(kThreads, 4) sdnet_peaks_kernel(const __grid_c
     const int q_last = nrows - 1 + 2 * R;  // ring sequence number of the last row any centre row needs
     u64* __restrict__ list = p.lists + (size_t)plane_id * p.cap;
     int* count_ptr = p.counts + plane_id;
-    u32* ghist = p.ghist + (size_t)plane_id * kBins;
     int* gfloor_ptr = p.gfloor + plane_id;
+    SharedFloors sf;
+    sf.cta_hist = nullptr; sf.cta_floor = nullptr;
+    sf.ghist = p.ghist + (size_t)plane_id * kFineBins;
+    sf.gfloor = gfloor_ptr;
 
     UnitState st;
     st.floorx = shared_floor(__ldcg(gfloor_ptr), xscale);
@@ -511,7 +582,7 @@ __global__ void __launch_bounds__(kThreads, 4) sdnet_peaks_kernel(const __grid_c
           if (ctr.z > floorx) cmask |= 4u;
           if (ctr.w > floorx) cmask |= 8u;
         }
-        append_row(st, cmask, ctr, (u32)((r_begin + t) * W + col0), buf, hist, minx, ghist, gfloor_ptr, count_ptr, list,
+        append_row(st, cmask, ctr, (u32)((r_begin + t) * W + col0), buf, hist, minx, sf, count_ptr, list,
                    p.cap, K, lane, pre, xscale, satx);
       }
       if ((t & 7) == 7) {
@@ -522,7 +593,7 @@ __global__ void __launch_bounds__(kThreads, 4) sdnet_peaks_kernel(const __grid_c
     feed.end_unit();
     if (st.nbuf) {
       __syncwarp();
-      flush_candidates(st, buf, hist, minx, ghist, gfloor_ptr, count_ptr, list, p.cap, K, lane, pre, xscale, satx);
+      flush_candidates(st, buf, hist, minx, sf, count_ptr, list, p.cap, K, lane, pre, xscale, satx);
     }
   }
 }
@@ -531,52 +602,57 @@ __global__ void __launch_bounds__(kThreads, 4) sdnet_peaks_kernel(const __grid_c
 // peaks kernel, warp-specialised form (the fast path; needs 16 B-aligned rows and W <= 896)
 //
 // CTA = NC consumer warps + 1 producer warp, working on one (plane, row strip) unit at a time.
-// The producer streams whole image rows (W*4 contiguous bytes) into a shared-memory ring with
-// 1-D bulk copies (TMA unit, SASS UBLKCP), four rows per mbarrier ("group"); consumer warp w
-// owns columns [128 w, 128 w + 128) of every row.  Ring row layout (floats):
-//     [4 x -inf | W columns | -inf up to 128 NC + 8]
-// so the horizontal neighbours of any pixel -- including across warps and beyond the image
-// edge -- are plain shared-memory reads.  Per group of four output rows a consumer waits on
-// one barrier, reads its four centre rows (4 x LDS.128), takes the max of the 16 values and
-// votes "does anything here beat the pruning floor?"; only then does it look at single rows.
+// The producer streams whole image rows into a shared-memory ring with 1-D bulk copies (TMA
+// unit, SASS UBLKCP): four rows per mbarrier ("group"), and -- when the plane is dense in
+// memory -- ONE copy of 4*W*4 contiguous bytes per group.  Ring rows are dense (W floats), so
+// horizontal neighbours, also across warps, are plain shared-memory reads; the two image-edge
+// cases are patched with -inf by the few lanes that touch them.  Consumer warp w owns columns
+// [128 w, 128 w + 128).  Per group of four output rows it waits on one barrier, reads its four
+// centre rows (4 x LDS.128), takes the max of the 16 values and votes "does anything here beat
+// the pruning floor?"; only then does it look at single rows.
 // ---------------------------------------------------------------------------------------------
 constexpr int kGroupRows = 4;
 constexpr int kMaxConsumers = 7;
 
 struct CtaGeom {
   int nc;       // consumer warps
-  int rpb;      // ring row pitch in bytes
+  int rpb;      // ring row pitch in bytes (= W * 4)
   int ng;       // ring groups
   int smem;     // dynamic shared memory per CTA
 };
 
-__host__ __device__ inline CtaGeom cta_geometry(int W, int ng) {
+inline CtaGeom cta_geometry(int W, int ng) {
   CtaGeom g;
   g.nc = (W + kPanelW - 1) / kPanelW;
-  g.rpb = (kPanelW * g.nc + 8) * 4;
+  g.rpb = W * 4;
   g.ng = ng;
-  g.smem = ng * kGroupRows * g.rpb + 2 * ng * 8 + g.nc * (kBins * 8 + kBuf * 8);
+  // ring, 512 B of slack (lanes past the last column read harmlessly beyond their row),
+  // barriers, per-consumer pruning state
+  g.smem = ng * kGroupRows * g.rpb + 512 + 2 * ng * 8 + 2 * kFineBins * 4 + 64 + g.nc * (kBins * 8 + kBuf * 8);
   return g;
 }
 
-// window maxima of a lane's four pixels for output row t, straight from the ring
-// (ring rows are contiguous in shared memory, so ring row q of a unit whose first group has running
-// number n lives at row (4 n + q) mod (4 NG): `rowbase` = 4 n, `rowmask` = 4 NG - 1)
+// Window maxima of a lane's four pixels for output row t, straight from the ring.  Ring rows
+// are contiguous in shared memory, so ring row q of a unit whose first group has running number
+// n lives at row (4 n + q) mod (4 NG): `rowbase` = 4 n, `rowmask` = 4 NG - 1.
 template <int R>
-__device__ __forceinline__ void window_max(u32 ring_own, u32 rowbase, u32 rowmask, int rpb, int t, float& h0,
-                                           float& h1, float& h2, float& h3) {
+__device__ __forceinline__ void window_max(u32 ring_own, u32 rowbase, u32 rowmask, int rpb, int t, bool left_ok,
+                                           bool right_ok, float& h0, float& h1, float& h2, float& h3) {
   const float ninf = -CUDART_INF_F;
   float v0 = ninf, v1 = ninf, v2 = ninf, v3 = ninf, v4 = ninf, v5 = ninf, v6 = ninf, v7 = ninf;  // cols c-2 .. c+5
+  const u32 loff = left_ok ? 8u : 0u;  // column 0 has no left neighbours (and nothing mapped before the ring)
 #pragma unroll
   for (int d = 0; d <= 2 * R; ++d) {
     const u32 a = ring_own + ((rowbase + (u32)(t + d)) & rowmask) * rpb;
     const float4 o = lds128(a);
-    const float2 l = lds64(a - 8);
+    const float2 l = lds64(a - loff);
     const float2 r = lds64(a + 16);
     v0 = fmaxf(v0, l.x); v1 = fmaxf(v1, l.y);
     v2 = fmaxf(v2, o.x); v3 = fmaxf(v3, o.y); v4 = fmaxf(v4, o.z); v5 = fmaxf(v5, o.w);
     v6 = fmaxf(v6, r.x); v7 = fmaxf(v7, r.y);
   }
+  if (!left_ok) { v0 = ninf; v1 = ninf; }    // beyond the left image edge: max_pool2d's -inf padding
+  if (!right_ok) { v6 = ninf; v7 = ninf; }   // beyond the right image edge
   if (R == 2) {
     const float m34 = fmaxf(v3, v4);
     h0 = max3(fmaxf(v0, v1), v2, m34);
@@ -592,22 +668,25 @@ __device__ __forceinline__ void window_max(u32 ring_own, u32 rowbase, u32 rowmas
 }
 
 template <int R, int NG>
-__global__ void __launch_bounds__((kMaxConsumers + 1) * 32) sdnet_peaks_cta_kernel(const __grid_constant__ PeaksParams p) {
+__global__ void __launch_bounds__((kMaxConsumers + 1) * 32, 3) sdnet_peaks_cta_kernel(const __grid_constant__ PeaksParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   static_assert((NG & (NG - 1)) == 0, "ring groups must be a power of two");
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int nc = (int)(blockDim.x >> 5) - 1;
-  const int rpb = (kPanelW * nc + 8) * 4;
-  const u32 ring_s = smem_u32(smem_raw);
-  const u32 full_s = ring_s + NG * kGroupRows * rpb;
-  const u32 empty_s = full_s + NG * 8;
-  unsigned char* wstate = smem_raw + NG * kGroupRows * rpb + 2 * NG * 8;
   const int C = p.M + p.N;
   const int H = p.H, W = p.W;
+  const int rpb = W * 4;
+  const u32 ring_s = smem_u32(smem_raw);
+  const u32 full_s = ring_s + NG * kGroupRows * rpb + 512;
+  const u32 empty_s = full_s + NG * 8;
+  // CTA-wide pruning state, double-buffered by unit parity: [2][kFineBins] histogram, then
+  // floor bin [2] and finished-consumer count [2]
+  u32* cta_hist = reinterpret_cast<u32*>(smem_raw + NG * kGroupRows * rpb + 512 + 2 * NG * 8);
+  int* cta_floor = reinterpret_cast<int*>(cta_hist + 2 * kFineBins);
+  volatile int* cta_done = cta_floor + 2;
+  unsigned char* wstate = reinterpret_cast<unsigned char*>(cta_hist + 2 * kFineBins) + 64;
 
-  // one-time setup: barriers, ring parked at -inf (everything a copy never overwrites must read
-  // as max_pool2d's -inf padding)
   if (threadIdx.x == 0) {
     for (int i = 0; i < NG; ++i) {
       mbar_init(full_s + 8 * i, 1);
@@ -615,15 +694,27 @@ __global__ void __launch_bounds__((kMaxConsumers + 1) * 32) sdnet_peaks_cta_kern
     }
     mbar_fence_init();
   }
-  for (int i = threadIdx.x; i < NG * kGroupRows * rpb / 16; i += blockDim.x) sts128(ring_s + 16 * i, -CUDART_INF_F);
-  fence_proxy_async();
+  for (int i = threadIdx.x; i < 2 * kFineBins + 16; i += blockDim.x) cta_hist[i] = 0;  // histograms + control words
   __syncthreads();
 
   if (warp == nc) {
     // ================================ producer warp ================================
-    const u32 row_bytes = (u32)W * 4;
+    const u32 row_bytes = (u32)rpb;
     u32 n = 0;  // running group number: slot n % NG, phase (n / NG) & 1
-    for (u32 unit = blockIdx.x; unit < (u32)p.units; unit += gridDim.x) {
+    int uo = 0;  // ordinal of the unit within this CTA
+    for (u32 unit = blockIdx.x; unit < (u32)p.units; unit += gridDim.x, ++uo) {
+      if (uo >= 2) {
+        // recycle the CTA-wide histogram of unit uo-2: wait until all its consumers are done
+        // (they are, unless units are only a few rows long), then clear it.  Consumers see the
+        // cleared state through the release/acquire of this unit's first full barrier.
+        const int slot = uo & 1;
+        const int want = nc * (uo >> 1);
+        if (lane == 0) while (cta_done[slot] < want) __nanosleep(64);
+        __syncwarp();
+        for (int i = lane; i < kFineBins; i += 32) cta_hist[slot * kFineBins + i] = 0;
+        if (lane == 0) cta_floor[slot] = 0;
+        __syncwarp();
+      }
       const int strip = unit % p.strips;
       const int plane_id = unit / p.strips;
       const int b = plane_id / C, c = plane_id % C;
@@ -632,39 +723,47 @@ __global__ void __launch_bounds__((kMaxConsumers + 1) * 32) sdnet_peaks_cta_kern
       const float* plane = vw.data + (long long)b * vw.sb + (long long)(is_anchor ? c : c - p.M) * vw.sc;
       const int r_begin = strip * p.rows_per_strip;
       const int r_end = min(H, r_begin + p.rows_per_strip);
-      const int q_count = r_end - r_begin + 2 * R;      // ring rows of this unit: image rows r_begin-R ..
+      const int q_count = r_end - r_begin + 2 * R;  // ring rows of this unit: image rows r_begin-R .. r_end-1+R
+      const int q_lo = max(0, R - r_begin);          // first ring row that lies inside the image
+      const int q_hi = min(q_count, H - (r_begin - R));  // one past the last ring row inside the image
       const int groups = (q_count + kGroupRows - 1) / kGroupRows;
       const long long pitch = vw.sh * 4;
+      const bool dense = pitch == (long long)row_bytes;
       const char* src0 = reinterpret_cast<const char*>(plane) + (long long)(r_begin - R) * pitch;
+      // Optional L2 prefetch ahead of the ring (SDNET_L2_PREFETCH_GROUPS): DRAM latency is then
+      // absorbed by L2 rather than by the small shared-memory ring.
+      const int pf = p.l2_prefetch_groups;
+      if (pf > 0 && dense && lane == 0) {
+        const int v1p = min(min(pf * kGroupRows, q_count), q_hi);
+        if (v1p > q_lo) bulk_prefetch_l2(src0 + (long long)q_lo * pitch, (u32)(v1p - q_lo) * row_bytes);
+      }
       for (int j = 0; j < groups; ++j, ++n) {
         const u32 slot = n & (NG - 1);
-        mbar_wait(empty_s + 8 * slot, ((n / NG) & 1u) ^ 1u);  // consumers are done with this slot
-        u32 valid = 0, fill = 0;
-#pragma unroll
-        for (int i = 0; i < kGroupRows; ++i) {
-          const int q = j * kGroupRows + i;
-          if (q < q_count) {
-            if ((unsigned)(r_begin - R + q) < (unsigned)H) valid |= 1u << i;
-            else fill |= 1u << i;
-          }
+        const int q0 = j * kGroupRows, q1 = min(q0 + kGroupRows, q_count);
+        if (pf > 0 && dense && lane == 0) {
+          const int pq0 = max((j + pf) * kGroupRows, q_lo), pq1 = min(min((j + pf + 1) * kGroupRows, q_count), q_hi);
+          if (pq1 > pq0) bulk_prefetch_l2(src0 + (long long)pq0 * pitch, (u32)(pq1 - pq0) * row_bytes);
         }
-        if (fill) {  // rows above / below the image: -inf
-#pragma unroll
-          for (int i = 0; i < kGroupRows; ++i)
-            if ((fill >> i) & 1u)
-              for (int k = lane; k < rpb / 16; k += 32) sts128(ring_s + (slot * kGroupRows + i) * rpb + 16 * k, -CUDART_INF_F);
+        const int v0 = max(q0, q_lo), v1 = min(q1, q_hi);  // [v0, v1) = rows of this group inside the image
+        mbar_wait(empty_s + 8 * slot, ((n / NG) & 1u) ^ 1u);  // consumers are done with this slot
+        if (v0 > q0 || v1 < q1) {  // rows above / below the image: -inf (max_pool2d's padding)
+          for (int q = q0; q < q1; ++q)
+            if (q < v0 || q >= v1)
+              for (int k = lane; k < rpb / 16; k += 32) sts128(ring_s + (slot * kGroupRows + (q - q0)) * rpb + 16 * k, -CUDART_INF_F);
           fence_proxy_async();
           __syncwarp();
         }
         if (lane == 0) {
           const u32 bar = full_s + 8 * slot;
-          if (valid) {
-            mbar_arrive_expect_tx(bar, (u32)__popc(valid) * row_bytes);
-#pragma unroll
-            for (int i = 0; i < kGroupRows; ++i)
-              if ((valid >> i) & 1u)
-                bulk_g2s(ring_s + (slot * kGroupRows + i) * rpb + 16, src0 + (long long)(j * kGroupRows + i) * pitch,
-                         row_bytes, bar);
+          if (v1 > v0) {
+            mbar_arrive_expect_tx(bar, (u32)(v1 - v0) * row_bytes);
+            if (dense) {
+              bulk_g2s(ring_s + (slot * kGroupRows + (v0 - q0)) * rpb, src0 + (long long)v0 * pitch,
+                       (u32)(v1 - v0) * row_bytes, bar);
+            } else {
+              for (int q = v0; q < v1; ++q)
+                bulk_g2s(ring_s + (slot * kGroupRows + (q - q0)) * rpb, src0 + (long long)q * pitch, row_bytes, bar);
+            }
           } else {
             mbar_arrive(bar);
           }
@@ -683,9 +782,14 @@ __global__ void __launch_bounds__((kMaxConsumers + 1) * 32) sdnet_peaks_cta_kern
   const float xscale = pre ? kPreScale : 1.0f;
   const float satx = pre ? CUDART_INF_F : kSatX;
   const int col0 = kPanelW * warp + 4 * lane;
-  const u32 own_off = (u32)(4 + col0) * 4;
+  const bool lane_ok = col0 < W;          // W % 4 == 0: a lane's four columns are all inside or all outside
+  const bool left_ok = col0 > 0;
+  const bool right_ok = col0 + 4 < W;
+  const u32 ring_own = ring_s + (u32)col0 * 4;
+  const float ninf = -CUDART_INF_F;
   u32 n = 0;
-  for (u32 unit = blockIdx.x; unit < (u32)p.units; unit += gridDim.x) {
+  int uo = 0;
+  for (u32 unit = blockIdx.x; unit < (u32)p.units; unit += gridDim.x, ++uo) {
     const int strip = unit % p.strips;
     const int plane_id = unit / p.strips;
     const int c = plane_id % C;
@@ -697,11 +801,17 @@ __global__ void __launch_bounds__((kMaxConsumers + 1) * 32) sdnet_peaks_cta_kern
     const int groups_out = (nrows + kGroupRows - 1) / kGroupRows;
     u64* __restrict__ list = p.lists + (size_t)plane_id * p.cap;
     int* count_ptr = p.counts + plane_id;
-    u32* ghist = p.ghist + (size_t)plane_id * kBins;
     int* gfloor_ptr = p.gfloor + plane_id;
+    SharedFloors sf;
+    sf.cta_hist = cta_hist + (uo & 1) * kFineBins;
+    sf.cta_floor = cta_floor + (uo & 1);
+    // with one strip per plane this CTA sees the whole plane: no plane-wide exchange needed
+    sf.ghist = p.strips > 1 ? p.ghist + (size_t)plane_id * kFineBins : nullptr;
+    sf.gfloor = gfloor_ptr;
+    const volatile int* cta_floor_v = sf.cta_floor;
 
     UnitState st;
-    st.floorx = shared_floor(__ldcg(gfloor_ptr), xscale);
+    st.floorx = p.strips > 1 ? shared_floor(__ldcg(gfloor_ptr), xscale) : -CUDART_INF_F;
     st.emitted = 0;
     st.nbuf = 0;
     __syncwarp();
@@ -709,55 +819,63 @@ __global__ void __launch_bounds__((kMaxConsumers + 1) * 32) sdnet_peaks_cta_kern
     *reinterpret_cast<int4*>(minx + 4 * lane) = make_int4(0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff);
     __syncwarp();
 
-    const u32 ring_own = ring_s + own_off;
     const u32 rowbase = n * kGroupRows;
+    constexpr u32 kRowMask = NG * kGroupRows - 1;
+    int gfloor_seen = 0;
     mbar_wait(full_s + 8 * (n & (NG - 1)), (n / NG) & 1u);
     for (int g = 0; g < groups_out; ++g) {
       const u32 n0 = n + g, n1 = n0 + 1;
       if (g + 1 < groups) mbar_wait(full_s + 8 * (n1 & (NG - 1)), (n1 / NG) & 1u);
-      const int gfloor_next = __ldcg(gfloor_ptr);  // consumed at the end of the group: latency hidden
-      const u32 gb0 = ring_s + (n0 & (NG - 1)) * kGroupRows * rpb + own_off;
-      const u32 gb1 = ring_s + (n1 & (NG - 1)) * kGroupRows * rpb + own_off;
+      // the floor the other warps of this CTA have reached (shared memory, always fresh) ...
+      st.floorx = fmaxf(st.floorx, shared_floor(*cta_floor_v, xscale));
+      if (p.strips > 1 && (g & 7) == 0) {
+        // ... and, every 32 rows, the one other CTAs working on this plane published (global
+        // memory; applied one period late so the load latency is never exposed)
+        st.floorx = fmaxf(st.floorx, shared_floor(gfloor_seen, xscale));
+        gfloor_seen = __ldcg(gfloor_ptr);
+      }
       const int t0 = g * kGroupRows;
       // centre row of output row t0+i is ring row t0+i+R
-      float4 c0, c1, c2, c3;
-      if (R == 2) {
-        c0 = lds128(gb0 + 2 * rpb); c1 = lds128(gb0 + 3 * rpb);
-      } else {
-        c0 = lds128(gb0 + 1 * rpb); c1 = lds128(gb0 + 2 * rpb);
+      const u32 a0 = ring_own + ((rowbase + (u32)(t0 + R)) & kRowMask) * rpb;
+      const u32 a1 = ring_own + ((rowbase + (u32)(t0 + R + 1)) & kRowMask) * rpb;
+      const u32 a2 = ring_own + ((rowbase + (u32)(t0 + R + 2)) & kRowMask) * rpb;
+      const u32 a3 = ring_own + ((rowbase + (u32)(t0 + R + 3)) & kRowMask) * rpb;
+      const int rows_here = min(kGroupRows, nrows - t0);
+      const float4 c0 = lds128(a0);
+      const float4 c1 = lds128(a1);   // rows past the strip hold stale data: masked out just below
+      const float4 c2 = lds128(a2);
+      const float4 c3 = lds128(a3);
+      float m0 = fmaxf(fmaxf(c0.x, c0.y), fmaxf(c0.z, c0.w));
+      float m1 = fmaxf(fmaxf(c1.x, c1.y), fmaxf(c1.z, c1.w));
+      float m2 = fmaxf(fmaxf(c2.x, c2.y), fmaxf(c2.z, c2.w));
+      float m3 = fmaxf(fmaxf(c3.x, c3.y), fmaxf(c3.z, c3.w));
+      if (rows_here < kGroupRows) {  // last, partial group of the strip (warp-uniform)
+        if (rows_here < 2) m1 = ninf;
+        if (rows_here < 3) m2 = ninf;
+        m3 = ninf;
       }
-      if (t0 + 3 < nrows) {
-        if (R == 2) { c2 = lds128(gb1); c3 = lds128(gb1 + rpb); }
-        else { c2 = lds128(gb0 + 3 * rpb); c3 = lds128(gb1); }
-      } else {
-        // last, partial group: rows past the strip do not exist
-        const float4 none = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
-        if (t0 + 1 >= nrows) c1 = none;
-        c2 = none; c3 = none;
-        if (t0 + 2 < nrows) c2 = (R == 2) ? lds128(gb1) : lds128(gb0 + 3 * rpb);
-      }
-      const float m0 = fmaxf(fmaxf(c0.x, c0.y), fmaxf(c0.z, c0.w));
-      const float m1 = fmaxf(fmaxf(c1.x, c1.y), fmaxf(c1.z, c1.w));
-      const float m2 = fmaxf(fmaxf(c2.x, c2.y), fmaxf(c2.z, c2.w));
-      const float m3 = fmaxf(fmaxf(c3.x, c3.y), fmaxf(c3.z, c3.w));
-      if (__any_sync(0xffffffffu, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) > st.floorx)) {
+      const float m = lane_ok ? fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) : ninf;
+      if (__any_sync(0xffffffffu, m > st.floorx)) {
         // something in these four rows beats the floor: visit only the rows that do (kept as a
         // real loop so the row code exists once -- it is large and instruction-cache bound)
-        u32 rowmask4 = (__any_sync(0xffffffffu, m0 > st.floorx) ? 1u : 0u) | (__any_sync(0xffffffffu, m1 > st.floorx) ? 2u : 0u) |
-                       (__any_sync(0xffffffffu, m2 > st.floorx) ? 4u : 0u) | (__any_sync(0xffffffffu, m3 > st.floorx) ? 8u : 0u);
+        u32 rowmask4 = (__any_sync(0xffffffffu, lane_ok && m0 > st.floorx) ? 1u : 0u) |
+                       (__any_sync(0xffffffffu, lane_ok && m1 > st.floorx) ? 2u : 0u) |
+                       (__any_sync(0xffffffffu, lane_ok && m2 > st.floorx) ? 4u : 0u) |
+                       (__any_sync(0xffffffffu, lane_ok && m3 > st.floorx) ? 8u : 0u);
 #pragma unroll 1
         while (rowmask4) {
           const int i = __ffs(rowmask4) - 1;
           rowmask4 &= rowmask4 - 1;
           const int t = t0 + i;
-          const float4 ctr = lds128(ring_own + ((rowbase + (u32)(t + R)) & (NG * kGroupRows - 1)) * rpb);
+          float4 ctr = lds128(ring_own + ((rowbase + (u32)(t + R)) & kRowMask) * rpb);
+          if (!lane_ok) ctr = make_float4(ninf, ninf, ninf, ninf);
           const float floorx = st.floorx;
           const float mi = fmaxf(fmaxf(ctr.x, ctr.y), fmaxf(ctr.z, ctr.w));
           if (!__any_sync(0xffffffffu, mi > floorx)) continue;  // an earlier row of the group raised the floor
           u32 cmask = 0;
           if (!pre) {
             float h0, h1, h2, h3;
-            window_max<R>(ring_own, rowbase, NG * kGroupRows - 1, rpb, t, h0, h1, h2, h3);
+            window_max<R>(ring_own, rowbase, kRowMask, rpb, t, left_ok, right_ok, h0, h1, h2, h3);
             cmask = classify_row<R>(ctr, h0, h1, h2, h3, floorx);
           } else {
             if (ctr.x > floorx) cmask |= 1u;
@@ -765,14 +883,18 @@ __global__ void __launch_bounds__((kMaxConsumers + 1) * 32) sdnet_peaks_cta_kern
             if (ctr.z > floorx) cmask |= 4u;
             if (ctr.w > floorx) cmask |= 8u;
           }
-          append_row(st, cmask, ctr, (u32)((r_begin + t) * W + col0), buf, hist, minx, ghist, gfloor_ptr, count_ptr,
+          append_row(st, cmask, ctr, (u32)((r_begin + t) * W + col0), buf, hist, minx, sf, count_ptr,
                      list, p.cap, K, lane, pre, xscale, satx);
         }
       }
       // every lane's reads of group n0 are consumed (the votes above): hand the slot back
       __syncwarp();
       if (lane == 0) mbar_arrive(empty_s + 8 * (n0 & (NG - 1)));
-      st.floorx = fmaxf(st.floorx, shared_floor(gfloor_next, xscale));
+      // while the CTA has no floor yet, publish early and often; later only in batches
+      if (st.nbuf >= 16 || (st.nbuf > 0 && *cta_floor_v == 0)) {
+        __syncwarp();
+        flush_candidates(st, buf, hist, minx, sf, count_ptr, list, p.cap, K, lane, pre, xscale, satx);
+      }
     }
     if (groups > groups_out) {  // a trailing group that only held the bottom halo rows
       __syncwarp();
@@ -781,8 +903,10 @@ __global__ void __launch_bounds__((kMaxConsumers + 1) * 32) sdnet_peaks_cta_kern
     n += (u32)groups;
     if (st.nbuf) {
       __syncwarp();
-      flush_candidates(st, buf, hist, minx, ghist, gfloor_ptr, count_ptr, list, p.cap, K, lane, pre, xscale, satx);
+      flush_candidates(st, buf, hist, minx, sf, count_ptr, list, p.cap, K, lane, pre, xscale, satx);
     }
+    __syncwarp();
+    if (lane == 0) atomicAdd(const_cast<int*>(cta_done) + (uo & 1), 1);  // this warp is done with the unit's shared state
   }
 }
 
@@ -1285,7 +1409,7 @@ Workspace plan_workspace(int B, int M, int N, int H, int W, int K, int P) {
   ws.off_flags = off;  off = align_up(off + planes * sizeof(int), 256);
   ws.off_sched = off;  off = align_up(off + 64, 256);
   ws.off_gfloor = off; off = align_up(off + planes * sizeof(int), 256);
-  ws.off_ghist = off;  off = align_up(off + planes * kBins * sizeof(u32), 256);
+  ws.off_ghist = off;  off = align_up(off + planes * kFineBins * sizeof(u32), 256);
   ws.off_lists = off;  off = align_up(off + planes * (size_t)ws.cap * sizeof(u64), 256);
   ws.total = off;
   return ws;
@@ -1362,6 +1486,7 @@ int launch_decode(const SdnetDecodeParams* p, cudaStream_t stream, cudaEvent_t* 
   pp.sched = reinterpret_cast<u32*>(base + ws.off_sched);
   pp.ghist = reinterpret_cast<u32*>(base + ws.off_ghist);
   pp.gfloor = reinterpret_cast<int*>(base + ws.off_gfloor);
+  pp.l2_prefetch_groups = 0;
   const int sms = device_sm_count();
   const bool aligned = view_aligned(p->anchor_hm, p->W) && view_aligned(p->part_hm, p->W);
   const bool use_cta = aligned && p->W <= kPanelW * kMaxConsumers && !(p->flags & SDNET_FLAG_WARP_KERNEL);
@@ -1378,6 +1503,11 @@ int launch_decode(const SdnetDecodeParams* p, cudaStream_t stream, cudaEvent_t* 
       const char* e = getenv("SDNET_RING_GROUPS");
       return (e && atoi(e) == 8) ? 8 : 4;
     }();
+    static const int l2_pf = [] {
+      const char* e = getenv("SDNET_L2_PREFETCH_GROUPS");
+      return e ? atoi(e) : 0;
+    }();
+    pp.l2_prefetch_groups = l2_pf;
     const CtaGeom geom = cta_geometry(p->W, ring_groups);
     auto kern = ring_groups == 8
                     ? (p->radius == 2 ? sdnet_peaks_cta_kernel<2, 8> : sdnet_peaks_cta_kernel<1, 8>)

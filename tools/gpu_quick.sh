@@ -6,6 +6,6 @@ for gb in 1024 128; do
   python - <<PY
 import json
 d=json.load(open("gpurun_out/q_${tag}_$gb.json")); r=d["roofline"]
-print("$tag noise", $gb, "img/s %.0f" % d["value"], {k: round(v,4) for k,v in r["kernel_ms"].items()}, "frac %.3f" % r["frac"])
+print("$tag noise", $gb, "img/s %.0f" % d["value"], {k: round(v,4) for k,v in r["kernel_ms"].items()}, "frac %.3f" % r["frac"], "cand/plane %.0f" % d["detections"]["candidates_per_plane_mean"])
 PY
 done
