@@ -28,6 +28,7 @@
 //   * ties: (score desc, class asc, flat index asc) -- what torch.topk does on CUDA for k > 32;
 //   * grouping arithmetic uses explicitly rounded mul/add/sqrt (no FMA contraction) and the
 //     first minimum wins.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include <stdint.h>
@@ -115,14 +116,6 @@ constexpr int kPeaksSmem = kWarps * kPeaksSmemPerWarp;
 
 __device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
 // predicated cp.async: global -> shared, no register staging
-__device__ __forceinline__ void cp_async16_if(u32 dst, const void* src, bool pred) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p cp.async.cg.shared.global [%0], [%1], 16;\n\t}"
-               ::"r"(dst), "l"(src), "r"((int)pred));
-}
-__device__ __forceinline__ void cp_async8_if(u32 dst, const void* src, bool pred) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p cp.async.ca.shared.global [%0], [%1], 8;\n\t}"
-               ::"r"(dst), "l"(src), "r"((int)pred));
-}
 __device__ __forceinline__ void cp_async4_if(u32 dst, const void* src, bool pred) {
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p cp.async.ca.shared.global [%0], [%1], 4;\n\t}"
                ::"r"(dst), "l"(src), "r"((int)pred));
@@ -474,7 +467,7 @@ __device__ __forceinline__ void append_row(UnitState& st, u32 cmask, const float
 
 template <bool kAligned, int R>
 __global__ void __launch_bounds__(kThreads, 4) sdnet_peaks_kernel(const __grid_constant__ PeaksParams p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   unsigned char* wbase = smem_raw + (size_t)warp * kPeaksSmemPerWarp;
@@ -669,7 +662,7 @@ __device__ __forceinline__ void window_max(u32 ring_own, u32 rowbase, u32 rowmas
 
 template <int R, int NG>
 __global__ void __launch_bounds__((kMaxConsumers + 1) * 32, 3) sdnet_peaks_cta_kernel(const __grid_constant__ PeaksParams p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   static_assert((NG & (NG - 1)) == 0, "ring groups must be a power of two");
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -907,6 +900,184 @@ __global__ void __launch_bounds__((kMaxConsumers + 1) * 32, 3) sdnet_peaks_cta_k
     }
     __syncwarp();
     if (lane == 0) atomicAdd(const_cast<int*>(cta_done) + (uo & 1), 1);  // this warp is done with the unit's shared state
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// peaks kernel, TMA-tile form (the default fast path; needs 16 B-aligned rows)
+//
+// Every warp is an autonomous pipeline over one (plane, row strip, 128-column panel) unit.
+// An elected lane pulls 4-row x 136-column tiles (the panel plus four columns either side)
+// into the warp's private shared-memory ring with 2-D tensor-map bulk copies (TMA, SASS
+// UTMALDG), completion on one mbarrier per ring slot.  The tensor map is encoded with NaN
+// out-of-bounds fill: fmaxf ignores a NaN operand and every ordered comparison with NaN is
+// false, so out-of-image rows and columns behave exactly like max_pool2d's -inf padding with
+// no edge code at all.  Per group of four output rows the warp waits on one barrier, reads its
+// four centre rows (4 x LDS.128), takes the max of the 16 values and votes "does anything here
+// beat the pruning floor?"; only then does it look at single rows.  No warp ever waits for
+// another warp.
+// ---------------------------------------------------------------------------------------------
+constexpr int kTileCols = kPanelW + 8;
+constexpr int kTilePitchB = kTileCols * 4;                   // 544 B per ring row
+constexpr int kTileBytes = kGroupRows * kTilePitchB;         // 2176 B per TMA tile (17 x 128 B)
+constexpr int kTileWarps = 4;
+constexpr int kTileNG = 4;                                   // ring slots (tiles) per warp
+constexpr int kTileSmemPerWarp = ((kTileNG * kTileBytes + kTileNG * 8 + kBins * 8 + kBuf * 8) + 127) / 128 * 128;
+constexpr int kTileSmem = kTileWarps * kTileSmemPerWarp;
+
+__device__ __forceinline__ void tma_tile_4d(u32 dst, const CUtensorMap* map, int x, int y, int c, int b, u32 bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+      ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(c), "r"(b), "r"(bar) : "memory");
+}
+
+template <int R>
+__global__ void __launch_bounds__(kTileWarps * 32, 5)
+sdnet_peaks_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_constant__ CUtensorMap tm_anchor,
+                        const __grid_constant__ CUtensorMap tm_part) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int NG = kTileNG;
+  constexpr u32 kRowMask = NG * kGroupRows - 1;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  unsigned char* wbase = smem_raw + (size_t)warp * kTileSmemPerWarp;
+  const u32 ring_s = smem_u32(wbase);
+  const u32 bars_s = ring_s + NG * kTileBytes;
+  u32* hist = reinterpret_cast<u32*>(wbase + NG * kTileBytes + NG * 8);
+  int* minx = reinterpret_cast<int*>(hist + kBins);
+  u64* buf = reinterpret_cast<u64*>(minx + kBins);
+  const bool pre = p.pre_activated != 0;
+  const float xscale = pre ? kPreScale : 1.0f;
+  const float satx = pre ? CUDART_INF_F : kSatX;
+  const int C = p.M + p.N;
+  const int H = p.H, W = p.W;
+  const u32 ring_own = ring_s + (u32)(4 + 4 * lane) * 4;
+  const float ninf = -CUDART_INF_F;
+
+  if (lane == 0) {
+    for (int i = 0; i < NG; ++i) mbar_init(bars_s + 8 * i, 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
+
+  u32 seq = 0;  // running tile number of this warp: slot seq % NG, phase (seq / NG) & 1
+  for (;;) {
+    u32 unit = 0;
+    if (lane == 0) unit = atomicAdd(p.sched, 1u);
+    unit = __shfl_sync(0xffffffffu, unit, 0);
+    if (unit >= (u32)p.units) break;
+    const int panel = unit % p.panels;
+    const int t1 = unit / p.panels;
+    const int strip = t1 % p.strips;
+    const int plane_id = t1 / p.strips;
+    const int b = plane_id / C, c = plane_id % C;
+    const bool is_anchor = c < p.M;
+    const CUtensorMap* tmap = is_anchor ? &tm_anchor : &tm_part;
+    const int csel = is_anchor ? c : c - p.M;
+    const int K = is_anchor ? p.K : p.P;
+    const int col0 = panel * kPanelW + 4 * lane;
+    const int x0 = panel * kPanelW - 4;
+    const int r_begin = strip * p.rows_per_strip;
+    const int r_end = min(H, r_begin + p.rows_per_strip);
+    const int nrows = r_end - r_begin;
+    const int y0 = r_begin - R;  // image row of ring row 0
+    const int groups = (nrows + 2 * R + kGroupRows - 1) / kGroupRows;
+    const int groups_out = (nrows + kGroupRows - 1) / kGroupRows;
+    u64* __restrict__ list = p.lists + (size_t)plane_id * p.cap;
+    int* count_ptr = p.counts + plane_id;
+    int* gfloor_ptr = p.gfloor + plane_id;
+    SharedFloors sf;
+    sf.cta_hist = nullptr; sf.cta_floor = nullptr;
+    sf.ghist = p.ghist + (size_t)plane_id * kFineBins;
+    sf.gfloor = gfloor_ptr;
+
+    UnitState st;
+    st.floorx = shared_floor(__ldcg(gfloor_ptr), xscale);
+    st.emitted = 0;
+    st.nbuf = 0;
+    __syncwarp();  // everyone is done with the previous unit's ring, histogram and buffer
+    *reinterpret_cast<uint4*>(hist + 4 * lane) = make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<int4*>(minx + 4 * lane) = make_int4(0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff);
+    __syncwarp();
+
+    // tile j of the unit = ring rows 4j..4j+3 = image rows y0+4j..; slot (seq + j) % NG
+    if (lane == 0) {
+      const int first = min(NG, groups);
+      for (int j = 0; j < first; ++j) {
+        const u32 slot = (seq + j) & (NG - 1);
+        mbar_arrive_expect_tx(bars_s + 8 * slot, kTileBytes);
+        tma_tile_4d(ring_s + slot * kTileBytes, tmap, x0, y0 + kGroupRows * j, csel, b, bars_s + 8 * slot);
+      }
+    }
+    const u32 rowbase = seq * kGroupRows;
+    int gfloor_seen = 0;
+    mbar_wait(bars_s + 8 * (seq & (NG - 1)), (seq / NG) & 1u);
+    for (int g = 0; g < groups_out; ++g) {
+      const u32 n0 = seq + g, n1 = n0 + 1;
+      if (g + 1 < groups) mbar_wait(bars_s + 8 * (n1 & (NG - 1)), (n1 / NG) & 1u);
+      if ((g & 3) == 0) {
+        // every 16 rows: apply the plane-wide floor fetched 16 rows ago (latency never exposed)
+        // and start the next fetch
+        st.floorx = fmaxf(st.floorx, shared_floor(gfloor_seen, xscale));
+        gfloor_seen = __ldcg(gfloor_ptr);
+      }
+      const int t0 = g * kGroupRows;
+      // centre row of output row t0+i is ring row t0+i+R
+      const float4 c0 = lds128(ring_own + ((rowbase + (u32)(t0 + R)) & kRowMask) * kTilePitchB);
+      const float4 c1 = lds128(ring_own + ((rowbase + (u32)(t0 + R + 1)) & kRowMask) * kTilePitchB);
+      const float4 c2 = lds128(ring_own + ((rowbase + (u32)(t0 + R + 2)) & kRowMask) * kTilePitchB);
+      const float4 c3 = lds128(ring_own + ((rowbase + (u32)(t0 + R + 3)) & kRowMask) * kTilePitchB);
+      const int rows_here = min(kGroupRows, nrows - t0);
+      float m0 = fmaxf(fmaxf(c0.x, c0.y), fmaxf(c0.z, c0.w));
+      float m1 = fmaxf(fmaxf(c1.x, c1.y), fmaxf(c1.z, c1.w));
+      float m2 = fmaxf(fmaxf(c2.x, c2.y), fmaxf(c2.z, c2.w));
+      float m3 = fmaxf(fmaxf(c3.x, c3.y), fmaxf(c3.z, c3.w));
+      if (rows_here < kGroupRows) {  // last, partial group of the strip (warp-uniform): rows past it belong to the next strip
+        if (rows_here < 2) m1 = ninf;
+        if (rows_here < 3) m2 = ninf;
+        m3 = ninf;
+      }
+      if (__any_sync(0xffffffffu, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) > st.floorx)) {
+        // something in these four rows beats the floor: visit only the rows that do (kept as a
+        // real loop so the row code exists once -- it is large and instruction-cache bound)
+        u32 rowmask4 = (__any_sync(0xffffffffu, m0 > st.floorx) ? 1u : 0u) | (__any_sync(0xffffffffu, m1 > st.floorx) ? 2u : 0u) |
+                       (__any_sync(0xffffffffu, m2 > st.floorx) ? 4u : 0u) | (__any_sync(0xffffffffu, m3 > st.floorx) ? 8u : 0u);
+#pragma unroll 1
+        while (rowmask4) {
+          const int i = __ffs(rowmask4) - 1;
+          rowmask4 &= rowmask4 - 1;
+          const int t = t0 + i;
+          const float4 ctr = lds128(ring_own + ((rowbase + (u32)(t + R)) & kRowMask) * kTilePitchB);
+          const float floorx = st.floorx;
+          u32 cmask = 0;
+          if (!pre) {
+            float h0, h1, h2, h3;
+            window_max<R>(ring_own, rowbase, kRowMask, kTilePitchB, t, true, true, h0, h1, h2, h3);
+            cmask = classify_row<R>(ctr, h0, h1, h2, h3, floorx);
+          } else {
+            if (ctr.x > floorx) cmask |= 1u;
+            if (ctr.y > floorx) cmask |= 2u;
+            if (ctr.z > floorx) cmask |= 4u;
+            if (ctr.w > floorx) cmask |= 8u;
+          }
+          append_row(st, cmask, ctr, (u32)((r_begin + t) * W + col0), buf, hist, minx, sf, count_ptr, list, p.cap, K,
+                     lane, pre, xscale, satx);
+        }
+      }
+      // every lane's reads of tile n0 are consumed (the votes above): refill its slot with
+      // the tile NG ahead
+      __syncwarp();
+      if (lane == 0 && g + NG < groups) {
+        const u32 slot = n0 & (NG - 1);
+        mbar_arrive_expect_tx(bars_s + 8 * slot, kTileBytes);
+        tma_tile_4d(ring_s + slot * kTileBytes, tmap, x0, y0 + kGroupRows * (g + NG), csel, b, bars_s + 8 * slot);
+      }
+    }
+    seq += (u32)groups;
+    if (st.nbuf) {
+      __syncwarp();
+      flush_candidates(st, buf, hist, minx, sf, count_ptr, list, p.cap, K, lane, pre, xscale, satx);
+    }
   }
 }
 
@@ -1459,6 +1630,39 @@ bool view_aligned(const SdnetTensor4& t, int W) {
 
 constexpr int kPeaksCtasPerSm = 4;
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      ptr = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(ptr);
+  }();
+  return fn;
+}
+
+// (W, H, channels, B) fp32 view -> tensor map with a 136 x 4 x 1 x 1 box and NaN out-of-bounds fill
+bool make_tile_map(CUtensorMap* map, const SdnetTensor4& t, int B, int Cn, int H, int W) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return false;
+  const cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Cn, (cuuint64_t)B};
+  // strides of size-1 dimensions are arbitrary in torch: make them canonical
+  const cuuint64_t sh = (cuuint64_t)t.stride_h * 4;
+  const cuuint64_t sc = Cn > 1 ? (cuuint64_t)t.stride_c * 4 : sh * (cuuint64_t)H;
+  const cuuint64_t sb = B > 1 ? (cuuint64_t)t.stride_b * 4 : sc * (cuuint64_t)Cn;
+  const cuuint64_t strides[3] = {sh, sc, sb};
+  const cuuint32_t box[4] = {(cuuint32_t)kTileCols, (cuuint32_t)kGroupRows, 1, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(t.data), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA) == CUDA_SUCCESS;
+}
+
 template <typename Kern>
 void launch_peaks(Kern kern, dim3 grid, dim3 block, cudaStream_t stream, const PeaksParams& pp) {
   // > 48 KB of dynamic shared memory needs the opt-in (idempotent, cheap)
@@ -1489,7 +1693,19 @@ int launch_decode(const SdnetDecodeParams* p, cudaStream_t stream, cudaEvent_t* 
   pp.l2_prefetch_groups = 0;
   const int sms = device_sm_count();
   const bool aligned = view_aligned(p->anchor_hm, p->W) && view_aligned(p->part_hm, p->W);
-  const bool use_cta = aligned && p->W <= kPanelW * kMaxConsumers && !(p->flags & SDNET_FLAG_WARP_KERNEL);
+  static const int path_override = [] {  // tuning knob, read once: SDNET_PEAKS_PATH = tile | cta | warp
+    const char* e = getenv("SDNET_PEAKS_PATH");
+    if (!e) return 0;
+    return e[0] == 't' ? 1 : (e[0] == 'c' ? 2 : (e[0] == 'w' ? 3 : 0));
+  }();
+  CUtensorMap tm_anchor, tm_part;
+  bool use_tile = aligned && !(p->flags & SDNET_FLAG_WARP_KERNEL) && path_override != 2 && path_override != 3 &&
+                  (long long)p->anchor_hm.stride_h * 4 >= (long long)p->W * 4;
+  if (use_tile)
+    use_tile = make_tile_map(&tm_anchor, p->anchor_hm, p->B, p->M, p->H, p->W) &&
+               make_tile_map(&tm_part, p->part_hm, p->B, p->N, p->H, p->W);
+  const bool use_cta = !use_tile && aligned && p->W <= kPanelW * kMaxConsumers && !(p->flags & SDNET_FLAG_WARP_KERNEL) &&
+                       path_override != 3;
   auto pick_strips = [&](long long units_per_strip1, long long want_units) {
     int strips = (int)((want_units + units_per_strip1 - 1) / units_per_strip1);
     const int max_strips = (p->H + 31) / 32;  // strips of at least 32 rows
@@ -1498,7 +1714,22 @@ int launch_decode(const SdnetDecodeParams* p, cudaStream_t stream, cudaEvent_t* 
     pp.rows_per_strip = (p->H + strips - 1) / strips;
     pp.strips = (p->H + pp.rows_per_strip - 1) / pp.rows_per_strip;
   };
-  if (use_cta) {
+  if (use_tile) {
+    auto kern = p->radius == 2 ? sdnet_peaks_tile_kernel<2> : sdnet_peaks_tile_kernel<1>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem);
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    static int per_sm = 0;
+    if (per_sm == 0 &&
+        (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTileWarps * 32, kTileSmem) != cudaSuccess || per_sm < 1))
+      per_sm = 1;
+    pp.panels = (p->W + kPanelW - 1) / kPanelW;
+    const long long resident_warps = (long long)sms * per_sm * kTileWarps;
+    pick_strips((long long)planes * pp.panels, 4 * resident_warps);
+    pp.units = (int)(planes * pp.strips * pp.panels);
+    long long ctas = ((long long)pp.units + kTileWarps - 1) / kTileWarps;
+    if (ctas > (long long)sms * per_sm) ctas = (long long)sms * per_sm;
+    kern<<<dim3((unsigned)ctas), dim3(kTileWarps * 32), kTileSmem, stream>>>(pp, tm_anchor, tm_part);
+  } else if (use_cta) {
     static const int ring_groups = [] {  // tuning knob, read once: SDNET_RING_GROUPS = 4 | 8
       const char* e = getenv("SDNET_RING_GROUPS");
       return (e && atoi(e) == 8) ? 8 : 4;
