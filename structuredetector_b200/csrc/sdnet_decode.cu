@@ -439,13 +439,33 @@ __device__ __forceinline__ u32 classify_row(const float4 ctr, float h0, float h1
   return cmask;
 }
 
-// Append the selected pixels of one row as (logit, index) records to the warp's buffer, one
-// column at a time, flushing when it fills up.
+// Append the selected pixels of one row as (logit, index) records to the warp's buffer.
+// Common case (<= 32 records in the row): positions from three back-to-back ballots on the bits
+// of each lane's record count, no branches.  Rows with more (plateaus) go column by column.
 __device__ __forceinline__ void append_row(UnitState& st, u32 cmask, const float4 ctr, u32 idx0, u64* buf, u32* hist,
                                            int* minx, const SharedFloors& sf, int* count_ptr,
                                            u64* __restrict__ list, int cap, int K, int lane, bool pre, float xscale,
                                            float satx) {
-  if (!__any_sync(0xffffffffu, cmask != 0)) return;
+  const u32 cnt = __popc(cmask);
+  const u32 b0 = __ballot_sync(0xffffffffu, cnt & 1u);
+  const u32 b1 = __ballot_sync(0xffffffffu, cnt & 2u);
+  const u32 b2 = __ballot_sync(0xffffffffu, cnt & 4u);
+  const u32 total = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
+  if (total == 0) return;
+  const u32 lt = (1u << lane) - 1u;
+  if (total <= 32) {
+    if (st.nbuf + (int)total > kBuf) {
+      __syncwarp();
+      flush_candidates(st, buf, hist, minx, sf, count_ptr, list, cap, K, lane, pre, xscale, satx);
+    }
+    int pos = st.nbuf + __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt);
+    if (cmask & 1u) buf[pos++] = ((u64)__float_as_uint(ctr.x) << 32) | (idx0 + 0);
+    if (cmask & 2u) buf[pos++] = ((u64)__float_as_uint(ctr.y) << 32) | (idx0 + 1);
+    if (cmask & 4u) buf[pos++] = ((u64)__float_as_uint(ctr.z) << 32) | (idx0 + 2);
+    if (cmask & 8u) buf[pos++] = ((u64)__float_as_uint(ctr.w) << 32) | (idx0 + 3);
+    st.nbuf += (int)total;
+    return;
+  }
 #pragma unroll
   for (int jj = 0; jj < 4; ++jj) {
     const bool mine = (cmask >> jj) & 1u;
@@ -455,13 +475,9 @@ __device__ __forceinline__ void append_row(UnitState& st, u32 cmask, const float
         __syncwarp();
         flush_candidates(st, buf, hist, minx, sf, count_ptr, list, cap, K, lane, pre, xscale, satx);
       }
-      if (mine) buf[st.nbuf + __popc(m & ((1u << lane) - 1u))] = ((u64)__float_as_uint(comp(ctr, jj)) << 32) | (idx0 + jj);
+      if (mine) buf[st.nbuf + __popc(m & lt)] = ((u64)__float_as_uint(comp(ctr, jj)) << 32) | (idx0 + jj);
       st.nbuf += __popc(m);
     }
-  }
-  if (st.nbuf >= 32) {
-    __syncwarp();
-    flush_candidates(st, buf, hist, minx, sf, count_ptr, list, cap, K, lane, pre, xscale, satx);
   }
 }
 
@@ -960,7 +976,7 @@ sdnet_peaks_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_cons
   }
   __syncwarp();
 
-  u32 seq = 0;  // running tile number of this warp: slot seq % NG, phase (seq / NG) & 1
+  u32 phases = 0;  // bit s = parity the next wait on ring slot s must use
   for (;;) {
     u32 unit = 0;
     if (lane == 0) unit = atomicAdd(p.sched, 1u);
@@ -1000,27 +1016,28 @@ sdnet_peaks_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_cons
     *reinterpret_cast<int4*>(minx + 4 * lane) = make_int4(0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff);
     __syncwarp();
 
-    // tile j of the unit = ring rows 4j..4j+3 = image rows y0+4j..; slot (seq + j) % NG
+    // tile j of the unit = ring rows 4j..4j+3 = image rows y0+4j..; slot j % NG; every tile that
+    // is issued is waited for exactly once, so one parity bit per slot tracks the phases
     if (lane == 0) {
       const int first = min(NG, groups);
       for (int j = 0; j < first; ++j) {
-        const u32 slot = (seq + j) & (NG - 1);
-        mbar_arrive_expect_tx(bars_s + 8 * slot, kTileBytes);
-        tma_tile_4d(ring_s + slot * kTileBytes, tmap, x0, y0 + kGroupRows * j, csel, b, bars_s + 8 * slot);
+        mbar_arrive_expect_tx(bars_s + 8 * j, kTileBytes);
+        tma_tile_4d(ring_s + j * kTileBytes, tmap, x0, y0 + kGroupRows * j, csel, b, bars_s + 8 * j);
       }
     }
-    const u32 rowbase = seq * kGroupRows;
+    constexpr u32 rowbase = 0;
     int gfloor_seen = 0;
-    mbar_wait(bars_s + 8 * (seq & (NG - 1)), (seq / NG) & 1u);
+    mbar_wait(bars_s, phases & 1u);
+    phases ^= 1u;
     for (int g = 0; g < groups_out; ++g) {
-      const u32 n0 = seq + g, n1 = n0 + 1;
-      if (g + 1 < groups) mbar_wait(bars_s + 8 * (n1 & (NG - 1)), (n1 / NG) & 1u);
-      if ((g & 3) == 0) {
-        // every 16 rows: apply the plane-wide floor fetched 16 rows ago (latency never exposed)
-        // and start the next fetch
-        st.floorx = fmaxf(st.floorx, shared_floor(gfloor_seen, xscale));
-        gfloor_seen = __ldcg(gfloor_ptr);
+      if (g + 1 < groups) {
+        const u32 s1 = (u32)(g + 1) & (NG - 1);
+        mbar_wait(bars_s + 8 * s1, (phases >> s1) & 1u);
+        phases ^= 1u << s1;
       }
+      // apply the plane-wide floor fetched one group ago (latency never exposed), start the next fetch
+      st.floorx = fmaxf(st.floorx, shared_floor(gfloor_seen, xscale));
+      gfloor_seen = __ldcg(gfloor_ptr);
       const int t0 = g * kGroupRows;
       // centre row of output row t0+i is ring row t0+i+R
       const float4 c0 = lds128(ring_own + ((rowbase + (u32)(t0 + R)) & kRowMask) * kTilePitchB);
@@ -1064,16 +1081,20 @@ sdnet_peaks_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_cons
                      lane, pre, xscale, satx);
         }
       }
-      // every lane's reads of tile n0 are consumed (the votes above): refill its slot with
+      // every lane's reads of tile g are consumed (the votes above): refill its slot with
       // the tile NG ahead
       __syncwarp();
       if (lane == 0 && g + NG < groups) {
-        const u32 slot = n0 & (NG - 1);
+        const u32 slot = (u32)g & (NG - 1);
         mbar_arrive_expect_tx(bars_s + 8 * slot, kTileBytes);
         tma_tile_4d(ring_s + slot * kTileBytes, tmap, x0, y0 + kGroupRows * (g + NG), csel, b, bars_s + 8 * slot);
       }
+      // while the plane has no floor yet, publish early and often; later only in batches
+      if (st.nbuf >= 16 || (st.nbuf > 0 && gfloor_seen <= 0)) {
+        __syncwarp();
+        flush_candidates(st, buf, hist, minx, sf, count_ptr, list, p.cap, K, lane, pre, xscale, satx);
+      }
     }
-    seq += (u32)groups;
     if (st.nbuf) {
       __syncwarp();
       flush_candidates(st, buf, hist, minx, sf, count_ptr, list, p.cap, K, lane, pre, xscale, satx);
