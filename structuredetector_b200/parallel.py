@@ -1,0 +1,74 @@
+"""Batch sharding across GPUs and the one collective of the path: gathering the packed detections.
+
+Images are independent (the reference never mixes batch entries: src/sdnet/data/decoders.py:44-100
+is batched on dim 0 and the object loop iterates images, :104), so the only parallelism is a
+contiguous split of the batch over ranks plus ONE all-gather of fixed-capacity packed records at
+the end.  One process per GPU; ``torch.distributed`` (NCCL on GPUs, gloo in the CPU
+tests) is plumbing only.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+
+__all__ = ["shard_bounds", "shard_sizes", "all_gather_packed", "merge_packed", "ShardedDecoder"]
+
+_FIELDS = ("anchor_out", "part_out", "anchor_inds", "part_inds", "part_emb", "assign", "counts", "diag")
+
+
+def shard_sizes(total: int, world: int) -> list[int]:
+    """Contiguous split, the first ``total % world`` ranks take one extra image."""
+    base, extra = divmod(total, world)
+    return [base + (1 if r < extra else 0) for r in range(world)]
+
+
+def shard_bounds(total: int, world: int, rank: int) -> tuple[int, int]:
+    sizes = shard_sizes(total, world)
+    lo = sum(sizes[:rank])
+    return lo, lo + sizes[rank]
+
+
+def merge_packed(blobs: list[torch.Tensor], sizes: list[int], K: int, P: int, C: int) -> ops.PackedDetections:
+    """Per-rank packed blobs (rank order) -> one PackedDetections for the whole batch."""
+    parts = [ops._carve(blob, n, K, P, C) for blob, n in zip(blobs, sizes) if n > 0]
+    fields = {name: torch.cat([getattr(p, name) for p in parts], dim=0) for name in _FIELDS}
+    return ops.PackedDetections(**fields, blob=None)
+
+
+def all_gather_packed(local_blob: torch.Tensor, sizes: list[int], K: int, P: int, C: int, group=None) -> ops.PackedDetections:
+    """All-gather every rank's packed blob and stitch the global result (identical on all ranks).
+
+    Blobs have a fixed capacity per image, so no size exchange is needed; with an uneven split the
+    shorter blobs are padded to the longest one for the collective.
+    """
+    world = dist.get_world_size(group)
+    assert len(sizes) == world
+    nbytes = [ops.packed_nbytes(n, K, P, C) for n in sizes]
+    width = max(nbytes)
+    send = local_blob
+    if local_blob.numel() != width:
+        send = torch.zeros(width, dtype=torch.uint8, device=local_blob.device)
+        send[: local_blob.numel()] = local_blob
+    recv = torch.empty(world * width, dtype=torch.uint8, device=local_blob.device)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    blobs = [recv[r * width : r * width + nbytes[r]] for r in range(world)]
+    return merge_packed(blobs, sizes, K, P, C)
+
+
+class ShardedDecoder:
+    """Decode this rank's contiguous slice of a global batch on its GPU and all-gather the packed
+    detections; ``rank``/``world`` come from the default process group."""
+
+    def __init__(self, max_objects: int, max_parts: int, conf_thresh: float, dist_thresh: float, group=None):
+        self.K, self.P, self.conf, self.dist, self.group = max_objects, max_parts, conf_thresh, dist_thresh, group
+
+    def __call__(self, local_outputs: dict, global_batch: int) -> ops.PackedDetections:
+        world = dist.get_world_size(self.group)
+        sizes = shard_sizes(global_batch, world)
+        rank = dist.get_rank(self.group)
+        assert local_outputs["anchor_hm"].shape[0] == sizes[rank], "local shard does not match the contiguous split"
+        packed = ops.decode_packed(local_outputs, self.K, self.P, self.conf, self.dist)
+        C = local_outputs["anchor_hm"].shape[1] + local_outputs["part_hm"].shape[1]
+        return all_gather_packed(packed.blob, sizes, self.K, self.P, C, self.group)

@@ -103,9 +103,14 @@ def _structured(cfg: DecodeConfig, batch: int, gen: torch.Generator, ladder: boo
     m, n, h, w = cfg.labels, cfg.parts, cfg.height, cfg.width
     raw = torch.empty(batch, cfg.channels, h, w, dtype=torch.float32)
     if ladder:
-        # flat, strictly sub-threshold background with no exact repeats inside any
-        # 5x5 window that could outrank a stamped peak
-        raw[:, : m + n] = -9.0 + 0.25 * torch.rand(batch, m + n, h, w, generator=gen)
+        # strictly sub-threshold background made of pairwise distinct, well separated logits
+        # (a random permutation of an arithmetic ladder) so that not even the below-threshold
+        # top-k slots can tie
+        for b in range(batch):
+            for c in range(m + n):
+                perm = torch.randperm(h * w, generator=gen).double()
+                steps = float(h * w * (m + n))  # channel-interleaved rungs: distinct across channels too
+                raw[b, c] = (-10.0 + 4.0 * (perm * (m + n) + c) / steps).float().view(h, w)
     else:
         raw[:, : m + n] = -6.0 + 0.5 * torch.randn(batch, m + n, h, w, generator=gen)
     raw[:, m + n : m + n + 2] = torch.rand(batch, 2, h, w, generator=gen)

@@ -77,3 +77,68 @@ def assert_packed_equal(got: dict, want: dict, *, what=""):
             g, w = np.ascontiguousarray(got[key]).view(np.uint32), np.ascontiguousarray(want[key]).view(np.uint32)
             bad = np.argwhere(g != w)
             assert bad.size == 0, f"{what}: {key} differs at {bad[:5].tolist()} got {got[key][tuple(bad[0])]} want {want[key][tuple(bad[0])]}"
+
+
+# ----------------------------------------------------------------------------- golden fixtures
+def load_golden(name):
+    """(meta dict, arrays dict) of one fixture written by tests/golden/make_golden.py."""
+    import json
+
+    index = json.loads((GOLDEN_DIR / "index.json").read_text())
+    return index[name], dict(np.load(GOLDEN_DIR / f"{name}.npz"))
+
+
+def golden_names():
+    import json
+
+    return sorted(json.loads((GOLDEN_DIR / "index.json").read_text()))
+
+
+def golden_args(meta):
+    _, m, n, _, _ = meta["shape"]
+    return SimpleNamespace(
+        _r_labels={i: f"label{i}" for i in range(m)}, _r_parts={i: f"part{i}" for i in range(n)},
+        anchor_name=meta["anchor_name"], down_ratio=meta["down_ratio"], max_objects=meta["K"], max_parts=meta["P"],
+        conf_threshold=meta["conf"], decoder_dist_thresh=meta["dist"])
+
+
+def listify(objs):
+    """tuples -> lists, so oracle/our output compares equal to what came back from JSON."""
+    if isinstance(objs, (list, tuple)):
+        return [listify(o) for o in objs]
+    return objs
+
+
+def assert_objects_close(got, want, *, score_atol=0.0, coord_rtol=0.0, what=""):
+    """Same structure, names and ordering; scores / coordinates within the given tolerances."""
+    assert len(got) == len(want), f"{what}: {len(got)} images vs {len(want)}"
+    for b, (gi, wi) in enumerate(zip(got, want)):
+        assert len(gi) == len(wi), f"{what}: image {b}: {len(gi)} objects vs {len(wi)}"
+        for o, (go, wo) in enumerate(zip(gi, wi)):
+            assert go[0] == wo[0], f"{what}: image {b} object {o}: label {go[0]} vs {wo[0]}"
+            kps_g, kps_w = [go[1]] + list(go[2]), [wo[1]] + list(wo[2])
+            assert len(kps_g) == len(kps_w), f"{what}: image {b} object {o}: {len(kps_g) - 1} parts vs {len(kps_w) - 1}"
+            for kg, kw in zip(kps_g, kps_w):
+                assert kg[0] == kw[0], f"{what}: image {b} object {o}: kind {kg[0]} vs {kw[0]}"
+                for a, c in ((kg[1], kw[1]), (kg[2], kw[2])):
+                    assert abs(a - c) <= coord_rtol * max(abs(c), 1.0), f"{what}: image {b} object {o}: coord {a} vs {c}"
+                assert abs(kg[3] - kw[3]) <= score_atol, f"{what}: image {b} object {o}: score {kg[3]} vs {kw[3]}"
+
+
+def assert_topk_equal_up_to_ties(got_scores, got_cls, got_inds, ref_scores, ref_cls, ref_inds, *, what=""):
+    """Scores identical slot by slot; (class, index) identical as SETS inside each run of equal
+    scores -- except the last run of a row, whose membership depends on torch.topk's tie rule."""
+    np.testing.assert_array_equal(got_scores, ref_scores, err_msg=f"{what}: scores")
+    for r in range(got_scores.shape[0]):
+        row = got_scores[r]
+        k = len(row)
+        start = 0
+        while start < k:
+            end = start
+            while end + 1 < k and row[end + 1] == row[start]:
+                end += 1
+            if end < k - 1:  # run closed inside the list: membership is unambiguous
+                g = sorted(zip(got_cls[r, start:end + 1].tolist(), got_inds[r, start:end + 1].tolist()))
+                w = sorted(zip(ref_cls[r, start:end + 1].tolist(), ref_inds[r, start:end + 1].tolist()))
+                assert g == w, f"{what}: row {r} slots {start}..{end}"
+            start = end + 1

@@ -1,0 +1,123 @@
+"""CPU: everything on the host side of the boundary -- the C-ABI library loads and exports every
+symbol include/sdnet_decode.h declares, argument errors are reported before any launch, the
+product path refuses to run without a CUDA device, and the annotation types behave like the
+reference's."""
+import ctypes
+import json
+import re
+from pathlib import Path
+
+import pytest
+import torch
+
+from structuredetector_b200 import ImageAnnotation, Keypoint, Object, _native, ops
+from structuredetector_b200.annotations import Box
+from structuredetector_b200.synth import CONFIGS, make_raw, split_outputs
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _header_functions():
+    text = (ROOT / "include" / "sdnet_decode.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(sdnet_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _native.load()
+    declared = _header_functions()
+    assert declared, "no functions parsed from the header"
+    for name in declared:
+        assert hasattr(lib, name), f"{name} is declared in include/sdnet_decode.h but not exported"
+    assert sorted(_native.EXPORTS) == declared
+    assert lib.sdnet_abi_version() == _native.ABI_VERSION
+
+
+def test_struct_layout_matches_the_header():
+    # the library checks struct_size itself; a mismatch comes back as SDNET_E_STRUCT (-7)
+    p = _native.SdnetDecodeParams()
+    p.struct_size = ctypes.sizeof(_native.SdnetDecodeParams) - 8
+    assert _native.load().sdnet_decode_launch(ctypes.byref(p), None) == -7
+    assert "struct_size" in _native.error_string(-7)
+
+
+def test_argument_errors_are_reported_before_any_launch():
+    lib = _native.load()
+    p = _native.SdnetDecodeParams()
+    p.struct_size = ctypes.sizeof(_native.SdnetDecodeParams)
+    p.dtype, p.radius = 0, 2
+    p.B, p.M, p.N, p.H, p.W, p.K, p.P = 1, 2, 1, 8, 8, 65, 10  # K > H*W: torch.topk's "k out of range"
+    assert lib.sdnet_decode_launch(ctypes.byref(p), None) == -2
+    p.K = 10
+    assert lib.sdnet_decode_launch(ctypes.byref(p), None) == -1  # NULL tensors
+    p.dtype = 3
+    assert lib.sdnet_decode_launch(ctypes.byref(p), None) == -4
+    p.dtype, p.radius = 0, 3
+    assert lib.sdnet_decode_launch(ctypes.byref(p), None) == -6
+    assert lib.sdnet_decode_launch(None, None) == -1
+    out = ctypes.c_size_t(0)
+    assert lib.sdnet_decode_workspace_bytes(1, 2, 1, 4096, 4096, 10, 10, 0, ctypes.byref(out)) == -2  # H*W >= 2^24
+    assert _native.workspace_bytes(16, 2, 1, 512, 612, 100, 100) > 16 * 3 * (512 * 612 // 8) * 8
+    with pytest.raises(RuntimeError):
+        _native.check(-2, "x")
+    with pytest.raises(ValueError):
+        _native.check(-5, "x")
+
+
+def test_product_path_has_no_cpu_fallback():
+    cfg = CONFIGS["cfg1"]
+    outs = split_outputs(make_raw(cfg, "blobs", batch=1), cfg.labels, cfg.parts)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.decode_packed(outs, 100, 100, 0.4, 0.1)
+    with pytest.raises(TypeError):
+        ops.decode_packed({k: v.half() for k, v in outs.items()}, 100, 100, 0.4, 0.1)
+    with pytest.raises(RuntimeError):
+        ops.activate_maps(outs["anchor_hm"])
+
+
+def test_product_package_never_imports_the_oracle():
+    for path in (ROOT / "structuredetector_b200").rglob("*.py"):
+        text = path.read_text()
+        assert "import oracle" not in text and "from oracle" not in text, f"{path} reaches into oracle/"
+    for path in (ROOT / "structuredetector_b200" / "csrc").glob("*"):
+        if path.suffix in (".cu", ".h", ".cuh"):
+            assert "oracle" not in path.read_text().lower()
+
+
+def test_packed_blob_layout_is_aligned_and_disjoint():
+    B, K, P, C = 3, 7, 5, 4
+    blob = torch.zeros(ops.packed_nbytes(B, K, P, C), dtype=torch.uint8)
+    v = ops._carve(blob, B, K, P, C)
+    assert v.anchor_out.shape == (B, K, 4) and v.part_out.shape == (B, P, 6) and v.assign.shape == (B, P)
+    spans = []
+    for t in (v.anchor_inds, v.part_inds, v.anchor_out, v.part_out, v.part_emb, v.assign, v.counts, v.diag):
+        off = t.data_ptr() - blob.data_ptr()
+        assert off % 16 == 0
+        spans.append((off, off + t.numel() * t.element_size()))
+    spans.sort()
+    assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:])) and spans[-1][1] <= blob.numel()
+
+
+def test_annotation_types_follow_the_reference_api(tmp_path):
+    kp = Keypoint("leaf", 10.0, 20.0, 0.9)
+    assert kp.resized((100, 50), (200, 200)).x == 20.0 and kp.x == 10.0
+    kp.resize((100, 50), (200, 200))
+    assert (kp.x, kp.y) == (20.0, 80.0)
+    obj = Object("bean", Keypoint("stem", 1.0, 2.0, 0.8), [kp], Box(3, 4, 1, 2))
+    assert obj.nb_parts == 1 and obj.x == 1.0
+    obj.x = 5.0
+    assert obj.anchor.x == 5.0
+    assert obj.box.standardized().x_min == 1 and obj.box.width == 2 and obj.box.x_mid == 2
+    rep = obj.json_repr()
+    assert rep["label"] == "bean" and rep["parts"][0]["kind"] == "stem" and rep["parts"][1]["location"] == {"x": 20.0, "y": 80.0}
+    back = Object.from_json(rep, "stem")
+    assert back.anchor.score == 0.8 and back.parts[0].kind == "leaf" and back.box.json_repr() == obj.box.json_repr()
+    ann = ImageAnnotation("batch_0", [obj], img_size=(100, 100))
+    assert len(ann) == 1 and ann.nb_parts == 1 and not ann.is_empty and ann.image_name == "batch_0"
+    norm = ann.normalized()
+    assert norm.objects[0].x == 0.05 and ann.objects[0].x == 5.0
+    ann.save_json(tmp_path)
+    again = ImageAnnotation.from_json(tmp_path / "batch_0.json", "stem")
+    assert again.objects[0].parts[0].score == 0.9 and again.img_size == [100, 100]
+    assert json.loads((tmp_path / "batch_0.json").read_text())["objects"][0]["label"] == "bean"
+    assert "Keypoint(kind: leaf" in repr(kp) and ImageAnnotation("x").is_empty
