@@ -1035,9 +1035,13 @@ sdnet_peaks_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_cons
         mbar_wait(bars_s + 8 * s1, (phases >> s1) & 1u);
         phases ^= 1u << s1;
       }
-      // apply the plane-wide floor fetched one group ago (latency never exposed), start the next fetch
-      st.floorx = fmaxf(st.floorx, shared_floor(gfloor_seen, xscale));
-      gfloor_seen = __ldcg(gfloor_ptr);
+      if ((g & 3) == 0) {
+        // every 16 rows: apply the plane-wide floor fetched 16 rows ago and start the next fetch.
+        // The load writes straight into the register it will be read from four groups later, so
+        // its latency is never waited for.
+        st.floorx = fmaxf(st.floorx, shared_floor(gfloor_seen, xscale));
+        asm volatile("ld.global.cg.s32 %0, [%1];" : "=r"(gfloor_seen) : "l"(gfloor_ptr) : "memory");
+      }
       const int t0 = g * kGroupRows;
       // centre row of output row t0+i is ring row t0+i+R
       const float4 c0 = lds128(ring_own + ((rowbase + (u32)(t0 + R)) & kRowMask) * kTilePitchB);
@@ -1354,7 +1358,11 @@ __device__ int select_group(const TailParams& p, int b, int c0, int nc, int want
   const int total = s_misc[0];
   u64 prefix = 0;   // value of the top `bits` bits that boundary elements share
   int bits = 0;
-  if (total > kSortN) {
+  // radix-refine until what is left (everything certainly selected + the boundary bucket) is a
+  // small sort: the bitonic network below costs O(n log^2 n) and dominated this kernel when it
+  // was handed the full 2048-element buffer
+  const int target = min(kSortN, max(want + 64, 128));
+  if (total > target) {
     int need = want;      // how many still have to come from the boundary bucket
     int certain = 0;      // elements strictly above the boundary bucket
     for (int level = 0; level < 8; ++level) {
@@ -1402,7 +1410,7 @@ __device__ int select_group(const TailParams& p, int b, int c0, int nc, int want
       prefix = (prefix << 8) | (u64)dsel;
       bits += 8;
       __syncthreads();
-      if (certain + binc <= kSortN) break;  // everything at or above the boundary bucket fits the sorter
+      if (certain + binc <= target) break;  // everything at or above the boundary bucket is a small sort
     }
   }
   // collect: all elements whose top `bits` bits are >= prefix
@@ -1727,8 +1735,13 @@ int launch_decode(const SdnetDecodeParams* p, cudaStream_t stream, cudaEvent_t* 
                make_tile_map(&tm_part, p->part_hm, p->B, p->N, p->H, p->W);
   const bool use_cta = !use_tile && aligned && p->W <= kPanelW * kMaxConsumers && !(p->flags & SDNET_FLAG_WARP_KERNEL) &&
                        path_override != 3;
+  static const int strips_override = [] {  // tuning knob, read once: SDNET_STRIPS = n
+    const char* e = getenv("SDNET_STRIPS");
+    return e ? atoi(e) : 0;
+  }();
   auto pick_strips = [&](long long units_per_strip1, long long want_units) {
     int strips = (int)((want_units + units_per_strip1 - 1) / units_per_strip1);
+    if (strips_override > 0) strips = strips_override;
     const int max_strips = (p->H + 31) / 32;  // strips of at least 32 rows
     if (strips > max_strips) strips = max_strips;
     if (strips < 1) strips = 1;
@@ -1745,7 +1758,12 @@ int launch_decode(const SdnetDecodeParams* p, cudaStream_t stream, cudaEvent_t* 
       per_sm = 1;
     pp.panels = (p->W + kPanelW - 1) / kPanelW;
     const long long resident_warps = (long long)sms * per_sm * kTileWarps;
-    pick_strips((long long)planes * pp.panels, 4 * resident_warps);
+    // long units prune best (measured: 128 images, 1 strip 0.169 ms, 7 strips 0.221 ms): split planes
+    // into strips only while there are fewer units than resident warps
+    {
+      const long long units1 = (long long)planes * pp.panels;
+      pick_strips(units1, units1 >= resident_warps ? units1 : (resident_warps / units1) * units1);
+    }
     pp.units = (int)(planes * pp.strips * pp.panels);
     long long ctas = ((long long)pp.units + kTileWarps - 1) / kTileWarps;
     if (ctas > (long long)sms * per_sm) ctas = (long long)sms * per_sm;
