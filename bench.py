@@ -115,6 +115,11 @@ def physical_gpu_index(local_rank: int) -> int:
     return local_rank
 
 
+def workload_name(cfg) -> str:
+    return (f"{WORKLOAD}: global batch {cfg.batch} of 2448x2048 inputs -> raw ({cfg.batch}, {cfg.channels}, {cfg.height}, "
+            f"{cfg.width}) fp32, K=P={cfg.max_objects}, conf {cfg.conf_threshold}, dist {cfg.dist_thresh}")
+
+
 # ----------------------------------------------------------------------------- CPU reference arm
 def cpu_reference_rate(cfg, mode: str, seconds: float, steps: int | None = None, warmup: int = 1):
     """images/s of the reference algorithm on the host CPU (oracle port, all torch threads)."""
@@ -170,8 +175,8 @@ def run_reference_arm(args, cfg):
         "vs_baseline": None,
         "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": f"{WORKLOAD}: 2448x2048 inputs -> (7, 512, 612) maps, K=P=100, conf 0.4, dist 0.1",
-                   "mode": args.mode, "images_per_step": CPU_BATCH},
+        "config": {"workload": workload_name(cfg), "mode": args.mode, "images_per_step": CPU_BATCH,
+                   "note": "CPU arm: each step decodes a bounded sample of the workload (16 images), all host threads"},
         "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": res["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -355,8 +360,7 @@ def main():
             "dtype": "f32",
             "data": "synthetic",
             "config": {
-                "workload": f"{WORKLOAD}: global batch {cfg.batch} of 2448x2048 inputs -> raw ({cfg.batch}, {M + N + 4}, {H}, {W}) fp32, "
-                            f"K=P={K}, conf {cfg.conf_threshold}, dist {cfg.dist_thresh}",
+                "workload": workload_name(cfg),
                 "mode": args.mode, "images_per_rank": shard, "parallelism": f"batch-shard x{world}",
                 "gather": "ncclAllGather of packed detections (every rank holds all results)" if world > 1 else "none",
                 "l2": f"inputs larger than L2 ({raw.numel() * 4 / 1e9:.2f} GB per rank, no flush needed)",
