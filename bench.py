@@ -181,12 +181,25 @@ def run_reference_arm(args, cfg):
         "e2e": {"value": res["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------- our arm
+def emit(line: dict):
+    """The ONE JSON line goes to the real stdout; everything else any library prints to fd 1 while
+    the bench runs (e.g. NCCL's version banner) was diverted to stderr by main()."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
     args = parse_args()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     from structuredetector_b200.synth import CONFIGS, DecodeConfig, make_raw, split_outputs
 
     cfg = CONFIGS[WORKLOAD]
@@ -375,7 +388,7 @@ def main():
                            "planes_via_exact_select": diag_overflow,
                            "candidates_per_plane_mean": cand_mean},
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

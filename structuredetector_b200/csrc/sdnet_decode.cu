@@ -79,6 +79,10 @@ struct PeaksParams {
   u32* ghist;              // [planes][kFineBins] plane-wide logit histogram of recorded candidates
   int* gfloor;             // [planes] highest fine bin b with >= K recorded candidates in bins >= b (0 = none)
   int l2_prefetch_groups;  // warp-specialised kernel: L2 prefetch distance in 4-row groups (0 = off)
+  // tile kernel, two-tier schedule: units [0, tier1_units) are whole-height panels of planes
+  // [0, tier1_planes); the remaining planes are cut into `strips` strips so that the last wave of
+  // warps is filled with short units instead of idling behind a few long ones
+  int tier1_units, tier1_planes;
 };
 
 // clamp(sigmoid(x)) bit-identical to ATen's CUDA kernels (UnarySpecialOpsKernel.cu sigmoid:
@@ -982,10 +986,20 @@ sdnet_peaks_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_cons
     if (lane == 0) unit = atomicAdd(p.sched, 1u);
     unit = __shfl_sync(0xffffffffu, unit, 0);
     if (unit >= (u32)p.units) break;
-    const int panel = unit % p.panels;
-    const int t1 = unit / p.panels;
-    const int strip = t1 % p.strips;
-    const int plane_id = t1 / p.strips;
+    int panel, plane_id, r_begin, r_end;
+    if (unit < (u32)p.tier1_units) {
+      panel = unit % p.panels;
+      plane_id = unit / p.panels;
+      r_begin = 0;
+      r_end = H;
+    } else {
+      const u32 u2 = unit - (u32)p.tier1_units;
+      panel = u2 % p.panels;
+      const int t1 = u2 / p.panels;
+      plane_id = p.tier1_planes + t1 / p.strips;
+      r_begin = (t1 % p.strips) * p.rows_per_strip;
+      r_end = min(H, r_begin + p.rows_per_strip);
+    }
     const int b = plane_id / C, c = plane_id % C;
     const bool is_anchor = c < p.M;
     const CUtensorMap* tmap = is_anchor ? &tm_anchor : &tm_part;
@@ -993,8 +1007,6 @@ sdnet_peaks_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_cons
     const int K = is_anchor ? p.K : p.P;
     const int col0 = panel * kPanelW + 4 * lane;
     const int x0 = panel * kPanelW - 4;
-    const int r_begin = strip * p.rows_per_strip;
-    const int r_end = min(H, r_begin + p.rows_per_strip);
     const int nrows = r_end - r_begin;
     const int y0 = r_begin - R;  // image row of ring row 0
     const int groups = (nrows + 2 * R + kGroupRows - 1) / kGroupRows;
@@ -1027,6 +1039,7 @@ sdnet_peaks_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_cons
     }
     constexpr u32 rowbase = 0;
     int gfloor_seen = 0;
+    const int poll_mask = nrows <= 160 ? 0 : 3;
     mbar_wait(bars_s, phases & 1u);
     phases ^= 1u;
     for (int g = 0; g < groups_out; ++g) {
@@ -1035,10 +1048,10 @@ sdnet_peaks_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_cons
         mbar_wait(bars_s + 8 * s1, (phases >> s1) & 1u);
         phases ^= 1u << s1;
       }
-      if ((g & 3) == 0) {
-        // every 16 rows: apply the plane-wide floor fetched 16 rows ago and start the next fetch.
-        // The load writes straight into the register it will be read from four groups later, so
-        // its latency is never waited for.
+      if ((g & poll_mask) == 0) {
+        // every 16 rows (every 4 in short strips): apply the plane-wide floor fetched one period ago
+        // and start the next fetch.  The load writes straight into the register it will be read
+        // from a period later, so its latency is never waited for.
         st.floorx = fmaxf(st.floorx, shared_floor(gfloor_seen, xscale));
         asm volatile("ld.global.cg.s32 %0, [%1];" : "=r"(gfloor_seen) : "l"(gfloor_ptr) : "memory");
       }
@@ -1720,6 +1733,8 @@ int launch_decode(const SdnetDecodeParams* p, cudaStream_t stream, cudaEvent_t* 
   pp.ghist = reinterpret_cast<u32*>(base + ws.off_ghist);
   pp.gfloor = reinterpret_cast<int*>(base + ws.off_gfloor);
   pp.l2_prefetch_groups = 0;
+  pp.tier1_units = 0;
+  pp.tier1_planes = 0;
   const int sms = device_sm_count();
   const bool aligned = view_aligned(p->anchor_hm, p->W) && view_aligned(p->part_hm, p->W);
   static const int path_override = [] {  // tuning knob, read once: SDNET_PEAKS_PATH = tile | cta | warp
@@ -1735,6 +1750,10 @@ int launch_decode(const SdnetDecodeParams* p, cudaStream_t stream, cudaEvent_t* 
                make_tile_map(&tm_part, p->part_hm, p->B, p->N, p->H, p->W);
   const bool use_cta = !use_tile && aligned && p->W <= kPanelW * kMaxConsumers && !(p->flags & SDNET_FLAG_WARP_KERNEL) &&
                        path_override != 3;
+  static const int tier2_strips = [] {  // tuning knob, read once: SDNET_TIER2_STRIPS = n (default 2)
+    const char* e = getenv("SDNET_TIER2_STRIPS");
+    return e && atoi(e) > 0 ? atoi(e) : 2;
+  }();
   static const int strips_override = [] {  // tuning knob, read once: SDNET_STRIPS = n
     const char* e = getenv("SDNET_STRIPS");
     return e ? atoi(e) : 0;
@@ -1762,9 +1781,34 @@ int launch_decode(const SdnetDecodeParams* p, cudaStream_t stream, cudaEvent_t* 
     // into strips only while there are fewer units than resident warps
     {
       const long long units1 = (long long)planes * pp.panels;
-      pick_strips(units1, units1 >= resident_warps ? units1 : (resident_warps / units1) * units1);
+      pp.tier1_units = 0;
+      pp.tier1_planes = 0;
+      if (units1 <= resident_warps || strips_override > 0) {
+        // Fewer units than resident warps: every warp gets at most one unit per wave, so the kernel
+        // lasts ceil(units / warps) unit-times.  Cutting planes into S strips shortens the unit but
+        // costs ~15 % per extra strip (each strip re-warms its pruning floor); pick the S that
+        // minimises waves(S) * (1 + 0.15 (S - 1)) / S.  Measured at 128 images: S = 1, 2, 3, 4 ->
+        // 0.151, 0.163, 0.138, 0.183 ms.
+        int best_s = 1;
+        double best_cost = 1e30;
+        const int max_s = (p->H + 31) / 32 < 16 ? (p->H + 31) / 32 : 16;
+        for (int cand = 1; cand <= (max_s > 0 ? max_s : 1); ++cand) {
+          const long long waves = (units1 * cand + resident_warps - 1) / resident_warps;
+          const double cost = (double)waves * (1.0 + 0.15 * (cand - 1)) / cand;
+          if (cost < best_cost - 1e-9) { best_cost = cost; best_s = cand; }
+        }
+        pick_strips(units1, units1 * best_s);
+        pp.units = (int)(planes * pp.strips * pp.panels);
+      } else {
+        // whole waves of whole-height units first, then the leftover planes in short strips
+        const long long full_waves = units1 / resident_warps;
+        pp.tier1_planes = (int)((full_waves * resident_warps) / pp.panels);
+        pp.tier1_units = pp.tier1_planes * pp.panels;
+        const long long rest = (long long)planes - pp.tier1_planes;
+        pick_strips(rest > 0 ? rest * pp.panels : 1, rest > 0 ? rest * pp.panels * tier2_strips : 1);
+        pp.units = (int)(pp.tier1_units + rest * pp.strips * pp.panels);
+      }
     }
-    pp.units = (int)(planes * pp.strips * pp.panels);
     long long ctas = ((long long)pp.units + kTileWarps - 1) / kTileWarps;
     if (ctas > (long long)sms * per_sm) ctas = (long long)sms * per_sm;
     kern<<<dim3((unsigned)ctas), dim3(kTileWarps * 32), kTileSmem, stream>>>(pp, tm_anchor, tm_part);
