@@ -58,7 +58,6 @@ constexpr float kClampLo = 1e-6f;
 constexpr float kClampHi = (float)(1.0 - 1e-6);
 constexpr float kFar = 1e6f;
 
-constexpr int kTailThreads = 256;
 constexpr int kSortN = 2048;           // tail sort buffer (>= SDNET_MAX_TOPK + boundary slack)
 
 struct View4 {
@@ -1199,9 +1198,18 @@ __global__ void __launch_bounds__(kExactThreads) sdnet_exact_select_kernel(const
   __shared__ int s_warp[kExactThreads / 32][2];
   __shared__ int s_base[2];
   const int C = p.M + p.N;
-  const int plane_id = blockIdx.x;
+  const int planes = p.B * C;
+  if (!p.force) {
+    // common case: nothing overflowed.  One coalesced look at this CTA's planes, then leave.
+    int mine = 0;
+    for (int q = blockIdx.x + threadIdx.x * gridDim.x; q < planes; q += blockDim.x * gridDim.x)
+      mine |= p.counts[q] > p.cap;
+    if (!__syncthreads_or(mine)) return;
+  }
+  for (int plane_id = blockIdx.x; plane_id < planes; plane_id += gridDim.x) {
   const int emitted = p.counts[plane_id];
-  if (!p.force && emitted <= p.cap) return;
+  if (!p.force && emitted <= p.cap) continue;  // block-uniform
+  __syncthreads();
   const int b = plane_id / C, c = plane_id % C;
   const bool is_anchor = c < p.M;
   const View4& vw = is_anchor ? p.anchor : p.part;
@@ -1307,6 +1315,8 @@ __global__ void __launch_bounds__(kExactThreads) sdnet_exact_select_kernel(const
     p.counts[plane_id] = s_base[0] + min(s_base[1], need);
     p.flags[plane_id] = 1;
   }
+  __syncthreads();
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1338,10 +1348,23 @@ __device__ __forceinline__ u64 make_comp(u64 rec, int c_local) {
   return ((u64)key << 32) | ((u64)(255u - (u32)c_local) << 24) | (u64)(0xFFFFFFu - idx);
 }
 
-__device__ void bitonic_sort_desc(u64* s, int n /* power of two */) {
+// The tail CTA is split into two teams of kTeamThreads threads that work concurrently: team 0
+// selects the anchors, team 1 the parts; each has its own sort buffer and syncs on its own named
+// barrier.  They meet once, before the grouping.
+constexpr int kTeamThreads = 256;
+
+struct Team {
+  int tid;    // thread index inside the team
+  int id;     // 0 = anchors, 1 = parts
+  __device__ __forceinline__ void sync() const {
+    asm volatile("bar.sync %0, %1;" ::"r"(id + 1), "r"(kTeamThreads) : "memory");
+  }
+};
+
+__device__ void bitonic_sort_desc(const Team& tm, u64* s, int n /* power of two */) {
   for (int k = 2; k <= n; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      for (int i = tm.tid; i < n; i += kTeamThreads) {
         const int ixj = i ^ j;
         if (ixj > i) {
           const u64 a = s[i], b = s[ixj];
@@ -1349,17 +1372,17 @@ __device__ void bitonic_sort_desc(u64* s, int n /* power of two */) {
           if (desc ? (a < b) : (a > b)) { s[i] = b; s[ixj] = a; }
         }
       }
-      __syncthreads();
+      tm.sync();
     }
   }
 }
 
 // Select the `want` largest composites of planes [c0, c0+nc) of image b into s_sel (sorted
 // descending).  Returns the number selected (< want only when fewer candidates exist).
-__device__ int select_group(const TailParams& p, int b, int c0, int nc, int want, u64* s_sel, u32* s_hist,
-                            int* s_misc) {
+__device__ int select_group(const Team& tm, const TailParams& p, int b, int c0, int nc, int want, u64* s_sel,
+                            u32* s_hist, int* s_misc) {
   const int C = p.M + p.N;
-  const int tid = threadIdx.x;
+  const int tid = tm.tid;
   // total candidates
   if (tid == 0) {
     int tot = 0;
@@ -1367,7 +1390,7 @@ __device__ int select_group(const TailParams& p, int b, int c0, int nc, int want
     s_misc[0] = tot;
     s_misc[1] = 0;  // collected
   }
-  __syncthreads();
+  tm.sync();
   const int total = s_misc[0];
   u64 prefix = 0;   // value of the top `bits` bits that boundary elements share
   int bits = 0;
@@ -1380,23 +1403,23 @@ __device__ int select_group(const TailParams& p, int b, int c0, int nc, int want
     int certain = 0;      // elements strictly above the boundary bucket
     for (int level = 0; level < 8; ++level) {
       const int shift = 56 - 8 * level;
-      for (int i = tid; i < 256; i += blockDim.x) s_hist[i] = 0;
-      __syncthreads();
+      for (int i = tid; i < 256; i += kTeamThreads) s_hist[i] = 0;
+      tm.sync();
       for (int c = 0; c < nc; ++c) {
         const int n = min(p.counts[(size_t)b * C + c0 + c], p.cap);
         const u64* list = p.lists + ((size_t)b * C + c0 + c) * p.cap;
-        for (int i = tid; i < n; i += blockDim.x) {
+        for (int i = tid; i < n; i += kTeamThreads) {
           const u64 v = make_comp(list[i], c);
           if (bits == 0 || (v >> (64 - bits)) == prefix) atomicAdd(&s_hist[(u32)(v >> shift) & 0xffu], 1u);
         }
       }
-      __syncthreads();
+      tm.sync();
       if (tid < 32) {
         // lane l owns digits 8l..8l+7; suffix-scan from the top
-        u32 loc[8], s = 0;
+        u32 loc[8], sum = 0;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) { loc[q] = s_hist[8 * tid + q]; s += loc[q]; }
-        u32 suf = s;
+        for (int q = 0; q < 8; ++q) { loc[q] = s_hist[8 * tid + q]; sum += loc[q]; }
+        u32 suf = sum;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
           u32 t = __shfl_down_sync(0xffffffffu, suf, d);
@@ -1405,7 +1428,7 @@ __device__ int select_group(const TailParams& p, int b, int c0, int nc, int want
         const u32 mask = __ballot_sync(0xffffffffu, suf >= (u32)need);
         const int L = 31 - __clz(mask);  // mask != 0 because the bucket holds >= need elements
         if (tid == L) {
-          u32 above = suf - s;
+          u32 above = suf - sum;
           int dsel = 8 * L;
           for (int q = 7; q >= 0; --q) {
             if (above + loc[q] >= (u32)need) { dsel = 8 * L + q; break; }
@@ -1416,13 +1439,13 @@ __device__ int select_group(const TailParams& p, int b, int c0, int nc, int want
           s_misc[4] = (int)s_hist[dsel];          // size of the new boundary bucket
         }
       }
-      __syncthreads();
+      tm.sync();
       const int dsel = s_misc[2], above = s_misc[3], binc = s_misc[4];
       certain += above;
       need -= above;
       prefix = (prefix << 8) | (u64)dsel;
       bits += 8;
-      __syncthreads();
+      tm.sync();
       if (certain + binc <= target) break;  // everything at or above the boundary bucket is a small sort
     }
   }
@@ -1430,7 +1453,7 @@ __device__ int select_group(const TailParams& p, int b, int c0, int nc, int want
   for (int c = 0; c < nc; ++c) {
     const int n = min(p.counts[(size_t)b * C + c0 + c], p.cap);
     const u64* list = p.lists + ((size_t)b * C + c0 + c) * p.cap;
-    for (int i = tid; i < n; i += blockDim.x) {
+    for (int i = tid; i < n; i += kTeamThreads) {
       const u64 v = make_comp(list[i], c);
       if (bits == 0 || (v >> (64 - bits)) >= prefix) {
         const int slot = atomicAdd(&s_misc[1], 1);
@@ -1438,33 +1461,34 @@ __device__ int select_group(const TailParams& p, int b, int c0, int nc, int want
       }
     }
   }
-  __syncthreads();
+  tm.sync();
   const int got = min(s_misc[1], kSortN);
   int n2 = 32;
   while (n2 < got) n2 <<= 1;
-  for (int i = got + tid; i < n2; i += blockDim.x) s_sel[i] = 0;
-  __syncthreads();
-  bitonic_sort_desc(s_sel, n2);
+  for (int i = got + tid; i < n2; i += kTeamThreads) s_sel[i] = 0;
+  tm.sync();
+  bitonic_sort_desc(tm, s_sel, n2);
   return min(got, want);
 }
 
 // Slots [have, want) of a group are the zero-valued entries torch.topk pads with: under
 // (value desc, index asc) they are the lowest-index pixels of the group's first plane that
 // did not survive NMS.  All of them lie below index `want`.
-__device__ void zero_fill(const TailParams& p, int b, int c0, int have, int want, u64* s_sel, u32* s_bits) {
+__device__ void zero_fill(const Team& tm, const TailParams& p, int b, int c0, int have, int want, u64* s_sel,
+                          u32* s_bits) {
   const int C = p.M + p.N;
-  const int tid = threadIdx.x;
+  const int tid = tm.tid;
   const int words = (want + 31) / 32;
-  for (int i = tid; i < words; i += blockDim.x) s_bits[i] = 0;
-  __syncthreads();
+  for (int i = tid; i < words; i += kTeamThreads) s_bits[i] = 0;
+  tm.sync();
   const int n = min(p.counts[(size_t)b * C + c0], p.cap);
   const u64* list = p.lists + ((size_t)b * C + c0) * p.cap;
-  for (int i = tid; i < n; i += blockDim.x) {
+  for (int i = tid; i < n; i += kTeamThreads) {
     const u32 idx = (u32)list[i];
     if (idx < (u32)want) atomicOr(&s_bits[idx >> 5], 1u << (idx & 31));
   }
-  __syncthreads();
-  for (int s = have + tid; s < want; s += blockDim.x) {
+  tm.sync();
+  for (int s = have + tid; s < want; s += kTeamThreads) {
     int rank = s - have;  // rank-th non-peak index
     int w = 0;
     for (; w < words; ++w) {
@@ -1478,92 +1502,100 @@ __device__ void zero_fill(const TailParams& p, int b, int c0, int have, int want
     // key 0 (score 0.0), class 0
     s_sel[s] = ((u64)255u << 24) | (u64)(0xFFFFFFu - idx);
   }
-  __syncthreads();
+  tm.sync();
 }
 
-__global__ void __launch_bounds__(kTailThreads) sdnet_tail_kernel(const __grid_constant__ TailParams p) {
-  __shared__ u64 s_sel[kSortN];
-  __shared__ u32 s_hist[256];
-  __shared__ int s_misc[8];
+__device__ __forceinline__ float key_to_score(u32 key, bool pre) {
+  if (!pre) return __uint_as_float(key);
+  const u32 bits = (key == 0) ? 0u : ((key & 0x80000000u) ? (key & 0x7fffffffu) : ~key);
+  return __uint_as_float(bits);
+}
+
+__global__ void __launch_bounds__(2 * kTeamThreads) sdnet_tail_kernel(const __grid_constant__ TailParams p) {
+  __shared__ u64 s_sel[2][kSortN];
+  __shared__ u32 s_hist[2][256];
+  __shared__ int s_misc[2][8];
   __shared__ float s_ax[SDNET_MAX_TOPK], s_ay[SDNET_MAX_TOPK];
   __shared__ int s_cnt[2];
   const int b = blockIdx.x;
-  const int tid = threadIdx.x;
+  Team tm;
+  tm.id = threadIdx.x / kTeamThreads;
+  tm.tid = threadIdx.x % kTeamThreads;
   const int W = p.W;
-  if (tid < 2) s_cnt[tid] = 0;
-
-  // ---- anchors
-  int have = select_group(p, b, 0, p.M, p.K, s_sel, s_hist, s_misc);
-  if (have < p.K) zero_fill(p, b, 0, have, p.K, s_sel, s_hist);
+  const bool pre = p.pre_activated != 0;
+  if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
   const float* offx = p.offsets.data + (long long)b * p.offsets.sb;
   const float* offy = offx + p.offsets.sc;
   const long long osh = p.offsets.sh;
-  int n_valid = 0;
-  for (int s = tid; s < p.K; s += blockDim.x) {
-    const u64 v = s_sel[s];
-    u32 key = (u32)(v >> 32);
-    const int cls = 255 - (int)((v >> 24) & 0xffu);
-    const u32 idx = 0xFFFFFFu - (u32)(v & 0xFFFFFFu);
-    const int yy = idx / W, xx = idx - yy * W;
-    float score;
-    if (p.pre_activated) {
-      u32 bits = (key == 0) ? 0u : ((key & 0x80000000u) ? (key & 0x7fffffffu) : ~key);
-      score = __uint_as_float(bits);
-    } else {
-      score = __uint_as_float(key);
+  u64* sel = s_sel[tm.id];
+
+  if (tm.id == 0) {
+    // ---- anchors
+    const int have = select_group(tm, p, b, 0, p.M, p.K, sel, s_hist[0], s_misc[0]);
+    if (have < p.K) zero_fill(tm, p, b, 0, have, p.K, sel, s_hist[0]);
+    int n_valid = 0;
+    for (int s = tm.tid; s < p.K; s += kTeamThreads) {
+      const u64 v = sel[s];
+      const int cls = 255 - (int)((v >> 24) & 0xffu);
+      const u32 idx = 0xFFFFFFu - (u32)(v & 0xFFFFFFu);
+      const int yy = idx / W, xx = idx - yy * W;
+      const float score = key_to_score((u32)(v >> 32), pre);
+      const float x = __fadd_rn((float)xx, __ldg(offx + (long long)yy * osh + xx));
+      const float y = __fadd_rn((float)yy, __ldg(offy + (long long)yy * osh + xx));
+      reinterpret_cast<float4*>(p.anchor_out)[(size_t)b * p.K + s] = make_float4(x, y, score, (float)cls);
+      p.anchor_inds[(size_t)b * p.K + s] = (long long)idx;
+      const bool valid = score > p.conf;
+      // masked anchors sit at (+1e6, +1e6): decoders.py:85-86
+      s_ax[s] = valid ? x : kFar;
+      s_ay[s] = valid ? y : kFar;
+      n_valid += valid ? 1 : 0;
     }
-    const float x = __fadd_rn((float)xx, __ldg(offx + (long long)yy * osh + xx));
-    const float y = __fadd_rn((float)yy, __ldg(offy + (long long)yy * osh + xx));
-    reinterpret_cast<float4*>(p.anchor_out)[(size_t)b * p.K + s] = make_float4(x, y, score, (float)cls);
-    p.anchor_inds[(size_t)b * p.K + s] = (long long)idx;
-    const bool valid = score > p.conf;
-    s_ax[s] = valid ? x : kFar;
-    s_ay[s] = valid ? y : kFar;
-    n_valid += valid ? 1 : 0;
+    if (n_valid) atomicAdd(&s_cnt[0], n_valid);
+  } else {
+    // ---- parts
+    const int have = select_group(tm, p, b, p.M, p.N, p.P, sel, s_hist[1], s_misc[1]);
+    if (have < p.P) zero_fill(tm, p, b, p.M, have, p.P, sel, s_hist[1]);
+    const float* embx = p.embeddings.data ? p.embeddings.data + (long long)b * p.embeddings.sb : nullptr;
+    const float* emby = embx ? embx + p.embeddings.sc : nullptr;
+    const long long esh = p.embeddings.sh;
+    int n_valid = 0;
+    for (int s = tm.tid; s < p.P; s += kTeamThreads) {
+      const u64 v = sel[s];
+      const int cls = 255 - (int)((v >> 24) & 0xffu);
+      const u32 idx = 0xFFFFFFu - (u32)(v & 0xFFFFFFu);
+      const int yy = idx / W, xx = idx - yy * W;
+      const float score = key_to_score((u32)(v >> 32), pre);
+      const float x = __fadd_rn((float)xx, __ldg(offx + (long long)yy * osh + xx));
+      const float y = __fadd_rn((float)yy, __ldg(offy + (long long)yy * osh + xx));
+      float ex = 0.f, ey = 0.f;
+      if (embx) {
+        ex = __ldg(embx + (long long)yy * esh + xx);
+        ey = __ldg(emby + (long long)yy * esh + xx);
+      }
+      const float ox = __fadd_rn(x, ex), oy = __fadd_rn(y, ey);
+      float2* po = reinterpret_cast<float2*>(p.part_out + ((size_t)b * p.P + s) * 6);
+      po[0] = make_float2(x, y);
+      po[1] = make_float2(score, (float)cls);
+      po[2] = make_float2(ox, oy);
+      p.part_inds[(size_t)b * p.P + s] = (long long)idx;
+      if (p.part_emb) reinterpret_cast<float2*>(p.part_emb)[(size_t)b * p.P + s] = make_float2(ex, ey);
+      const bool valid = score > p.conf;
+      n_valid += valid ? 1 : 0;
+      // masked parts sit at (-1e6, -1e6): decoders.py:80-81.  The slot's composite is no longer
+      // needed: keep the part's origin there for the grouping pass.
+      reinterpret_cast<float2*>(sel)[s] = make_float2(valid ? ox : -kFar, valid ? oy : -kFar);
+    }
+    if (n_valid) atomicAdd(&s_cnt[1], n_valid);
   }
-  if (n_valid) atomicAdd(&s_cnt[0], n_valid);
   __syncthreads();
 
-  // ---- parts
-  have = select_group(p, b, p.M, p.N, p.P, s_sel, s_hist, s_misc);
-  if (have < p.P) zero_fill(p, b, p.M, have, p.P, s_sel, s_hist);
-  const float* embx = p.embeddings.data ? p.embeddings.data + (long long)b * p.embeddings.sb : nullptr;
-  const float* emby = embx ? embx + p.embeddings.sc : nullptr;
-  const long long esh = p.embeddings.sh;
-  n_valid = 0;
-  for (int s = tid; s < p.P; s += blockDim.x) {
-    const u64 v = s_sel[s];
-    u32 key = (u32)(v >> 32);
-    const int cls = 255 - (int)((v >> 24) & 0xffu);
-    const u32 idx = 0xFFFFFFu - (u32)(v & 0xFFFFFFu);
-    const int yy = idx / W, xx = idx - yy * W;
-    float score;
-    if (p.pre_activated) {
-      u32 bits = (key == 0) ? 0u : ((key & 0x80000000u) ? (key & 0x7fffffffu) : ~key);
-      score = __uint_as_float(bits);
-    } else {
-      score = __uint_as_float(key);
-    }
-    const float x = __fadd_rn((float)xx, __ldg(offx + (long long)yy * osh + xx));
-    const float y = __fadd_rn((float)yy, __ldg(offy + (long long)yy * osh + xx));
-    float ex = 0.f, ey = 0.f;
-    if (embx) {
-      ex = __ldg(embx + (long long)yy * esh + xx);
-      ey = __ldg(emby + (long long)yy * esh + xx);
-    }
-    const float ox = __fadd_rn(x, ex), oy = __fadd_rn(y, ey);
-    float2* po = reinterpret_cast<float2*>(p.part_out + ((size_t)b * p.P + s) * 6);
-    po[0] = make_float2(x, y);
-    po[1] = make_float2(score, (float)cls);
-    po[2] = make_float2(ox, oy);
-    p.part_inds[(size_t)b * p.P + s] = (long long)idx;
-    if (p.part_emb) reinterpret_cast<float2*>(p.part_emb)[(size_t)b * p.P + s] = make_float2(ex, ey);
-    const bool valid = score > p.conf;
-    n_valid += valid ? 1 : 0;
+  // ---- grouping: every part to its nearest anchor (first minimum), gated by the distance threshold
+  const float2* origin = reinterpret_cast<const float2*>(s_sel[1]);
+  for (int s = threadIdx.x; s < p.P; s += blockDim.x) {
     int slot = -1;
     if (!p.no_grouping) {
-      // masked parts sit at (-1e6, -1e6), masked anchors at (+1e6, +1e6): decoders.py:80-86
-      const float qx = valid ? ox : -kFar, qy = valid ? oy : -kFar;
+      const float qx = origin[s].x, qy = origin[s].y;
       float best = CUDART_INF_F;
       int arg = 0;
       for (int a = 0; a < p.K; ++a) {
@@ -1575,12 +1607,10 @@ __global__ void __launch_bounds__(kTailThreads) sdnet_tail_kernel(const __grid_c
     }
     p.assign[(size_t)b * p.P + s] = slot;
   }
-  if (n_valid) atomicAdd(&s_cnt[1], n_valid);
-  __syncthreads();
-  if (tid < 2) p.out_counts[(size_t)b * 2 + tid] = s_cnt[tid];
+  if (threadIdx.x < 2) p.out_counts[(size_t)b * 2 + threadIdx.x] = s_cnt[threadIdx.x];
   if (p.diag) {
     const int C = p.M + p.N;
-    for (int c = tid; c < C; c += blockDim.x) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
       p.diag[((size_t)b * C + c) * 2 + 0] = p.counts[(size_t)b * C + c];
       p.diag[((size_t)b * C + c) * 2 + 1] = p.exact_flags[(size_t)b * C + c];
     }
@@ -1867,7 +1897,10 @@ int launch_decode(const SdnetDecodeParams* p, cudaStream_t stream, cudaEvent_t* 
     ep.pre_activated = pp.pre_activated;
     ep.lists = pp.lists; ep.counts = pp.counts;
     ep.flags = reinterpret_cast<int*>(base + ws.off_flags);
-    sdnet_exact_select_kernel<<<dim3((unsigned)planes), dim3(kExactThreads), 0, stream>>>(ep);
+    {
+      const size_t exact_grid = planes < (size_t)sms * 2 ? planes : (size_t)sms * 2;
+      sdnet_exact_select_kernel<<<dim3((unsigned)exact_grid), dim3(kExactThreads), 0, stream>>>(ep);
+    }
     err = cudaGetLastError();
     if (err != cudaSuccess) return (int)err;
     if (marks) cudaEventRecord(marks[2], stream);
@@ -1893,7 +1926,7 @@ int launch_decode(const SdnetDecodeParams* p, cudaStream_t stream, cudaEvent_t* 
   tp.out_counts = p->counts;
   tp.diag = p->diag;
   tp.exact_flags = reinterpret_cast<const int*>(base + ws.off_flags);
-  sdnet_tail_kernel<<<dim3((unsigned)p->B), dim3(kTailThreads), 0, stream>>>(tp);
+  sdnet_tail_kernel<<<dim3((unsigned)p->B), dim3(2 * kTeamThreads), 0, stream>>>(tp);
   err = cudaGetLastError();
   if (marks) cudaEventRecord(marks[3], stream);
   return (int)err;
