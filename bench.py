@@ -304,7 +304,7 @@ def main():
             traffic = None
     step_s = ms_per_step * 1e-3
     roofline = {
-        "bound": "hbm", "kernel": "sdnet_peaks_kernel", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+        "bound": "hbm", "kernel": "sdnet_peaks_tile_kernel", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
         "frac": achieved / peak_gbs, "traffic": traffic, "peak_source": peak_src,
         "kernel_ms": {"peaks": peaks_ms, "exact_select": exact_ms, "tail": tail_ms},
         "kernel_share_of_step": peaks_ms / (peaks_ms + exact_ms + tail_ms),
