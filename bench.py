@@ -46,6 +46,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--gather", choices=("fused", "nccl"), default="fused",
+                    help="N > 1: tail kernel stores into every peer (symmetric memory) + barrier, or ncclAllGather")
     return ap.parse_args()
 
 
@@ -242,9 +244,27 @@ def main():
     dist32 = float(torch.tensor(cfg.dist_thresh * min(W, H), dtype=torch.float32))
     plan = ops.DecodePlan(device, shard, M, N, H, W, K, P)
     blob_bytes = plan.out.blob.numel()
-    gathered = torch.empty(world * blob_bytes, dtype=torch.uint8, device=device) if world > 1 else None
+    gathered = None
+    fused = None
+    gather_kind = "none"
+    if world > 1 and args.gather == "fused":
+        try:
+            from structuredetector_b200.parallel import FusedGatherPlan
+
+            fused = FusedGatherPlan(device, cfg.batch, M, N, H, W, K, P)
+            gather_kind = ("fused: tail kernel stores each rank's packed detections into every peer's copy "
+                           "(symmetric memory, st.global over NVLink) + one symmetric-memory barrier")
+        except Exception as exc:  # noqa: BLE001
+            print(f"[bench] symmetric memory unavailable ({exc!r}); falling back to ncclAllGather", file=sys.stderr)
+            fused = None
+    if world > 1 and fused is None:
+        gathered = torch.empty(world * blob_bytes, dtype=torch.uint8, device=device)
+        gather_kind = "ncclAllGather of packed detections (every rank holds all results)"
 
     def step():
+        if fused is not None:
+            fused.run(outs["anchor_hm"], outs["part_hm"], outs["offsets"], outs["embeddings"], conf32, dist32)
+            return
         plan.run(outs["anchor_hm"], outs["part_hm"], outs["offsets"], outs["embeddings"], conf32, dist32)
         if world > 1:
             dist.all_gather_into_tensor(gathered, plan.out.blob)
@@ -277,9 +297,12 @@ def main():
     value = cfg.batch / (ms_per_step * 1e-3)
 
     # ---- sanity: the timed path produced real detections (and every rank agrees after the gather)
-    counts = plan.out.counts.sum(dim=0).tolist()
-    diag_overflow = int(plan.out.diag[:, 1].sum())
-    cand_mean = float(plan.out.diag[:, 0].float().mean())
+    res = fused.result if fused is not None else plan.out
+    counts = res.counts.sum(dim=0).tolist()  # fused: the whole batch, gathered; else this rank's shard
+    if fused is None and world > 1:
+        counts = [c * world for c in counts]
+    diag_overflow = int(res.diag[:, 1].sum())
+    cand_mean = float(res.diag[:, 0].float().mean())
 
     # ---- roofline leg: device time of each kernel (events between the launches), averaged
     reps = 20
@@ -375,7 +398,7 @@ def main():
             "config": {
                 "workload": workload_name(cfg),
                 "mode": args.mode, "images_per_rank": shard, "parallelism": f"batch-shard x{world}",
-                "gather": "ncclAllGather of packed detections (every rank holds all results)" if world > 1 else "none",
+                "gather": gather_kind,
                 "l2": f"inputs larger than L2 ({raw.numel() * 4 / 1e9:.2f} GB per rank, no flush needed)",
                 "unique_images": int(min(UNIQUE_IMAGES, cfg.batch)),
             },

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SDNET_ABI_VERSION 1
+#define SDNET_ABI_VERSION 2
 
 /* element types of the four input tensors */
 #define SDNET_DTYPE_F32 0
@@ -50,6 +50,7 @@ extern "C" {
 
 #define SDNET_MAX_TOPK 1024
 #define SDNET_MAX_CHANNELS 255
+#define SDNET_MAX_DEST 16
 
 /* A strided NCHW view.  Strides are in ELEMENTS.  The decoder consumes the channel-slice
  * views produced by the reference network (src/sdnet/model/network.py:79-84), which are
@@ -83,6 +84,14 @@ typedef struct SdnetDecodeParams {
   int32_t* diag;        /* optional (B*(M+N), 2): candidates emitted per plane, 1 if the exact select ran */
   void* workspace;
   size_t workspace_bytes;
+  /* Fused detection gather (multi-GPU): when n_dest > 0 every output above is written n_dest times, to
+   * (char*)ptr + dest_delta[j].  With the outputs placed in a symmetric (peer-mapped) allocation,
+   * dest_delta[j] = peer_base[j] - local_base makes the tail kernel store each rank's detections
+   * straight into every peer's copy over NVLink; one cross-GPU barrier afterwards replaces the
+   * all-gather.  Include 0 in dest_delta to also keep the local copy.  n_dest = 0: plain local stores. */
+  int32_t n_dest;
+  int32_t reserved0;
+  int64_t dest_delta[SDNET_MAX_DEST];
 } SdnetDecodeParams;
 
 /* Library / ABI identification. */

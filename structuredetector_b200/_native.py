@@ -10,7 +10,7 @@ import ctypes
 from pathlib import Path
 
 LIB_PATH = Path(__file__).resolve().parent / "csrc" / "libsdnet_decode.so"
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 FLAG_PRE_ACTIVATED = 1
 FLAG_NO_GROUPING = 2
@@ -19,6 +19,7 @@ FLAG_WARP_KERNEL = 8
 DTYPE_F32 = 0
 MAX_TOPK = 1024
 MAX_CHANNELS = 255
+MAX_DEST = 16
 
 EXPORTS = (
     "sdnet_abi_version",
@@ -70,6 +71,9 @@ class SdnetDecodeParams(ctypes.Structure):
         ("diag", ctypes.c_void_p),
         ("workspace", ctypes.c_void_p),
         ("workspace_bytes", ctypes.c_size_t),
+        ("n_dest", ctypes.c_int32),
+        ("reserved0", ctypes.c_int32),
+        ("dest_delta", ctypes.c_int64 * MAX_DEST),
     ]
 
 

@@ -1357,7 +1357,20 @@ struct TailParams {
   int* out_counts;
   int* diag;
   const int* exact_flags;  // [planes] 1 if the exact select rewrote the list
+  int n_dest;              // fused gather: every output is stored n_dest times, at ptr + dest_delta[j]
+  long long dest_delta[SDNET_MAX_DEST];
 };
+
+// Store one output value locally (n_dest == 0) or into every destination copy of the output blob
+// (fused detection gather: peer-mapped symmetric memory, plain st.global over NVLink).
+template <typename T>
+__device__ __forceinline__ void store_out(const TailParams& p, T* ptr, const T& v) {
+  if (p.n_dest == 0) {
+    *ptr = v;
+  } else {
+    for (int j = 0; j < p.n_dest; ++j) *reinterpret_cast<T*>(reinterpret_cast<char*>(ptr) + p.dest_delta[j]) = v;
+  }
+}
 
 __device__ __forceinline__ u64 make_comp(u64 rec, int c_local) {
   // rec = key:32 | idx:32  ->  key:32 | (255-c):8 | (0xFFFFFF-idx):24 ; larger = earlier in the output
@@ -1561,8 +1574,8 @@ __global__ void __launch_bounds__(2 * kTeamThreads) sdnet_tail_kernel(const __gr
       const float score = key_to_score((u32)(v >> 32), pre);
       const float x = __fadd_rn((float)xx, __ldg(offx + (long long)yy * osh + xx));
       const float y = __fadd_rn((float)yy, __ldg(offy + (long long)yy * osh + xx));
-      reinterpret_cast<float4*>(p.anchor_out)[(size_t)b * p.K + s] = make_float4(x, y, score, (float)cls);
-      p.anchor_inds[(size_t)b * p.K + s] = (long long)idx;
+      store_out(p, reinterpret_cast<float4*>(p.anchor_out) + (size_t)b * p.K + s, make_float4(x, y, score, (float)cls));
+      store_out(p, p.anchor_inds + (size_t)b * p.K + s, (long long)idx);
       const bool valid = score > p.conf;
       // masked anchors sit at (+1e6, +1e6): decoders.py:85-86
       s_ax[s] = valid ? x : kFar;
@@ -1593,11 +1606,11 @@ __global__ void __launch_bounds__(2 * kTeamThreads) sdnet_tail_kernel(const __gr
       }
       const float ox = __fadd_rn(x, ex), oy = __fadd_rn(y, ey);
       float2* po = reinterpret_cast<float2*>(p.part_out + ((size_t)b * p.P + s) * 6);
-      po[0] = make_float2(x, y);
-      po[1] = make_float2(score, (float)cls);
-      po[2] = make_float2(ox, oy);
-      p.part_inds[(size_t)b * p.P + s] = (long long)idx;
-      if (p.part_emb) reinterpret_cast<float2*>(p.part_emb)[(size_t)b * p.P + s] = make_float2(ex, ey);
+      store_out(p, po + 0, make_float2(x, y));
+      store_out(p, po + 1, make_float2(score, (float)cls));
+      store_out(p, po + 2, make_float2(ox, oy));
+      store_out(p, p.part_inds + (size_t)b * p.P + s, (long long)idx);
+      if (p.part_emb) store_out(p, reinterpret_cast<float2*>(p.part_emb) + (size_t)b * p.P + s, make_float2(ex, ey));
       const bool valid = score > p.conf;
       n_valid += valid ? 1 : 0;
       // masked parts sit at (-1e6, -1e6): decoders.py:80-81.  The slot's composite is no longer
@@ -1623,16 +1636,17 @@ __global__ void __launch_bounds__(2 * kTeamThreads) sdnet_tail_kernel(const __gr
       }
       slot = (best < p.dist_abs) ? arg : -1;
     }
-    p.assign[(size_t)b * p.P + s] = slot;
+    store_out(p, p.assign + (size_t)b * p.P + s, slot);
   }
-  if (threadIdx.x < 2) p.out_counts[(size_t)b * 2 + threadIdx.x] = s_cnt[threadIdx.x];
+  if (threadIdx.x < 2) store_out(p, p.out_counts + (size_t)b * 2 + threadIdx.x, s_cnt[threadIdx.x]);
   if (p.diag) {
     const int C = p.M + p.N;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      p.diag[((size_t)b * C + c) * 2 + 0] = p.counts[(size_t)b * C + c];
-      p.diag[((size_t)b * C + c) * 2 + 1] = p.exact_flags[(size_t)b * C + c];
+      store_out(p, p.diag + ((size_t)b * C + c) * 2 + 0, p.counts[(size_t)b * C + c]);
+      store_out(p, p.diag + ((size_t)b * C + c) * 2 + 1, p.exact_flags[(size_t)b * C + c]);
     }
   }
+  if (p.n_dest) __threadfence_system();  // peer stores performed before the kernel retires
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1695,6 +1709,7 @@ int validate(const SdnetDecodeParams* p) {
   if (hw >= (1ll << 24) || p->K > hw || p->P > hw) return SDNET_E_SHAPE;
   if (p->K > SDNET_MAX_TOPK || p->P > SDNET_MAX_TOPK || p->M + p->N > SDNET_MAX_CHANNELS) return SDNET_E_SHAPE;
   if (p->radius != 1 && p->radius != 2) return SDNET_E_RADIUS;
+  if (p->n_dest < 0 || p->n_dest > SDNET_MAX_DEST) return SDNET_E_SHAPE;
   const bool no_group = (p->flags & SDNET_FLAG_NO_GROUPING) != 0;
   if (!p->anchor_hm.data || !p->part_hm.data || !p->offsets.data || (!no_group && !p->embeddings.data)) return SDNET_E_NULL;
   if (!p->anchor_out || !p->part_out || !p->anchor_inds || !p->part_inds || !p->assign || !p->counts) return SDNET_E_NULL;
@@ -1944,6 +1959,8 @@ int launch_decode(const SdnetDecodeParams* p, cudaStream_t stream, cudaEvent_t* 
   tp.out_counts = p->counts;
   tp.diag = p->diag;
   tp.exact_flags = reinterpret_cast<const int*>(base + ws.off_flags);
+  tp.n_dest = p->n_dest;
+  for (int j = 0; j < SDNET_MAX_DEST; ++j) tp.dest_delta[j] = j < p->n_dest ? p->dest_delta[j] : 0;
   sdnet_tail_kernel<<<dim3((unsigned)p->B), dim3(2 * kTeamThreads), 0, stream>>>(tp);
   err = cudaGetLastError();
   if (marks) cudaEventRecord(marks[3], stream);

@@ -13,7 +13,7 @@ import torch.distributed as dist
 
 from . import ops
 
-__all__ = ["shard_bounds", "shard_sizes", "all_gather_packed", "merge_packed", "ShardedDecoder"]
+__all__ = ["shard_bounds", "shard_sizes", "all_gather_packed", "merge_packed", "ShardedDecoder", "FusedGatherPlan"]
 
 _FIELDS = ("anchor_out", "part_out", "anchor_inds", "part_inds", "part_emb", "assign", "counts", "diag")
 
@@ -72,3 +72,50 @@ class ShardedDecoder:
         packed = ops.decode_packed(local_outputs, self.K, self.P, self.conf, self.dist)
         C = local_outputs["anchor_hm"].shape[1] + local_outputs["part_hm"].shape[1]
         return all_gather_packed(packed.blob, sizes, self.K, self.P, C, self.group)
+
+
+class FusedGatherPlan:
+    """Decode + gather in one pass: the tail kernel stores every rank's packed detections straight
+    into EVERY rank's copy of the global result (peer-mapped symmetric memory, plain stores over
+    NVLink / NVSwitch), and one cross-GPU barrier replaces the all-gather collective.
+
+    The global result is one packed blob for the whole batch (``ops._carve`` layout); rank r owns the
+    image rows ``shard_bounds(B, world, r)`` of every field.  ``dest_delta[j] = peer_base[j] -
+    local_base`` (``SdnetDecodeParams.dest_delta``) is all the kernel needs, because symmetric buffers
+    share one layout.  Requires equal per-field offsets on all ranks, i.e. the same (B, K, P, C).
+    """
+
+    def __init__(self, device, global_batch: int, M: int, N: int, H: int, W: int, K: int, P: int, group=None):
+        import torch.distributed._symmetric_memory as symm
+
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.sizes = shard_sizes(global_batch, self.world)
+        self.lo, self.hi = shard_bounds(global_batch, self.world, self.rank)
+        C = M + N
+        nbytes = ops.packed_nbytes(global_batch, K, P, C)
+        self.blob = symm.empty(nbytes, dtype=torch.uint8, device=device)
+        self.handle = symm.rendezvous(self.blob, self.group)
+        self.result = ops._carve(self.blob, global_batch, K, P, C)  # the gathered detections, valid after run()
+        shard = self.hi - self.lo
+        self.plan = ops.DecodePlan(device, shard, M, N, H, W, K, P)
+        # point the plan's outputs at this rank's rows of the global blob ...
+        lo, hi = self.lo, self.hi
+        mine = ops.PackedDetections(
+            self.result.anchor_out[lo:hi], self.result.part_out[lo:hi], self.result.anchor_inds[lo:hi],
+            self.result.part_inds[lo:hi], self.result.part_emb[lo:hi], self.result.assign[lo:hi],
+            self.result.counts[lo:hi], self.result.diag[lo * C:hi * C], None)
+        self.plan._bind_outputs(mine)
+        # ... and have every store replicated into the peers' copies
+        ptrs = list(self.handle.buffer_ptrs)
+        prm = self.plan.params
+        prm.n_dest = self.world
+        for j in range(self.world):
+            prm.dest_delta[j] = int(ptrs[j]) - int(ptrs[self.rank])
+        self.handle.barrier()  # everyone is mapped before the first remote store
+
+    def run(self, anchor_hm, part_hm, offsets, embeddings, conf_f32, dist_abs_f32, radius=2, flags=0) -> ops.PackedDetections:
+        """Enqueue decode + remote stores + the barrier on the current stream; returns the global result."""
+        self.plan.run(anchor_hm, part_hm, offsets, embeddings, conf_f32, dist_abs_f32, radius, flags)
+        self.handle.barrier()
+        return self.result
