@@ -94,6 +94,13 @@ __device__ __forceinline__ float activate(float x) {
 
 __device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
 
+// Programmatic dependent launch: the next kernel of the decode may be scheduled while this one is
+// still running (its CTAs take whatever SM resources free up and park at pdl_wait), which hides the
+// launch latency between the three kernels.  pdl_wait returns once the previous kernel has fully
+// completed and its memory is visible.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ float comp(const float4& v, int j) {
   return j == 0 ? v.x : (j == 1 ? v.y : (j == 2 ? v.z : v.w));
 }
@@ -975,6 +982,7 @@ sdnet_peaks_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_cons
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int NG = kTileNG;
   constexpr u32 kRowMask = NG * kGroupRows - 1;
+  pdl_launch_dependents();
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   unsigned char* wbase = smem_raw + (size_t)warp * kTileSmemPerWarp;
@@ -1217,6 +1225,8 @@ __global__ void __launch_bounds__(kExactThreads) sdnet_exact_select_kernel(const
   __shared__ int s_base[2];
   const int C = p.M + p.N;
   const int planes = p.B * C;
+  pdl_launch_dependents();
+  pdl_wait();  // the peaks kernel's lists and counts are complete and visible
   if (!p.force) {
     // common case: nothing overflowed.  One coalesced look at this CTA's planes, then leave.
     int mine = 0;
@@ -1555,6 +1565,7 @@ __global__ void __launch_bounds__(2 * kTeamThreads) sdnet_tail_kernel(const __gr
   const int W = p.W;
   const bool pre = p.pre_activated != 0;
   if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
+  pdl_wait();  // candidate lists (peaks kernel, possibly rewritten by the exact select) are final
   __syncthreads();
   const float* offx = p.offsets.data + (long long)b * p.offsets.sb;
   const float* offy = offx + p.offsets.sc;
@@ -1775,6 +1786,22 @@ void launch_peaks(Kern kern, dim3 grid, dim3 block, cudaStream_t stream, const P
   kern<<<grid, block, kPeaksSmem, stream>>>(pp);
 }
 
+// Launch with programmatic stream serialization (PDL): see pdl_wait() in the kernels.
+template <typename Kern, typename Params>
+void launch_pdl(Kern kern, dim3 grid, dim3 block, cudaStream_t stream, const Params& prm) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kern, prm);
+}
+
 int launch_decode(const SdnetDecodeParams* p, cudaStream_t stream, cudaEvent_t* marks = nullptr) {
   const Workspace ws = plan_workspace(p->B, p->M, p->N, p->H, p->W, p->K, p->P);
   char* base = static_cast<char*>(p->workspace);
@@ -1932,7 +1959,7 @@ int launch_decode(const SdnetDecodeParams* p, cudaStream_t stream, cudaEvent_t* 
     ep.flags = reinterpret_cast<int*>(base + ws.off_flags);
     {
       const size_t exact_grid = planes < (size_t)sms * 2 ? planes : (size_t)sms * 2;
-      sdnet_exact_select_kernel<<<dim3((unsigned)exact_grid), dim3(kExactThreads), 0, stream>>>(ep);
+      launch_pdl(sdnet_exact_select_kernel, dim3((unsigned)exact_grid), dim3(kExactThreads), stream, ep);
     }
     err = cudaGetLastError();
     if (err != cudaSuccess) return (int)err;
@@ -1961,7 +1988,7 @@ int launch_decode(const SdnetDecodeParams* p, cudaStream_t stream, cudaEvent_t* 
   tp.exact_flags = reinterpret_cast<const int*>(base + ws.off_flags);
   tp.n_dest = p->n_dest;
   for (int j = 0; j < SDNET_MAX_DEST; ++j) tp.dest_delta[j] = j < p->n_dest ? p->dest_delta[j] : 0;
-  sdnet_tail_kernel<<<dim3((unsigned)p->B), dim3(2 * kTeamThreads), 0, stream>>>(tp);
+  launch_pdl(sdnet_tail_kernel, dim3((unsigned)p->B), dim3(2 * kTeamThreads), stream, tp);
   err = cudaGetLastError();
   if (marks) cudaEventRecord(marks[3], stream);
   return (int)err;
