@@ -672,15 +672,15 @@ inline CtaGeom cta_geometry(int W, int ng) {
 // Window maxima of a lane's four pixels for output row t, straight from the ring.  Ring rows
 // are contiguous in shared memory, so ring row q of a unit whose first group has running number
 // n lives at row (4 n + q) mod (4 NG): `rowbase` = 4 n, `rowmask` = 4 NG - 1.
-template <int R>
-__device__ __forceinline__ void window_max(u32 ring_own, u32 rowbase, u32 rowmask, int rpb, int t, bool left_ok,
+template <int R, u32 kRows>
+__device__ __forceinline__ void window_max(u32 ring_own, u32 rowbase, int rpb, int t, bool left_ok,
                                            bool right_ok, float& h0, float& h1, float& h2, float& h3) {
   const float ninf = -CUDART_INF_F;
   float v0 = ninf, v1 = ninf, v2 = ninf, v3 = ninf, v4 = ninf, v5 = ninf, v6 = ninf, v7 = ninf;  // cols c-2 .. c+5
   const u32 loff = left_ok ? 8u : 0u;  // column 0 has no left neighbours (and nothing mapped before the ring)
 #pragma unroll
   for (int d = 0; d <= 2 * R; ++d) {
-    const u32 a = ring_own + ((rowbase + (u32)(t + d)) & rowmask) * rpb;
+    const u32 a = ring_own + ((rowbase + (u32)(t + d)) % kRows) * rpb;  // kRows is a constant: AND when a power of two
     const float4 o = lds128(a);
     const float2 l = lds64(a - loff);
     const float2 r = lds64(a + 16);
@@ -912,7 +912,7 @@ __global__ void __launch_bounds__((kMaxConsumers + 1) * 32, 3) sdnet_peaks_cta_k
           u32 cmask = 0;
           if (!pre) {
             float h0, h1, h2, h3;
-            window_max<R>(ring_own, rowbase, kRowMask, rpb, t, left_ok, right_ok, h0, h1, h2, h3);
+            window_max<R, NG * kGroupRows>(ring_own, rowbase, rpb, t, left_ok, right_ok, h0, h1, h2, h3);
             cmask = classify_row<R>(ctr, h0, h1, h2, h3, floorx);
           } else {
             if (ctr.x > floorx) cmask |= 1u;
@@ -965,9 +965,9 @@ constexpr int kTileCols = kPanelW + 8;
 constexpr int kTilePitchB = kTileCols * 4;                   // 544 B per ring row
 constexpr int kTileBytes = kGroupRows * kTilePitchB;         // 2176 B per TMA tile (17 x 128 B)
 constexpr int kTileWarps = 4;
-constexpr int kTileNG = 4;                                   // ring slots (tiles) per warp
-constexpr int kTileSmemPerWarp = ((kTileNG * kTileBytes + kTileNG * 8 + kBins * 8 + kBuf * 8) + 127) / 128 * 128;
-constexpr int kTileSmem = kTileWarps * kTileSmemPerWarp;
+// ring slots (tiles) per warp: 4 = two tiles in flight, 5 CTAs/SM; 3 = one in flight, 6 CTAs/SM
+__host__ __device__ constexpr int tile_smem_per_warp(int ng) { return ((ng * kTileBytes + 32 + kBins * 8 + kBuf * 8) + 127) / 128 * 128; }
+__host__ __device__ constexpr int tile_smem(int ng) { return kTileWarps * tile_smem_per_warp(ng); }
 
 __device__ __forceinline__ void tma_tile_4d(u32 dst, const CUtensorMap* map, int x, int y, int c, int b, u32 bar) {
   asm volatile(
@@ -975,20 +975,20 @@ __device__ __forceinline__ void tma_tile_4d(u32 dst, const CUtensorMap* map, int
       ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(c), "r"(b), "r"(bar) : "memory");
 }
 
-template <int R>
-__global__ void __launch_bounds__(kTileWarps * 32, 5)
+template <int R, int NG>
+__global__ void __launch_bounds__(kTileWarps * 32, NG == 3 ? 6 : 5)
 sdnet_peaks_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_constant__ CUtensorMap tm_anchor,
                         const __grid_constant__ CUtensorMap tm_part) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  constexpr int NG = kTileNG;
-  constexpr u32 kRowMask = NG * kGroupRows - 1;
+  constexpr u32 kRows = NG * kGroupRows;
+  constexpr int kTileSmemPerWarp = tile_smem_per_warp(NG);
   pdl_launch_dependents();
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   unsigned char* wbase = smem_raw + (size_t)warp * kTileSmemPerWarp;
   const u32 ring_s = smem_u32(wbase);
   const u32 bars_s = ring_s + NG * kTileBytes;
-  u32* hist = reinterpret_cast<u32*>(wbase + NG * kTileBytes + NG * 8);
+  u32* hist = reinterpret_cast<u32*>(wbase + NG * kTileBytes + 32);
   int* minx = reinterpret_cast<int*>(hist + kBins);
   u64* buf = reinterpret_cast<u64*>(minx + kBins);
   const bool pre = p.pre_activated != 0;
@@ -1069,7 +1069,7 @@ sdnet_peaks_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_cons
     phases ^= 1u;
     for (int g = 0; g < groups_out; ++g) {
       if (g + 1 < groups) {
-        const u32 s1 = (u32)(g + 1) & (NG - 1);
+        const u32 s1 = (u32)(g + 1) % NG;
         mbar_wait(bars_s + 8 * s1, (phases >> s1) & 1u);
         phases ^= 1u << s1;
       }
@@ -1082,10 +1082,10 @@ sdnet_peaks_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_cons
       }
       const int t0 = g * kGroupRows;
       // centre row of output row t0+i is ring row t0+i+R
-      const float4 c0 = lds128(ring_own + ((rowbase + (u32)(t0 + R)) & kRowMask) * kTilePitchB);
-      const float4 c1 = lds128(ring_own + ((rowbase + (u32)(t0 + R + 1)) & kRowMask) * kTilePitchB);
-      const float4 c2 = lds128(ring_own + ((rowbase + (u32)(t0 + R + 2)) & kRowMask) * kTilePitchB);
-      const float4 c3 = lds128(ring_own + ((rowbase + (u32)(t0 + R + 3)) & kRowMask) * kTilePitchB);
+      const float4 c0 = lds128(ring_own + ((rowbase + (u32)(t0 + R)) % kRows) * kTilePitchB);
+      const float4 c1 = lds128(ring_own + ((rowbase + (u32)(t0 + R + 1)) % kRows) * kTilePitchB);
+      const float4 c2 = lds128(ring_own + ((rowbase + (u32)(t0 + R + 2)) % kRows) * kTilePitchB);
+      const float4 c3 = lds128(ring_own + ((rowbase + (u32)(t0 + R + 3)) % kRows) * kTilePitchB);
       const int rows_here = min(kGroupRows, nrows - t0);
       float m0 = fmaxf(fmaxf(c0.x, c0.y), fmaxf(c0.z, c0.w));
       float m1 = fmaxf(fmaxf(c1.x, c1.y), fmaxf(c1.z, c1.w));
@@ -1106,12 +1106,12 @@ sdnet_peaks_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_cons
           const int i = __ffs(rowmask4) - 1;
           rowmask4 &= rowmask4 - 1;
           const int t = t0 + i;
-          const float4 ctr = lds128(ring_own + ((rowbase + (u32)(t + R)) & kRowMask) * kTilePitchB);
+          const float4 ctr = lds128(ring_own + ((rowbase + (u32)(t + R)) % kRows) * kTilePitchB);
           const float floorx = st.floorx;
           u32 cmask = 0;
           if (!pre) {
             float h0, h1, h2, h3;
-            window_max<R>(ring_own, rowbase, kRowMask, kTilePitchB, t, true, true, h0, h1, h2, h3);
+            window_max<R, kRows>(ring_own, rowbase, kTilePitchB, t, true, true, h0, h1, h2, h3);
             cmask = classify_row<R>(ctr, h0, h1, h2, h3, floorx);
           } else {
             if (ctr.x > floorx) cmask |= 1u;
@@ -1127,7 +1127,7 @@ sdnet_peaks_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_cons
       // the tile NG ahead
       __syncwarp();
       if (lane == 0 && g + NG < groups) {
-        const u32 slot = (u32)g & (NG - 1);
+        const u32 slot = (u32)g % NG;
         mbar_arrive_expect_tx(bars_s + 8 * slot, kTileBytes);
         tma_tile_4d(ring_s + slot * kTileBytes, tmap, x0, y0 + kGroupRows * (g + NG), csel, b, bars_s + 8 * slot);
       }
@@ -1858,7 +1858,13 @@ int launch_decode(const SdnetDecodeParams* p, cudaStream_t stream, cudaEvent_t* 
     pp.strips = (p->H + pp.rows_per_strip - 1) / pp.rows_per_strip;
   };
   if (use_tile) {
-    auto kern = p->radius == 2 ? sdnet_peaks_tile_kernel<2> : sdnet_peaks_tile_kernel<1>;
+    static const int tile_ng = [] {  // tuning knob, read once: SDNET_TILE_RING = 3 | 4
+      const char* e = getenv("SDNET_TILE_RING");
+      return (e && atoi(e) == 3) ? 3 : 4;
+    }();
+    auto kern = tile_ng == 3 ? (p->radius == 2 ? sdnet_peaks_tile_kernel<2, 3> : sdnet_peaks_tile_kernel<1, 3>)
+                             : (p->radius == 2 ? sdnet_peaks_tile_kernel<2, 4> : sdnet_peaks_tile_kernel<1, 4>);
+    const int kTileSmem = tile_smem(tile_ng);
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem);
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     static int per_sm = 0;

@@ -164,3 +164,25 @@ def test_strided_channel_views_and_errors(cuda_device):
         ops.decode_packed({k: v.half() for k, v in outs.items()}, 100, 100, 0.4, 0.1)
     with pytest.raises(RuntimeError):
         ops.decode_packed(outs, 128 * 128 + 1, 100, 0.4, 0.1)
+
+
+def test_randomised_shapes_and_thresholds(cuda_device):
+    """Seeded fuzz over shapes, class counts, K/P, thresholds, radius and input modes: every case
+    bit-exact against the oracle fed the device's sigmoid."""
+    rng = np.random.default_rng(20260118)
+    modes = ("noise", "blobs", "ties", "ladder")
+    for case in range(40):
+        h = int(rng.integers(1, 90))
+        w = int(rng.choice([rng.integers(1, 40), rng.integers(40, 300), 4 * rng.integers(1, 80)]))
+        m, n = int(rng.integers(1, 5)), int(rng.integers(1, 4))
+        k = int(rng.integers(1, min(h * w, 120) + 1))
+        p = int(rng.integers(1, min(h * w, 120) + 1))
+        cfg = DecodeConfig(f"fuzz{case}", int(rng.integers(1, 4)), m, n, h, w, k, p, cfg_id=200 + case)
+        mode = modes[case % len(modes)]
+        raw = make_raw(cfg, mode)
+        conf = float(rng.choice([0.05, 0.3, 0.4, 0.5, 0.9]))
+        dist = float(rng.choice([0.02, 0.1, 0.5, 2.0]))
+        radius = 2 if case % 5 else 1
+        got, want = _decode_both(cfg, raw, cuda_device, conf=conf, dist=dist, radius=radius,
+                                 warp_kernel=bool(case % 7 == 3), exact_select=bool(case % 11 == 5))
+        assert_packed_equal(got, want, what=f"fuzz {case}: {h}x{w} M{m} N{n} K{k} P{p} {mode} conf{conf} dist{dist} r{radius}")
