@@ -42,6 +42,8 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", choices=("ours", "reference"), default="ours")
     ap.add_argument("--mode", choices=("noise", "blobs"), default="noise")
+    ap.add_argument("--dtype", choices=("f32", "f16", "bf16"), default="f32",
+                    help="element type of the network outputs (f32 = the headline; f16/bf16 = the --amp validation path)")
     ap.add_argument("--global-batch", type=int, default=None, help="override cfg5's 1024 (debug only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -237,13 +239,18 @@ def main():
     uniq = make_raw(cfg, args.mode, batch=min(UNIQUE_IMAGES, cfg.batch))
     uniq_dev = uniq.to(device)
     idx = (torch.arange(shard, device=device) + rank * shard) % uniq_dev.shape[0]
-    raw = uniq_dev[idx].contiguous()  # (shard, M+N+4, H, W), resident in HBM
+    tdtype = {"f32": torch.float32, "f16": torch.float16, "bf16": torch.bfloat16}[args.dtype]
+    esize = 4 if args.dtype == "f32" else 2
+    raw = uniq_dev[idx].contiguous().to(tdtype)  # (shard, M+N+4, H, W), resident in HBM
     del uniq_dev
     outs = split_outputs(raw, M, N)
-    conf32 = float(torch.tensor(cfg.conf_threshold, dtype=torch.float32))
+    conf32 = float(torch.tensor(cfg.conf_threshold, dtype=tdtype))
     dist32 = float(torch.tensor(cfg.dist_thresh * min(W, H), dtype=torch.float32))
-    plan = ops.DecodePlan(device, shard, M, N, H, W, K, P)
+    plan = ops.DecodePlan(device, shard, M, N, H, W, K, P, tdtype)
     blob_bytes = plan.out.blob.numel()
+    if args.dtype != "f32":
+        args.no_e2e = True       # the host-buffer entry point is fp32-only
+        args.gather = "nccl" if args.gather == "fused" else args.gather
     gathered = None
     fused = None
     gather_kind = "none"
@@ -311,7 +318,7 @@ def main():
     peaks_ms = statistics.mean(k[0] for k in kms)
     exact_ms = statistics.mean(k[1] for k in kms)
     tail_ms = statistics.mean(k[2] for k in kms)
-    peaks_bytes = shard * (M + N) * H * W * 4  # algorithmic bytes of the dominant kernel: heat maps read once
+    peaks_bytes = shard * (M + N) * H * W * esize  # algorithmic bytes of the dominant kernel: heat maps read once
     peaks_path = ROOT / "MEASURED_PEAKS.json"
     if peaks_path.exists():
         peak_gbs, peak_src = float(json.loads(peaks_path.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
@@ -327,16 +334,16 @@ def main():
             traffic = None
     step_s = ms_per_step * 1e-3
     roofline = {
-        "bound": "hbm", "kernel": "sdnet_peaks_tile_kernel", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+        "bound": "hbm", "kernel": "sdnet_peaks_tile_kernel" if args.dtype == "f32" else "sdnet_peaks_kernel (converting feed)", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
         "frac": achieved / peak_gbs, "traffic": traffic, "peak_source": peak_src,
         "kernel_ms": {"peaks": peaks_ms, "exact_select": exact_ms, "tail": tail_ms},
         "kernel_share_of_step": peaks_ms / (peaks_ms + exact_ms + tail_ms),
         "algorithmic_bytes_per_launch": peaks_bytes,
         # whole step (all kernels + gather), per rank, under the two denominators of SURVEY 8(d)
-        "step_achieved_min_gbs": shard * cfg.min_bytes_per_image / step_s / 1e9,
-        "step_achieved_contract_gbs": shard * cfg.contract_bytes_per_image / step_s / 1e9,
-        "frac_of_8tbs_min": shard * cfg.min_bytes_per_image / step_s / 8e12,
-        "frac_of_8tbs_contract": shard * cfg.contract_bytes_per_image / step_s / 8e12,
+        "step_achieved_min_gbs": shard * cfg.min_bytes_per_image * esize / 4 / step_s / 1e9,
+        "step_achieved_contract_gbs": shard * cfg.contract_bytes_per_image * esize / 4 / step_s / 1e9,
+        "frac_of_8tbs_min": shard * cfg.min_bytes_per_image * esize / 4 / step_s / 8e12,
+        "frac_of_8tbs_contract": shard * cfg.contract_bytes_per_image * esize / 4 / step_s / 8e12,
     }
 
     # ---- end to end through the C ABI with HOST buffers: pinned inputs -> packed results on the host
@@ -376,7 +383,7 @@ def main():
         del host_raw, staging
 
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.dtype == "f32":
         res = cpu_reference_rate(cfg, args.mode, seconds=12.0)
         cpu_baseline = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
         cpu_baseline["host_cpus"] = res["host_cpus"]
@@ -393,10 +400,10 @@ def main():
             "higher_is_better": True,
             "scaling": "strong",
             "vs_baseline": None,
-            "dtype": "f32",
+            "dtype": args.dtype,
             "data": "synthetic",
             "config": {
-                "workload": workload_name(cfg),
+                "workload": workload_name(cfg) if args.dtype == "f32" else workload_name(cfg).replace("fp32", args.dtype),
                 "mode": args.mode, "images_per_rank": shard, "parallelism": f"batch-shard x{world}",
                 "gather": gather_kind,
                 "l2": f"inputs larger than L2 ({raw.numel() * 4 / 1e9:.2f} GB per rank, no flush needed)",

@@ -31,6 +31,8 @@ extern "C" {
 
 /* element types of the four input tensors */
 #define SDNET_DTYPE_F32 0
+#define SDNET_DTYPE_F16 1  /* what the reference's --amp validation feeds the decoder (src/sdnet/model/trainer.py:40-42,142-157) */
+#define SDNET_DTYPE_BF16 2
 
 /* SdnetDecodeParams.flags */
 #define SDNET_FLAG_PRE_ACTIVATED 1u /* heat maps already sigmoid+NMS'd: decoders.py:211,226 (CoreMLDecoder) */
@@ -62,7 +64,7 @@ typedef struct SdnetTensor4 {
 
 typedef struct SdnetDecodeParams {
   uint32_t struct_size; /* sizeof(SdnetDecodeParams) */
-  int32_t dtype;        /* SDNET_DTYPE_* */
+  int32_t dtype;        /* SDNET_DTYPE_*: element type of all four input tensors */
   int32_t B, M, N, H, W; /* batch, anchor classes, part kinds, map rows, map cols */
   int32_t K, P;          /* max_objects, max_parts (decoders.py:25-26) */
   int32_t radius;        /* NMS window radius; 2 = the reference's 5x5 (utils.py:442) */

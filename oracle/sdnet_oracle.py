@@ -140,12 +140,20 @@ def decode_packed(
     pre_activated: bool = False,
     radius: int = 2,
     group: bool = True,
+    activation_fn=None,
+    conf_cmp=None,
 ):
     """Tensor half of the decoder (reference: src/sdnet/data/decoders.py:40-100).
 
     ``pre_activated`` skips sigmoid+NMS (the CoreMLDecoder variant, decoders.py:211,226).
     Returns a dict of numpy arrays laid out like the C-ABI outputs in
     ``include/sdnet_decode.h``.
+
+    Reduced-precision inputs (fp16 / bf16, what the reference decodes under ``--amp``): pass the maps
+    converted exactly to float32, ``activation_fn`` = the dtype's whole clamped sigmoid (ATen rounds
+    the sigmoid and the clamp to the tensor dtype; its results are exactly representable in float32)
+    and ``conf_cmp`` = the threshold rounded to that dtype (``scores > conf`` compares in the scores'
+    dtype).  Everything after the activation is dtype-independent.
     """
     anchor_hm = np.asarray(anchor_hm, dtype=F32)
     part_hm = np.asarray(part_hm, dtype=F32)
@@ -157,8 +165,8 @@ def decode_packed(
     if pre_activated:
         a_sig, p_sig, a_nms, p_nms = anchor_hm, part_hm, anchor_hm, part_hm
     else:
-        a_sig = clamped_sigmoid(anchor_hm, sigmoid_fn)
-        p_sig = clamped_sigmoid(part_hm, sigmoid_fn)
+        act = (lambda m: np.asarray(activation_fn(m), dtype=F32)) if activation_fn else (lambda m: clamped_sigmoid(m, sigmoid_fn))
+        a_sig, p_sig = act(anchor_hm), act(part_hm)
         a_nms, p_nms = nms(a_sig, radius), nms(p_sig, radius)
 
     a_score, a_ind, a_cls, a_ys, a_xs = topk(a_nms, k)
@@ -188,7 +196,7 @@ def decode_packed(
     if not group:
         return out
 
-    conf32 = F32(conf_thresh)  # tensor > python-float compares in fp32
+    conf32 = F32(conf_thresh if conf_cmp is None else conf_cmp)  # tensor > python-float compares in the tensor's dtype
     one = F32(1.0)
     p_mask = (p_score > conf32).astype(F32)
     a_mask = (a_score > conf32).astype(F32)

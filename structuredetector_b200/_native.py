@@ -17,6 +17,8 @@ FLAG_NO_GROUPING = 2
 FLAG_EXACT_SELECT = 4
 FLAG_WARP_KERNEL = 8
 DTYPE_F32 = 0
+DTYPE_F16 = 1
+DTYPE_BF16 = 2
 MAX_TOPK = 1024
 MAX_CHANNELS = 255
 MAX_DEST = 16

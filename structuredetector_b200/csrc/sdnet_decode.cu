@@ -29,6 +29,8 @@
 //   * grouping arithmetic uses explicitly rounded mul/add/sqrt (no FMA contraction) and the
 //     first minimum wins.
 #include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include <stdint.h>
@@ -50,9 +52,6 @@ constexpr float kBinScale = 4.0f;      // bins of 0.25 logit
 constexpr int kFineBins = 512;         // shared (CTA-wide / plane-wide) histograms: bins of 1/16 logit
 constexpr float kFineScale = 16.0f;    // (256 x 0.125: blobs 3 % slower; 1024 x 1/32: flushes 25 % slower)
 constexpr int kFinePerLane = kFineBins / 32;
-constexpr float kNearTie = 2e-3f;      // logit margin inside which two scores may round equal (|x| <= 8)
-constexpr float kHiZone = 8.0f;        // above this, score spacing approaches 1 ulp: always check exactly
-constexpr float kLoZone = -13.0f;      // below this, scores approach the 1e-6 clamp: always check exactly
 constexpr float kSatX = 14.0f;         // |x| >= 14 is inside the clamp on both sides: S(x) == S(+-14)
 constexpr float kPreScale = 8.0f;      // pre-activated maps: histogram runs on 8*value
 constexpr float kClampLo = 1e-6f;
@@ -62,8 +61,8 @@ constexpr float kFar = 1e6f;
 constexpr int kSortN = 2048;           // tail sort buffer (>= SDNET_MAX_TOPK + boundary slack)
 
 struct View4 {
-  const float* data;
-  long long sb, sc, sh;
+  const void* data;      // element type given by the launch's dtype
+  long long sb, sc, sh;  // strides in elements
 };
 
 struct PeaksParams {
@@ -85,11 +84,57 @@ struct PeaksParams {
   int tier1_units, tier1_planes;
 };
 
-// clamp(sigmoid(x)) bit-identical to ATen's CUDA kernels (UnarySpecialOpsKernel.cu sigmoid:
-// one / (one + std::exp(-a)); clamp: min(max(v, lo), hi)).
-__device__ __forceinline__ float activate(float x) {
-  float s = 1.0f / (1.0f + expf(-x));
-  return fminf(fmaxf(s, kClampLo), kClampHi);
+// Numerics of the score function per input dtype DT (SDNET_DTYPE_*).
+//
+// fp32: S(x) = clamp(1/(1+expf(-x))), bit-identical to ATen's CUDA kernels (UnarySpecialOpsKernel.cu
+// sigmoid: one / (one + std::exp(-a)); TensorCompare.cu clamp: min(max(v, lo), hi)).
+// fp16 / bf16 (what the reference's `--amp` validation feeds the decoder): ATen evaluates both ops in
+// fp32 and rounds each result to the tensor dtype, so S_T(x) = T(clamp(float(T(sigmoid(float(x)))))),
+// returned here as the exactly representable float.  Every S_T is monotone non-decreasing in x.
+//
+// kNear / kHi / kLo say when two different logits x < h might share a score: only if
+// x >= h - kNear with h in [kLo, kHi], or h > kHi and x > kHi - 1, or h < kLo.  Outside that, S(x) <
+// S(h) strictly; verified exhaustively on the device by tests/test_gpu_parity.py for every dtype.
+template <int DT>
+struct Num;
+
+template <>
+struct Num<SDNET_DTYPE_F32> {
+  typedef float In;
+  static constexpr float kNear = 2e-3f, kHi = 8.0f, kLo = -13.0f;
+  static __device__ __forceinline__ float act(float x) {
+    const float s = 1.0f / (1.0f + expf(-x));
+    return fminf(fmaxf(s, kClampLo), kClampHi);
+  }
+  static __device__ __forceinline__ float to_float(float v) { return v; }
+};
+
+template <>
+struct Num<SDNET_DTYPE_F16> {
+  typedef __half In;
+  static constexpr float kNear = 0.02f, kHi = 3.0f, kLo = -11.0f;
+  static __device__ __forceinline__ float act(float x) {
+    const float s = __half2float(__float2half_rn(1.0f / (1.0f + expf(-x))));
+    return __half2float(__float2half_rn(fminf(fmaxf(s, kClampLo), kClampHi)));
+  }
+  static __device__ __forceinline__ float to_float(__half v) { return __half2float(v); }
+};
+
+template <>
+struct Num<SDNET_DTYPE_BF16> {
+  typedef __nv_bfloat16 In;
+  static constexpr float kNear = 0.1f, kHi = 2.0f, kLo = -13.0f;
+  static __device__ __forceinline__ float act(float x) {
+    const float s = __bfloat162float(__float2bfloat16_rn(1.0f / (1.0f + expf(-x))));
+    return __bfloat162float(__float2bfloat16_rn(fminf(fmaxf(s, kClampLo), kClampHi)));
+  }
+  static __device__ __forceinline__ float to_float(__nv_bfloat16 v) { return __bfloat162float(v); }
+};
+
+// element `idx` of a tensor whose dtype is DT, as float (exact)
+template <int DT>
+__device__ __forceinline__ float ld_in(const void* base, long long idx) {
+  return Num<DT>::to_float(__ldg(static_cast<const typename Num<DT>::In*>(base) + idx));
 }
 
 __device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
@@ -198,8 +243,9 @@ struct RowFeed<false> {
     s_own = ring + (4 + 4 * lane) * 4;
     s_halo = ring + (lane == 31 ? 4 + kPanelW : 2) * 4;
   }
-  __device__ __forceinline__ void begin_unit(const float* plane, long long sh, int r0, int H_, int W, int panel_col0,
+  __device__ __forceinline__ void begin_unit(const void* plane_v, long long sh, int r0, int H_, int W, int panel_col0,
                                              int q_last_, int lane) {
+    const float* plane = static_cast<const float*>(plane_v);
     row0 = r0; H = H_; q_last = q_last_;
     const int col0 = panel_col0 + 4 * lane;
     const int halo_col = lane == 31 ? panel_col0 + kPanelW : panel_col0 - 2;
@@ -238,6 +284,82 @@ struct RowFeed<false> {
   __device__ __forceinline__ void wait_step() const { cp_async_wait<kStages - 1 - 2 * R>(); }
   __device__ __forceinline__ void end_unit() { cp_async_wait<0>(); }
 };
+
+// Feed for fp16 / bf16 maps: the ring stays fp32 (so everything downstream is shared with the
+// fp32 path); each lane loads its own four columns (and lanes 0 / 31 the two halo columns) with
+// plain 2-byte loads -- any alignment, any W -- converts, and stores to the ring three steps
+// later, so kDepth rows per warp are in flight in registers.  Same call pattern as RowFeed<false>:
+// issue(q) makes row q - kDepth resident, which is exactly the row step q - 7 needs.
+template <int DT>
+struct RowFeedCvt {
+  typedef typename Num<DT>::In In;
+  static constexpr int kDepth = 3;
+  u32 ring_s, s_own, s_halo, own_ok, halo_ok;
+  const In* gown;
+  const In* ghalo;
+  long long pitch;
+  int row0, H, q_last;
+  float4 own[kDepth];
+  float2 halo[kDepth];
+
+  __device__ __forceinline__ void init(u32 ring, u32, int lane) {
+    ring_s = ring;
+    s_own = ring + (4 + 4 * lane) * 4;
+    s_halo = ring + (lane == 31 ? 4 + kPanelW : 2) * 4;
+  }
+  __device__ __forceinline__ void begin_unit(const void* plane_v, long long sh, int r0, int H_, int W, int panel_col0,
+                                             int q_last_, int lane) {
+    const In* plane = static_cast<const In*>(plane_v);
+    row0 = r0; H = H_; q_last = q_last_;
+    const int col0 = panel_col0 + 4 * lane;
+    const int halo_col = lane == 31 ? panel_col0 + kPanelW : panel_col0 - 2;
+    pitch = sh;
+    gown = plane + (long long)r0 * sh + col0;
+    ghalo = plane + (long long)r0 * sh + halo_col;
+    own_ok = 0;
+    for (int jj = 0; jj < 4; ++jj) own_ok |= (col0 + jj < W ? 1u : 0u) << jj;
+    halo_ok = 0;
+    if (lane == 0 || lane == 31)
+      for (int jj = 0; jj < 2; ++jj) halo_ok |= ((halo_col + jj >= 0 && halo_col + jj < W) ? 1u : 0u) << jj;
+    for (int i = lane; i < kStages * kPitch / 4; i += 32) sts128(ring_s + 16 * i, -CUDART_INF_F);
+    __syncwarp();
+  }
+  __device__ __forceinline__ u32 slot_addr(int q) const { return ring_s + (q & (kStages - 1)) * kPitchB; }
+  __device__ __forceinline__ void issue(int q, int lane) {
+    const float ninf = -CUDART_INF_F;
+    if (q >= kDepth && q - kDepth <= q_last) {  // retire the oldest register stage into the ring
+      const u32 slot = (u32)(q - kDepth) & (kStages - 1);
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(s_own + slot * kPitchB), "f"(own[0].x), "f"(own[0].y),
+                   "f"(own[0].z), "f"(own[0].w) : "memory");
+      if (lane == 0 || lane == 31)
+        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(s_halo + slot * kPitchB), "f"(halo[0].x), "f"(halo[0].y) : "memory");
+    }
+#pragma unroll
+    for (int d = 0; d + 1 < kDepth; ++d) { own[d] = own[d + 1]; halo[d] = halo[d + 1]; }
+    float4 v = make_float4(ninf, ninf, ninf, ninf);
+    float2 hv = make_float2(ninf, ninf);
+    if (q <= q_last && (unsigned)(row0 + q) < (unsigned)H) {
+      if (own_ok & 1u) v.x = Num<DT>::to_float(__ldg(gown + 0));
+      if (own_ok & 2u) v.y = Num<DT>::to_float(__ldg(gown + 1));
+      if (own_ok & 4u) v.z = Num<DT>::to_float(__ldg(gown + 2));
+      if (own_ok & 8u) v.w = Num<DT>::to_float(__ldg(gown + 3));
+      if (halo_ok & 1u) hv.x = Num<DT>::to_float(__ldg(ghalo + 0));
+      if (halo_ok & 2u) hv.y = Num<DT>::to_float(__ldg(ghalo + 1));
+    }
+    own[kDepth - 1] = v;
+    halo[kDepth - 1] = hv;
+    gown += pitch;
+    ghalo += pitch;
+  }
+  template <int R>
+  __device__ __forceinline__ void wait_step() const {}
+  __device__ __forceinline__ void end_unit() {}
+};
+
+template <int DT>
+struct FeedFor { typedef RowFeedCvt<DT> type; };
+template <>
+struct FeedFor<SDNET_DTYPE_F32> { typedef RowFeed<false> type; };
 
 __device__ __forceinline__ int logit_bin(float x) {
   int bin = __float2int_rd((x - kBinLo) * kBinScale);
@@ -348,14 +470,15 @@ __device__ __forceinline__ int floor_bin_fine(const u32* hist, int lane, int K) 
 // Floor shared between warps working on the same plane (CTA-wide in shared memory, plane-wide in
 // global memory).  Unlike the warp-local floor (which may drop equal scores because everything
 // it counted has a lower index), a shared floor needs a strict score gap: a pixel is dropped
-// only if its logit is below edge(b) - kNearTie with edge(b) in [kLoZone, kHiZone], where
-// S(x - kNearTie) < S(x) is verified exhaustively (tests/test_gpu_parity.py).
+// only if its logit is below edge(b) - kNear with edge(b) in [kLo, kHi] (Num<DT>), where
+// S(x - kNear) < S(x) is verified exhaustively (tests/test_gpu_parity.py).
+template <int DT = SDNET_DTYPE_F32>
 __device__ __forceinline__ float shared_floor(int fbin, float xscale) {
   if (fbin <= 0) return -CUDART_INF_F;
   const float edge = kBinLo + (float)fbin * (1.0f / kFineScale);
   if (xscale != 1.0f) return edge / xscale;  // pre-activated: keys are strictly monotone in the value
-  if (edge < kLoZone || edge > kHiZone) return -CUDART_INF_F;
-  return edge - kNearTie;
+  if (edge < Num<DT>::kLo || edge > Num<DT>::kHi) return -CUDART_INF_F;
+  return edge - Num<DT>::kNear;
 }
 
 // Where a warp publishes / picks up shared floors.
@@ -375,6 +498,7 @@ struct UnitState {
   int nbuf;       // records waiting in the shared-memory buffer
 };
 
+template <int DT = SDNET_DTYPE_F32>
 __device__ __forceinline__ void flush_candidates(UnitState& st, const u64* buf, u32* hist, int* minx,
                                                  const SharedFloors& sf, int* count_ptr, u64* __restrict__ list,
                                                  int cap, int K, int lane, bool pre, float xscale, float satx) {
@@ -394,7 +518,7 @@ __device__ __forceinline__ void flush_candidates(UnitState& st, const u64* buf, 
         const u32 bits = __float_as_uint(x);
         key = (bits & 0x80000000u) ? ~bits : (bits | 0x80000000u);
       } else {
-        key = __float_as_uint(activate(x));
+        key = __float_as_uint(Num<DT>::act(x));
       }
       if (valid) {
         if (base + i < cap) list[base + i] = ((u64)key << 32) | (u32)rec;
@@ -419,7 +543,7 @@ __device__ __forceinline__ void flush_candidates(UnitState& st, const u64* buf, 
     const int b = floor_bin_fine<true>(sf.cta_hist, lane, K);
     if (b > 0) {
       if (lane == 0) atomicMax(sf.cta_floor, b);
-      st.floorx = fmaxf(st.floorx, shared_floor(b, xscale));
+      st.floorx = fmaxf(st.floorx, shared_floor<DT>(b, xscale));
     }
   }
   if (sf.ghist) {
@@ -429,7 +553,7 @@ __device__ __forceinline__ void flush_candidates(UnitState& st, const u64* buf, 
         atomicMax(sf.gfloor, gb);
         if (sf.cta_floor) atomicMax(sf.cta_floor, gb);
       }
-      st.floorx = fmaxf(st.floorx, shared_floor(gb, xscale));
+      st.floorx = fmaxf(st.floorx, shared_floor<DT>(gb, xscale));
     }
   }
   // a floor at the saturation clamp means "nothing can beat what we have": every x >= satx has
@@ -441,8 +565,9 @@ __device__ __forceinline__ void flush_candidates(UnitState& st, const u64* buf, 
 //   x == h            -> certainly survives;
 //   x <  h but so close that the two scores may round equal -> settled with the exact score.
 // Columns outside the image hold -inf and never pass x > floorx.
-template <int R>
+template <int R, int DT = SDNET_DTYPE_F32>
 __device__ __forceinline__ u32 classify_row(const float4 ctr, float h0, float h1, float h2, float h3, float floorx) {
+  constexpr float kNearTie = Num<DT>::kNear, kHiZone = Num<DT>::kHi, kLoZone = Num<DT>::kLo;
   u32 cmask = 0, amb = 0;
 #define SDNET_CLASSIFY(x, h, j)                                                                        \
   if ((x) > floorx) {                                                                                  \
@@ -461,7 +586,7 @@ __device__ __forceinline__ u32 classify_row(const float4 ctr, float h0, float h1
     const int jj = has ? __ffs(amb) - 1 : 0;
     const float x = jj == 0 ? ctr.x : (jj == 1 ? ctr.y : (jj == 2 ? ctr.z : ctr.w));
     const float h = jj == 0 ? h0 : (jj == 1 ? h1 : (jj == 2 ? h2 : h3));
-    if (has && activate(x) == activate(h)) cmask |= 1u << jj;
+    if (has && Num<DT>::act(x) == Num<DT>::act(h)) cmask |= 1u << jj;
     amb &= amb - 1;
   }
   return cmask;
@@ -470,6 +595,7 @@ __device__ __forceinline__ u32 classify_row(const float4 ctr, float h0, float h1
 // Append the selected pixels of one row as (logit, index) records to the warp's buffer.
 // Common case (<= 32 records in the row): positions from three back-to-back ballots on the bits
 // of each lane's record count, no branches.  Rows with more (plateaus) go column by column.
+template <int DT = SDNET_DTYPE_F32>
 __device__ __forceinline__ void append_row(UnitState& st, u32 cmask, const float4 ctr, u32 idx0, u64* buf, u32* hist,
                                            int* minx, const SharedFloors& sf, int* count_ptr,
                                            u64* __restrict__ list, int cap, int K, int lane, bool pre, float xscale,
@@ -484,7 +610,7 @@ __device__ __forceinline__ void append_row(UnitState& st, u32 cmask, const float
   if (total <= 32) {
     if (st.nbuf + (int)total > kBuf) {
       __syncwarp();
-      flush_candidates(st, buf, hist, minx, sf, count_ptr, list, cap, K, lane, pre, xscale, satx);
+      flush_candidates<DT>(st, buf, hist, minx, sf, count_ptr, list, cap, K, lane, pre, xscale, satx);
     }
     int pos = st.nbuf + __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt);
     if (cmask & 1u) buf[pos++] = ((u64)__float_as_uint(ctr.x) << 32) | (idx0 + 0);
@@ -501,7 +627,7 @@ __device__ __forceinline__ void append_row(UnitState& st, u32 cmask, const float
     if (m) {  // warp-uniform
       if (st.nbuf > kBuf - 32) {
         __syncwarp();
-        flush_candidates(st, buf, hist, minx, sf, count_ptr, list, cap, K, lane, pre, xscale, satx);
+        flush_candidates<DT>(st, buf, hist, minx, sf, count_ptr, list, cap, K, lane, pre, xscale, satx);
       }
       if (mine) buf[st.nbuf + __popc(m & lt)] = ((u64)__float_as_uint(comp(ctr, jj)) << 32) | (idx0 + jj);
       st.nbuf += __popc(m);
@@ -509,8 +635,9 @@ __device__ __forceinline__ void append_row(UnitState& st, u32 cmask, const float
   }
 }
 
-template <bool kAligned, int R>
-__global__ void __launch_bounds__(kThreads, 4) sdnet_peaks_kernel(const __grid_constant__ PeaksParams p) {
+template <bool kAligned, int R, int DT>
+__global__ void __launch_bounds__(kThreads, DT == SDNET_DTYPE_F32 ? 4 : 3)
+sdnet_peaks_kernel(const __grid_constant__ PeaksParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -527,7 +654,7 @@ __global__ void __launch_bounds__(kThreads, 4) sdnet_peaks_kernel(const __grid_c
   const int H = p.H, W = p.W;
   const u32 own_off = (4 + 4 * lane) * 4;                      // this lane's four columns inside a ring row
   const u32 halo_off = (lane == 31 ? 4 + kPanelW : 2) * 4;     // the two columns beyond the panel edge
-  RowFeed<false> feed;
+  typename FeedFor<DT>::type feed;
   feed.init(ring_s, bars_s, lane);
 
   for (;;) {
@@ -542,7 +669,8 @@ __global__ void __launch_bounds__(kThreads, 4) sdnet_peaks_kernel(const __grid_c
     const int b = plane_id / C, c = plane_id % C;
     const bool is_anchor = c < p.M;
     const View4& vw = is_anchor ? p.anchor : p.part;
-    const float* __restrict__ plane = vw.data + (long long)b * vw.sb + (long long)(is_anchor ? c : c - p.M) * vw.sc;
+    const void* plane = static_cast<const typename Num<DT>::In*>(vw.data) + (long long)b * vw.sb +
+                        (long long)(is_anchor ? c : c - p.M) * vw.sc;
     const int K = is_anchor ? p.K : p.P;
     const int panel_col0 = panel * kPanelW;
     const int col0 = panel_col0 + lane * 4;
@@ -559,7 +687,7 @@ __global__ void __launch_bounds__(kThreads, 4) sdnet_peaks_kernel(const __grid_c
     sf.gfloor = gfloor_ptr;
 
     UnitState st;
-    st.floorx = shared_floor(__ldcg(gfloor_ptr), xscale);
+    st.floorx = shared_floor<DT>(__ldcg(gfloor_ptr), xscale);
     st.emitted = 0;
     st.nbuf = 0;
 
@@ -611,7 +739,7 @@ __global__ void __launch_bounds__(kThreads, 4) sdnet_peaks_kernel(const __grid_c
             h2 = max3(v.y, v.z, v.w);
             h3 = max3(v.z, v.w, R0);
           }
-          cmask = classify_row<R>(ctr, h0, h1, h2, h3, floorx);
+          cmask = classify_row<R, DT>(ctr, h0, h1, h2, h3, floorx);
         } else {
           // pre-activated maps (CoreMLDecoder): every pixel above the floor is a candidate
           if (ctr.x > floorx) cmask |= 1u;
@@ -619,18 +747,18 @@ __global__ void __launch_bounds__(kThreads, 4) sdnet_peaks_kernel(const __grid_c
           if (ctr.z > floorx) cmask |= 4u;
           if (ctr.w > floorx) cmask |= 8u;
         }
-        append_row(st, cmask, ctr, (u32)((r_begin + t) * W + col0), buf, hist, minx, sf, count_ptr, list,
+        append_row<DT>(st, cmask, ctr, (u32)((r_begin + t) * W + col0), buf, hist, minx, sf, count_ptr, list,
                    p.cap, K, lane, pre, xscale, satx);
       }
       if ((t & 7) == 7) {
         // every 8 rows: pick up the plane-wide floor other warps may have raised
-        st.floorx = fmaxf(st.floorx, shared_floor(__ldcg(gfloor_ptr), xscale));
+        st.floorx = fmaxf(st.floorx, shared_floor<DT>(__ldcg(gfloor_ptr), xscale));
       }
     }
     feed.end_unit();
     if (st.nbuf) {
       __syncwarp();
-      flush_candidates(st, buf, hist, minx, sf, count_ptr, list, p.cap, K, lane, pre, xscale, satx);
+      flush_candidates<DT>(st, buf, hist, minx, sf, count_ptr, list, p.cap, K, lane, pre, xscale, satx);
     }
   }
 }
@@ -757,7 +885,7 @@ __global__ void __launch_bounds__((kMaxConsumers + 1) * 32, 3) sdnet_peaks_cta_k
       const int b = plane_id / C, c = plane_id % C;
       const bool is_anchor = c < p.M;
       const View4& vw = is_anchor ? p.anchor : p.part;
-      const float* plane = vw.data + (long long)b * vw.sb + (long long)(is_anchor ? c : c - p.M) * vw.sc;
+      const float* plane = static_cast<const float*>(vw.data) + (long long)b * vw.sb + (long long)(is_anchor ? c : c - p.M) * vw.sc;
       const int r_begin = strip * p.rows_per_strip;
       const int r_end = min(H, r_begin + p.rows_per_strip);
       const int q_count = r_end - r_begin + 2 * R;  // ring rows of this unit: image rows r_begin-R .. r_end-1+R
@@ -1162,9 +1290,9 @@ struct ExactParams {
   int* flags;
 };
 
-__device__ __forceinline__ u32 exact_key(const float* __restrict__ plane, long long sh, int H, int W, int R, int y,
-                                         int x, bool pre) {
-  const float v = __ldg(plane + (long long)y * sh + x);
+template <int DT>
+__device__ __forceinline__ u32 exact_key(const void* plane, long long sh, int H, int W, int R, int y, int x, bool pre) {
+  const float v = ld_in<DT>(plane, (long long)y * sh + x);
   if (pre) {
     const u32 bits = __float_as_uint(v);
     return (bits & 0x80000000u) ? ~bits : (bits | 0x80000000u);
@@ -1173,15 +1301,25 @@ __device__ __forceinline__ u32 exact_key(const float* __restrict__ plane, long l
   for (int dy = -R; dy <= R; ++dy) {
     const int yy = y + dy;
     if (yy < 0 || yy >= H) continue;
-    const float* rp = plane + (long long)yy * sh;
     for (int dx = -R; dx <= R; ++dx) {
       const int xx = x + dx;
-      if (xx >= 0 && xx < W) h = fmaxf(h, __ldg(rp + xx));
+      if (xx >= 0 && xx < W) h = fmaxf(h, ld_in<DT>(plane, (long long)yy * sh + xx));
     }
   }
-  const float sv = activate(v);
-  const bool peak = (v == h) || (sv == activate(h));
+  const float sv = Num<DT>::act(v);
+  const bool peak = (v == h) || (sv == Num<DT>::act(h));
   return peak ? __float_as_uint(sv) : 0u;
+}
+
+// key of a pixel already known to survive NMS
+template <int DT>
+__device__ __forceinline__ u32 survivor_key(const void* plane, long long idx, bool pre) {
+  const float v = ld_in<DT>(plane, idx);
+  if (pre) {
+    const u32 bits = __float_as_uint(v);
+    return (bits & 0x80000000u) ? ~bits : (bits | 0x80000000u);
+  }
+  return __float_as_uint(Num<DT>::act(v));
 }
 
 // digit (from the top) at which the cumulative count reaches `need`; bins = 2048
@@ -1218,6 +1356,7 @@ __device__ void pick_digit(const u32* s_hist, int nbins, int need, int* s_out) {
   __syncthreads();
 }
 
+template <int DT>
 __global__ void __launch_bounds__(kExactThreads) sdnet_exact_select_kernel(const __grid_constant__ ExactParams p) {
   __shared__ u32 s_hist[2048];
   __shared__ int s_out[2];
@@ -1241,7 +1380,8 @@ __global__ void __launch_bounds__(kExactThreads) sdnet_exact_select_kernel(const
   const int b = plane_id / C, c = plane_id % C;
   const bool is_anchor = c < p.M;
   const View4& vw = is_anchor ? p.anchor : p.part;
-  const float* __restrict__ plane = vw.data + (long long)b * vw.sb + (long long)(is_anchor ? c : c - p.M) * vw.sc;
+  const void* plane = static_cast<const typename Num<DT>::In*>(vw.data) + (long long)b * vw.sb +
+                      (long long)(is_anchor ? c : c - p.M) * vw.sc;
   const long long sh = vw.sh;
   const int K = is_anchor ? p.K : p.P;
   const int H = p.H, W = p.W, HW = H * W, R = p.radius;
@@ -1259,7 +1399,7 @@ __global__ void __launch_bounds__(kExactThreads) sdnet_exact_select_kernel(const
   for (int base = 0; base < words * 32; base += blockDim.x) {
     const int i = base + tid;
     u32 key = 0;
-    if (i < HW) key = exact_key(plane, sh, H, W, R, i / W, i % W, pre);
+    if (i < HW) key = exact_key<DT>(plane, sh, H, W, R, i / W, i % W, pre);
     const u32 m = __ballot_sync(0xffffffffu, key != 0);
     if ((tid & 31) == 0 && (i >> 5) < words) bitmap[i >> 5] = m;
     if (key) atomicAdd(&s_hist[key >> 21], 1u);
@@ -1280,9 +1420,7 @@ __global__ void __launch_bounds__(kExactThreads) sdnet_exact_select_kernel(const
     __syncthreads();
     for (int i = tid; i < HW; i += blockDim.x) {
       if (!((bitmap[i >> 5] >> (i & 31)) & 1u)) continue;
-      const float v = __ldg(plane + (long long)(i / W) * sh + (i % W));
-      const u32 key = pre ? ((__float_as_uint(v) & 0x80000000u) ? ~__float_as_uint(v) : (__float_as_uint(v) | 0x80000000u))
-                          : __float_as_uint(activate(v));
+      const u32 key = survivor_key<DT>(plane, (long long)(i / W) * sh + (i % W), pre);
       if ((key >> 21) == prefix) atomicAdd(&s_hist[(key >> 10) & 0x7ffu], 1u);
     }
     __syncthreads();
@@ -1295,9 +1433,7 @@ __global__ void __launch_bounds__(kExactThreads) sdnet_exact_select_kernel(const
     __syncthreads();
     for (int i = tid; i < HW; i += blockDim.x) {
       if (!((bitmap[i >> 5] >> (i & 31)) & 1u)) continue;
-      const float v = __ldg(plane + (long long)(i / W) * sh + (i % W));
-      const u32 key = pre ? ((__float_as_uint(v) & 0x80000000u) ? ~__float_as_uint(v) : (__float_as_uint(v) | 0x80000000u))
-                          : __float_as_uint(activate(v));
+      const u32 key = survivor_key<DT>(plane, (long long)(i / W) * sh + (i % W), pre);
       if ((key >> 10) == prefix) atomicAdd(&s_hist[key & 0x3ffu], 1u);
     }
     __syncthreads();
@@ -1314,9 +1450,7 @@ __global__ void __launch_bounds__(kExactThreads) sdnet_exact_select_kernel(const
     const int i = base + tid;
     u32 key = 0;
     if (i < HW && ((bitmap[i >> 5] >> (i & 31)) & 1u)) {
-      const float v = __ldg(plane + (long long)(i / W) * sh + (i % W));
-      key = pre ? ((__float_as_uint(v) & 0x80000000u) ? ~__float_as_uint(v) : (__float_as_uint(v) | 0x80000000u))
-                : __float_as_uint(activate(v));
+      key = survivor_key<DT>(plane, (long long)(i / W) * sh + (i % W), pre);
     }
     const bool gt = key != 0 && (all || key > thresh);
     const bool eq = key != 0 && !all && key == thresh;
@@ -1552,6 +1686,7 @@ __device__ __forceinline__ float key_to_score(u32 key, bool pre) {
   return __uint_as_float(bits);
 }
 
+template <int DT>
 __global__ void __launch_bounds__(2 * kTeamThreads) sdnet_tail_kernel(const __grid_constant__ TailParams p) {
   __shared__ u64 s_sel[2][kSortN];
   __shared__ u32 s_hist[2][256];
@@ -1567,8 +1702,9 @@ __global__ void __launch_bounds__(2 * kTeamThreads) sdnet_tail_kernel(const __gr
   if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
   pdl_wait();  // candidate lists (peaks kernel, possibly rewritten by the exact select) are final
   __syncthreads();
-  const float* offx = p.offsets.data + (long long)b * p.offsets.sb;
-  const float* offy = offx + p.offsets.sc;
+  typedef typename Num<DT>::In In;
+  const In* offx = static_cast<const In*>(p.offsets.data) + (long long)b * p.offsets.sb;
+  const In* offy = offx + p.offsets.sc;
   const long long osh = p.offsets.sh;
   u64* sel = s_sel[tm.id];
 
@@ -1583,8 +1719,8 @@ __global__ void __launch_bounds__(2 * kTeamThreads) sdnet_tail_kernel(const __gr
       const u32 idx = 0xFFFFFFu - (u32)(v & 0xFFFFFFu);
       const int yy = idx / W, xx = idx - yy * W;
       const float score = key_to_score((u32)(v >> 32), pre);
-      const float x = __fadd_rn((float)xx, __ldg(offx + (long long)yy * osh + xx));
-      const float y = __fadd_rn((float)yy, __ldg(offy + (long long)yy * osh + xx));
+      const float x = __fadd_rn((float)xx, Num<DT>::to_float(__ldg(offx + (long long)yy * osh + xx)));
+      const float y = __fadd_rn((float)yy, Num<DT>::to_float(__ldg(offy + (long long)yy * osh + xx)));
       store_out(p, reinterpret_cast<float4*>(p.anchor_out) + (size_t)b * p.K + s, make_float4(x, y, score, (float)cls));
       store_out(p, p.anchor_inds + (size_t)b * p.K + s, (long long)idx);
       const bool valid = score > p.conf;
@@ -1598,8 +1734,8 @@ __global__ void __launch_bounds__(2 * kTeamThreads) sdnet_tail_kernel(const __gr
     // ---- parts
     const int have = select_group(tm, p, b, p.M, p.N, p.P, sel, s_hist[1], s_misc[1]);
     if (have < p.P) zero_fill(tm, p, b, p.M, have, p.P, sel, s_hist[1]);
-    const float* embx = p.embeddings.data ? p.embeddings.data + (long long)b * p.embeddings.sb : nullptr;
-    const float* emby = embx ? embx + p.embeddings.sc : nullptr;
+    const In* embx = p.embeddings.data ? static_cast<const In*>(p.embeddings.data) + (long long)b * p.embeddings.sb : nullptr;
+    const In* emby = embx ? embx + p.embeddings.sc : nullptr;
     const long long esh = p.embeddings.sh;
     int n_valid = 0;
     for (int s = tm.tid; s < p.P; s += kTeamThreads) {
@@ -1608,12 +1744,12 @@ __global__ void __launch_bounds__(2 * kTeamThreads) sdnet_tail_kernel(const __gr
       const u32 idx = 0xFFFFFFu - (u32)(v & 0xFFFFFFu);
       const int yy = idx / W, xx = idx - yy * W;
       const float score = key_to_score((u32)(v >> 32), pre);
-      const float x = __fadd_rn((float)xx, __ldg(offx + (long long)yy * osh + xx));
-      const float y = __fadd_rn((float)yy, __ldg(offy + (long long)yy * osh + xx));
+      const float x = __fadd_rn((float)xx, Num<DT>::to_float(__ldg(offx + (long long)yy * osh + xx)));
+      const float y = __fadd_rn((float)yy, Num<DT>::to_float(__ldg(offy + (long long)yy * osh + xx)));
       float ex = 0.f, ey = 0.f;
       if (embx) {
-        ex = __ldg(embx + (long long)yy * esh + xx);
-        ey = __ldg(emby + (long long)yy * esh + xx);
+        ex = Num<DT>::to_float(__ldg(embx + (long long)yy * esh + xx));
+        ey = Num<DT>::to_float(__ldg(emby + (long long)yy * esh + xx));
       }
       const float ox = __fadd_rn(x, ex), oy = __fadd_rn(y, ey);
       float2* po = reinterpret_cast<float2*>(p.part_out + ((size_t)b * p.P + s) * 6);
@@ -1663,6 +1799,7 @@ __global__ void __launch_bounds__(2 * kTeamThreads) sdnet_tail_kernel(const __gr
 // ---------------------------------------------------------------------------------------------
 // metadata: clamped-sigmoid maps
 // ---------------------------------------------------------------------------------------------
+template <int DT>
 __global__ void sdnet_activate_kernel(View4 in, int C, int H, int W, size_t total, float* __restrict__ out) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int x = (int)(i % W);
@@ -1671,7 +1808,7 @@ __global__ void sdnet_activate_kernel(View4 in, int C, int H, int W, size_t tota
     t /= H;
     const int c = (int)(t % C);
     const long long b = (long long)(t / C);
-    out[i] = activate(__ldg(in.data + b * in.sb + (long long)c * in.sc + (long long)y * in.sh + x));
+    out[i] = Num<DT>::act(ld_in<DT>(in.data, b * in.sb + (long long)c * in.sc + (long long)y * in.sh + x));
   }
 }
 
@@ -1714,7 +1851,7 @@ int device_sm_count() {
 int validate(const SdnetDecodeParams* p) {
   if (!p) return SDNET_E_NULL;
   if (p->struct_size != sizeof(SdnetDecodeParams)) return SDNET_E_STRUCT;
-  if (p->dtype != SDNET_DTYPE_F32) return SDNET_E_DTYPE;
+  if (p->dtype != SDNET_DTYPE_F32 && p->dtype != SDNET_DTYPE_F16 && p->dtype != SDNET_DTYPE_BF16) return SDNET_E_DTYPE;
   if (p->B <= 0 || p->M <= 0 || p->N <= 0 || p->H <= 0 || p->W <= 0 || p->K <= 0 || p->P <= 0) return SDNET_E_SHAPE;
   const long long hw = (long long)p->H * p->W;
   if (hw >= (1ll << 24) || p->K > hw || p->P > hw) return SDNET_E_SHAPE;
@@ -1734,7 +1871,7 @@ int validate(const SdnetDecodeParams* p) {
 
 View4 to_view(const SdnetTensor4& t) {
   View4 v;
-  v.data = static_cast<const float*>(t.data);
+  v.data = t.data;
   v.sb = t.stride_b; v.sc = t.stride_c; v.sh = t.stride_h;
   return v;
 }
@@ -1833,12 +1970,13 @@ int launch_decode(const SdnetDecodeParams* p, cudaStream_t stream, cudaEvent_t* 
     return e[0] == 't' ? 1 : (e[0] == 'c' ? 2 : (e[0] == 'w' ? 3 : 0));
   }();
   CUtensorMap tm_anchor, tm_part;
-  bool use_tile = aligned && !(p->flags & SDNET_FLAG_WARP_KERNEL) && path_override != 2 && path_override != 3 &&
+  const bool is_f32 = p->dtype == SDNET_DTYPE_F32;  // the TMA kernels are fp32-only; fp16/bf16 take the converting feed
+  bool use_tile = is_f32 && aligned && !(p->flags & SDNET_FLAG_WARP_KERNEL) && path_override != 2 && path_override != 3 &&
                   (long long)p->anchor_hm.stride_h * 4 >= (long long)p->W * 4;
   if (use_tile)
     use_tile = make_tile_map(&tm_anchor, p->anchor_hm, p->B, p->M, p->H, p->W) &&
                make_tile_map(&tm_part, p->part_hm, p->B, p->N, p->H, p->W);
-  const bool use_cta = !use_tile && aligned && p->W <= kPanelW * kMaxConsumers && !(p->flags & SDNET_FLAG_WARP_KERNEL) &&
+  const bool use_cta = is_f32 && !use_tile && aligned && p->W <= kPanelW * kMaxConsumers && !(p->flags & SDNET_FLAG_WARP_KERNEL) &&
                        path_override != 3;
   static const int tier2_strips = [] {  // tuning knob, read once: SDNET_TIER2_STRIPS = n (default 2)
     const char* e = getenv("SDNET_TIER2_STRIPS");
@@ -1942,12 +2080,16 @@ int launch_decode(const SdnetDecodeParams* p, cudaStream_t stream, cudaEvent_t* 
     long long ctas = ((long long)pp.units + kWarps - 1) / kWarps;
     if (ctas > (long long)sms * kPeaksCtasPerSm) ctas = (long long)sms * kPeaksCtasPerSm;
     dim3 grid((unsigned)ctas), block(kThreads);
-    if (p->radius == 2) {
-      if (aligned) launch_peaks(sdnet_peaks_kernel<true, 2>, grid, block, stream, pp);
-      else launch_peaks(sdnet_peaks_kernel<false, 2>, grid, block, stream, pp);
+    const bool r2 = p->radius == 2;
+    if (p->dtype == SDNET_DTYPE_F16) {
+      if (r2) launch_peaks(sdnet_peaks_kernel<false, 2, SDNET_DTYPE_F16>, grid, block, stream, pp);
+      else launch_peaks(sdnet_peaks_kernel<false, 1, SDNET_DTYPE_F16>, grid, block, stream, pp);
+    } else if (p->dtype == SDNET_DTYPE_BF16) {
+      if (r2) launch_peaks(sdnet_peaks_kernel<false, 2, SDNET_DTYPE_BF16>, grid, block, stream, pp);
+      else launch_peaks(sdnet_peaks_kernel<false, 1, SDNET_DTYPE_BF16>, grid, block, stream, pp);
     } else {
-      if (aligned) launch_peaks(sdnet_peaks_kernel<true, 1>, grid, block, stream, pp);
-      else launch_peaks(sdnet_peaks_kernel<false, 1>, grid, block, stream, pp);
+      if (r2) launch_peaks(sdnet_peaks_kernel<false, 2, SDNET_DTYPE_F32>, grid, block, stream, pp);
+      else launch_peaks(sdnet_peaks_kernel<false, 1, SDNET_DTYPE_F32>, grid, block, stream, pp);
     }
   }
   err = cudaGetLastError();
@@ -1965,7 +2107,9 @@ int launch_decode(const SdnetDecodeParams* p, cudaStream_t stream, cudaEvent_t* 
     ep.flags = reinterpret_cast<int*>(base + ws.off_flags);
     {
       const size_t exact_grid = planes < (size_t)sms * 2 ? planes : (size_t)sms * 2;
-      launch_pdl(sdnet_exact_select_kernel, dim3((unsigned)exact_grid), dim3(kExactThreads), stream, ep);
+      if (p->dtype == SDNET_DTYPE_F16) launch_pdl(sdnet_exact_select_kernel<SDNET_DTYPE_F16>, dim3((unsigned)exact_grid), dim3(kExactThreads), stream, ep);
+      else if (p->dtype == SDNET_DTYPE_BF16) launch_pdl(sdnet_exact_select_kernel<SDNET_DTYPE_BF16>, dim3((unsigned)exact_grid), dim3(kExactThreads), stream, ep);
+      else launch_pdl(sdnet_exact_select_kernel<SDNET_DTYPE_F32>, dim3((unsigned)exact_grid), dim3(kExactThreads), stream, ep);
     }
     err = cudaGetLastError();
     if (err != cudaSuccess) return (int)err;
@@ -1994,7 +2138,9 @@ int launch_decode(const SdnetDecodeParams* p, cudaStream_t stream, cudaEvent_t* 
   tp.exact_flags = reinterpret_cast<const int*>(base + ws.off_flags);
   tp.n_dest = p->n_dest;
   for (int j = 0; j < SDNET_MAX_DEST; ++j) tp.dest_delta[j] = j < p->n_dest ? p->dest_delta[j] : 0;
-  launch_pdl(sdnet_tail_kernel, dim3((unsigned)p->B), dim3(2 * kTeamThreads), stream, tp);
+  if (p->dtype == SDNET_DTYPE_F16) launch_pdl(sdnet_tail_kernel<SDNET_DTYPE_F16>, dim3((unsigned)p->B), dim3(2 * kTeamThreads), stream, tp);
+  else if (p->dtype == SDNET_DTYPE_BF16) launch_pdl(sdnet_tail_kernel<SDNET_DTYPE_BF16>, dim3((unsigned)p->B), dim3(2 * kTeamThreads), stream, tp);
+  else launch_pdl(sdnet_tail_kernel<SDNET_DTYPE_F32>, dim3((unsigned)p->B), dim3(2 * kTeamThreads), stream, tp);
   err = cudaGetLastError();
   if (marks) cudaEventRecord(marks[3], stream);
   return (int)err;
@@ -2022,7 +2168,7 @@ const char* sdnet_error_string(int code) {
 
 int sdnet_decode_workspace_bytes(int B, int M, int N, int H, int W, int K, int P, int dtype, size_t* out_bytes) {
   if (!out_bytes) return SDNET_E_NULL;
-  if (dtype != SDNET_DTYPE_F32) return SDNET_E_DTYPE;
+  if (dtype != SDNET_DTYPE_F32 && dtype != SDNET_DTYPE_F16 && dtype != SDNET_DTYPE_BF16) return SDNET_E_DTYPE;
   if (B <= 0 || M <= 0 || N <= 0 || H <= 0 || W <= 0 || K <= 0 || P <= 0) return SDNET_E_SHAPE;
   if ((long long)H * W >= (1ll << 24)) return SDNET_E_SHAPE;
   *out_bytes = plan_workspace(B, M, N, H, W, K, P).total;
@@ -2060,15 +2206,17 @@ int sdnet_decode_launch_timed(const SdnetDecodeParams* params, void* stream_v, f
 
 int sdnet_activate_launch(const SdnetTensor4* in, int dtype, int B, int C, int H, int W, float* out, void* stream) {
   if (!in || !in->data || !out) return SDNET_E_NULL;
-  if (dtype != SDNET_DTYPE_F32) return SDNET_E_DTYPE;
+  if (dtype != SDNET_DTYPE_F32 && dtype != SDNET_DTYPE_F16 && dtype != SDNET_DTYPE_BF16) return SDNET_E_DTYPE;
   if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return SDNET_E_SHAPE;
   if (in->stride_w != 1) return SDNET_E_STRIDE;
   const size_t total = (size_t)B * C * H * W;
   const int sms = device_sm_count();
   size_t blocks = (total + 255) / 256;
   if (blocks > (size_t)sms * 8) blocks = (size_t)sms * 8;
-  sdnet_activate_kernel<<<dim3((unsigned)blocks), dim3(256), 0, static_cast<cudaStream_t>(stream)>>>(
-      to_view(*in), C, H, W, total, out);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == SDNET_DTYPE_F16) sdnet_activate_kernel<SDNET_DTYPE_F16><<<dim3((unsigned)blocks), dim3(256), 0, st>>>(to_view(*in), C, H, W, total, out);
+  else if (dtype == SDNET_DTYPE_BF16) sdnet_activate_kernel<SDNET_DTYPE_BF16><<<dim3((unsigned)blocks), dim3(256), 0, st>>>(to_view(*in), C, H, W, total, out);
+  else sdnet_activate_kernel<SDNET_DTYPE_F32><<<dim3((unsigned)blocks), dim3(256), 0, st>>>(to_view(*in), C, H, W, total, out);
   return (int)cudaGetLastError();
 }
 
@@ -2076,6 +2224,7 @@ int sdnet_decode_host_launch(const SdnetDecodeParams* params, void* staging, siz
   const int rc = validate(params);
   if (rc) return rc;
   if (!staging) return SDNET_E_NULL;
+  if (params->dtype != SDNET_DTYPE_F32) return SDNET_E_DTYPE;  // host-buffer entry point: fp32 only for now
   const SdnetDecodeParams& p = *params;
   const size_t plane_bytes = (size_t)p.H * p.W * sizeof(float);
   const size_t need = (size_t)p.B * (p.M + p.N) * plane_bytes;

@@ -68,9 +68,10 @@ class Decoder(_DecoderBase):
         a, p = packed.anchor_out, packed.part_out
         # the reference re-binds the score tensors to their masked (-1) versions before
         # returning them (decoders.py:79,84 then 166-173): kept, oddity included
-        conf32 = torch.tensor(conf_thresh, dtype=torch.float32, device=a.device)
+        in_dtype = outputs["anchor_hm"].dtype
+        conf32 = torch.tensor(conf_thresh, dtype=in_dtype, device=a.device).float()  # compared in the scores' dtype
         mask = lambda s: torch.where(s > conf32, s, torch.full_like(s, -1.0))
-        meta["embeddings"] = packed.part_emb
+        meta["embeddings"] = packed.part_emb if in_dtype == torch.float32 else packed.part_emb.to(in_dtype)
         meta["topk_anchor"] = (mask(a[..., 2]), packed.anchor_inds, a[..., 3], a[..., 1], a[..., 0])
         meta["topk_kp"] = (mask(p[..., 2]), packed.part_inds, p[..., 3], p[..., 1], p[..., 0])
         meta["raw_parts"] = self._raw_parts(host, conf_thresh, out_size, in_size)

@@ -35,12 +35,17 @@ def _view4(t: torch.Tensor) -> SdnetTensor4:
     return SdnetTensor4(t.data_ptr(), sb, sc, sh, sw)
 
 
-def _require_cuda_f32(name: str, t: torch.Tensor, allow_pinned_host: bool = False):
-    if t.dtype != torch.float32:
-        raise TypeError(
-            f"{name}: dtype {t.dtype} is not supported by the B200 decode path yet (fp32 only); "
-            "the reference computes the sigmoid in the input dtype, so a silent upcast would change results"
-        )
+_DTYPES = {torch.float32: _native.DTYPE_F32, torch.float16: _native.DTYPE_F16, torch.bfloat16: _native.DTYPE_BF16}
+
+
+def _require_cuda_f32(name: str, t: torch.Tensor, allow_pinned_host: bool = False, dtype: torch.dtype | None = None):
+    """Device / rank / dtype checks (the name is historical: fp16 and bf16 are accepted too -- the
+    reference computes the sigmoid in the input dtype, and so do the kernels; nothing is upcast)."""
+    if t.dtype not in _DTYPES:
+        raise TypeError(f"{name}: dtype {t.dtype} is not supported by the B200 decode path (float32, float16, bfloat16)")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"{name}: dtype {t.dtype} differs from anchor_hm's {dtype}; the four network outputs are views "
+                        "of one tensor in the reference and must share a dtype")
     if t.dim() != 4:
         raise ValueError(f"{name}: expected a (B, C, H, W) tensor, got shape {tuple(t.shape)}")
     if not t.is_cuda and not (allow_pinned_host and t.is_pinned()):
@@ -99,8 +104,9 @@ class DecodePlan:
     """Pre-sized workspace + output blob for one (device, shape, K, P): the low-overhead way
     to call the C ABI repeatedly (bench loop, CUDA-graph capture, sharded decode)."""
 
-    def __init__(self, device, B, M, N, H, W, K, P):
+    def __init__(self, device, B, M, N, H, W, K, P, dtype: torch.dtype = torch.float32):
         self.shape = (B, M, N, H, W, K, P)
+        self.dtype = dtype
         self.device = torch.device(device)
         self.lib = _native.load()
         self.workspace_bytes = _native.workspace_bytes(B, M, N, H, W, K, P)
@@ -110,7 +116,7 @@ class DecodePlan:
         self.params = SdnetDecodeParams()
         p = self.params
         p.struct_size = ctypes.sizeof(SdnetDecodeParams)
-        p.dtype = _native.DTYPE_F32
+        p.dtype = _DTYPES[dtype]
         p.B, p.M, p.N, p.H, p.W, p.K, p.P = B, M, N, H, W, K, P
         p.workspace = self.workspace.data_ptr()
         p.workspace_bytes = self.workspace_bytes
@@ -162,9 +168,10 @@ class DecodePlan:
         return self.out
 
 
-def _f32(value: float) -> float:
-    """Round a Python double to fp32 the way torch does when a tensor is compared with a scalar."""
-    return float(torch.tensor(value, dtype=torch.float32))
+def _f32(value: float, dtype: torch.dtype = torch.float32) -> float:
+    """Round a Python double to `dtype` the way torch does when a tensor of that dtype is compared
+    with a scalar (the result is exactly representable in fp32 for every supported dtype)."""
+    return float(torch.tensor(value, dtype=dtype))
 
 
 # ------------------------------------------------------------------------------------ custom ops
@@ -175,7 +182,7 @@ def _decode_op(anchor_hm: torch.Tensor, part_hm: torch.Tensor, offsets: torch.Te
     B, M, H, W = anchor_hm.shape
     N = part_hm.shape[1]
     with torch.cuda.device(anchor_hm.device):
-        plan = DecodePlan(anchor_hm.device, B, M, N, H, W, max_objects, max_parts)
+        plan = DecodePlan(anchor_hm.device, B, M, N, H, W, max_objects, max_parts, anchor_hm.dtype)
         plan.run(anchor_hm, part_hm, offsets, embeddings, conf_f32, dist_abs_f32, radius, flags)
     return plan.out.blob
 
@@ -193,7 +200,7 @@ def _activate_op(hm: torch.Tensor) -> torch.Tensor:
     out = torch.empty((B, C, H, W), dtype=torch.float32, device=hm.device)
     view = _view4(hm)
     with torch.cuda.device(hm.device):
-        rc = _native.load().sdnet_activate_launch(ctypes.byref(view), _native.DTYPE_F32, B, C, H, W,
+        rc = _native.load().sdnet_activate_launch(ctypes.byref(view), _DTYPES[hm.dtype], B, C, H, W,
                                                   ctypes.c_void_p(out.data_ptr()),
                                                   ctypes.c_void_p(torch.cuda.current_stream(hm.device).cuda_stream))
     _native.check(rc, "sdnet_activate_launch")
@@ -217,7 +224,7 @@ def decode_packed(outputs: dict, max_objects: int, max_parts: int, conf_thresh: 
     a_hm, p_hm, off = outputs["anchor_hm"], outputs["part_hm"], outputs["offsets"]
     emb = outputs["embeddings"] if group or "embeddings" in outputs else None
     for name, t in (("anchor_hm", a_hm), ("part_hm", p_hm), ("offsets", off)) + ((("embeddings", emb),) if emb is not None else ()):
-        _require_cuda_f32(name, t)
+        _require_cuda_f32(name, t, dtype=a_hm.dtype)
     B, M, H, W = a_hm.shape
     N = p_hm.shape[1]
     if emb is None:
@@ -225,12 +232,15 @@ def decode_packed(outputs: dict, max_objects: int, max_parts: int, conf_thresh: 
     flags = (FLAG_PRE_ACTIVATED if pre_activated else 0) | (0 if group else FLAG_NO_GROUPING) | (
         FLAG_EXACT_SELECT if exact_select else 0) | (FLAG_WARP_KERNEL if warp_kernel else 0)
     a_hm, p_hm, off, emb = map(_unit_w_stride, (a_hm, p_hm, off, emb))
-    blob = _decode_op(a_hm, p_hm, off, emb, int(max_objects), int(max_parts), _f32(conf_thresh),
+    # `scores > conf` compares in the scores' dtype (fp16 scores against fp16(conf)); the distance gate
+    # always compares fp32 distances
+    blob = _decode_op(a_hm, p_hm, off, emb, int(max_objects), int(max_parts), _f32(conf_thresh, a_hm.dtype),
                       _f32(float(dist_thresh) * min(W, H)), int(radius), int(flags))
     return _carve(blob, B, int(max_objects), int(max_parts), M + N)
 
 
 def activate_maps(hm: torch.Tensor) -> torch.Tensor:
-    """``clamp(sigmoid(hm), 1e-6, 1-1e-6)`` as a contiguous fp32 tensor (reference utils.py:355-361)."""
+    """``clamp(sigmoid(hm), 1e-6, 1-1e-6)`` as a contiguous tensor of hm's dtype (reference utils.py:355-361)."""
     _require_cuda_f32("heat map", hm)
-    return _activate_op(_unit_w_stride(hm))
+    out = _activate_op(_unit_w_stride(hm))  # fp32 storage of values exactly representable in hm.dtype
+    return out if hm.dtype == torch.float32 else out.to(hm.dtype)

@@ -161,7 +161,7 @@ def test_strided_channel_views_and_errors(cuda_device):
     with pytest.raises(RuntimeError):
         ops.decode_packed({k: v.cpu() for k, v in outs.items()}, 100, 100, 0.4, 0.1)
     with pytest.raises(TypeError):
-        ops.decode_packed({k: v.half() for k, v in outs.items()}, 100, 100, 0.4, 0.1)
+        ops.decode_packed({k: v.double() for k, v in outs.items()}, 100, 100, 0.4, 0.1)
     with pytest.raises(RuntimeError):
         ops.decode_packed(outs, 128 * 128 + 1, 100, 0.4, 0.1)
 

@@ -70,7 +70,7 @@ def test_product_path_has_no_cpu_fallback():
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         ops.decode_packed(outs, 100, 100, 0.4, 0.1)
     with pytest.raises(TypeError):
-        ops.decode_packed({k: v.half() for k, v in outs.items()}, 100, 100, 0.4, 0.1)
+        ops.decode_packed({k: v.double() for k, v in outs.items()}, 100, 100, 0.4, 0.1)
     with pytest.raises(RuntimeError):
         ops.activate_maps(outs["anchor_hm"])
 
