@@ -117,6 +117,23 @@ def main():
         }
         print(name, "objects", [len(a) for a in index[name]["annotation"]], "stable", index[name]["anchor_stable"],
               index[name]["part_stable"])
+    # reduced-precision inputs (the --amp validation path): ties everywhere, so only tie-independent
+    # facts are stored -- the sorted score lists and the number of objects per image
+    for name, dtype in (("half_f16", torch.float16), ("half_bf16", torch.bfloat16)):
+        cfg = DecodeConfig(name, 2, 2, 1, 48, 64, 40, 40, 0.4, 0.1, cfg_id=150)
+        raw = make_raw(cfg, "blobs").to(dtype)
+        outs = split_outputs(raw, 2, 1)
+        args = args_for(cfg, 0.4, 0.1)
+        meta = Decoder(args)({key: val.clone() for key, val in outs.items()}, return_metadata=True)
+        np.savez_compressed(HERE / f"{name}.npz", raw=raw.float().numpy(),
+                            a_scores_masked=meta["topk_anchor"][0].float().numpy(),
+                            p_scores_masked=meta["topk_kp"][0].float().numpy(),
+                            anchor_sig=meta["anchor_hm_sig"].float().numpy())
+        index[name] = {"shape": [2, 2, 1, 48, 64], "K": 40, "P": 40, "mode": "blobs", "conf": 0.4, "dist": 0.1,
+                       "anchor_name": "stem", "down_ratio": 4.0, "dtype": str(dtype).split(".")[-1],
+                       "objects_per_image": [len(a) for a in meta["annotation"]],
+                       "parts_per_image": [a.nb_parts for a in meta["annotation"]], "torch": torch.__version__}
+        print(name, index[name]["objects_per_image"], index[name]["parts_per_image"])
     (HERE / "index.json").write_text(json.dumps(index))
     print("wrote", len(CASES), "cases")
 

@@ -11,7 +11,7 @@ from structuredetector_b200.synth import CONFIGS, DecodeConfig, make_raw, split_
 from tests.helpers import (assert_objects_close, assert_topk_equal_up_to_ties, golden_args, golden_names, import_reference,
                            listify, load_golden, np_inputs, plain, reference_available, torch_sigmoid_fn)
 
-TIE_FREE = [n for n in golden_names() if not n.startswith("ties")]
+TIE_FREE = [n for n in golden_names() if not n.startswith(("ties", "half"))]
 
 
 def _oracle_on_golden(name, sigmoid_fn):
@@ -145,3 +145,28 @@ def test_oracle_matches_live_reference(mode):
     objs = O.assemble(pk, args._r_labels, args._r_parts, args.anchor_name, cfg.conf_threshold,
                       (cfg.width, cfg.height), (4 * cfg.width, 4 * cfg.height))
     assert plain(anns) == objs
+
+
+@pytest.mark.parametrize("name", ["half_f16", "half_bf16"])
+def test_oracle_reduced_precision_matches_reference_golden(name):
+    """fp16 / bf16 inputs (the reference under --amp): scores sit on a coarse grid, so torch-CPU's
+    unspecified tie order shuffles slots; what does not depend on it must match exactly -- the
+    activated maps, the sorted score lists, and how many objects / parts each image yields."""
+    meta, arr = load_golden(name)
+    dtype = {"float16": torch.float16, "bfloat16": torch.bfloat16}[meta["dtype"]]
+    b, m, n, h, w = meta["shape"]
+    raw = arr["raw"]
+
+    def act(x):  # the reference's clamped sigmoid in `dtype`, evaluated by torch on the CPU
+        t = torch.from_numpy(np.ascontiguousarray(x)).to(dtype)
+        return torch.clamp(torch.sigmoid(t), min=1e-6, max=1 - 1e-6).float().numpy()
+
+    pk = O.decode_packed(raw[:, :m], raw[:, m:m + n], raw[:, m + n:m + n + 2], raw[:, m + n + 2:], meta["K"], meta["P"],
+                         meta["conf"], meta["dist"], activation_fn=act,
+                         conf_cmp=float(torch.tensor(meta["conf"], dtype=dtype)))
+    np.testing.assert_array_equal(pk["anchor_sig"], arr["anchor_sig"])
+    np.testing.assert_array_equal(pk["anchor_scores_masked"], arr["a_scores_masked"])
+    np.testing.assert_array_equal(pk["part_scores_masked"], arr["p_scores_masked"])
+    args = golden_args(meta)
+    objs = O.assemble(pk, args._r_labels, args._r_parts, args.anchor_name, meta["conf"], (w, h), (4 * w, 4 * h))
+    assert [len(o) for o in objs] == meta["objects_per_image"]
