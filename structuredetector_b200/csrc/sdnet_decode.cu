@@ -92,9 +92,10 @@ struct PeaksParams {
 // fp32 and rounds each result to the tensor dtype, so S_T(x) = T(clamp(float(T(sigmoid(float(x)))))),
 // returned here as the exactly representable float.  Every S_T is monotone non-decreasing in x.
 //
-// kNear / kHi / kLo say when two different logits x < h might share a score: only if
-// x >= h - kNear with h in [kLo, kHi], or h > kHi and x > kHi - 1, or h < kLo.  Outside that, S(x) <
-// S(h) strictly; verified exhaustively on the device by tests/test_gpu_parity.py for every dtype.
+// The margins say when two different logits x < h might share a score: only if x >= h - kNear with h in
+// [kLo, kHi], or x >= h - kNear2 with h in (kHi, kHi2], or h > kHi2 and x > kHi2 - 1, or h < kLo.
+// Outside that, S(x) < S(h) strictly; verified exhaustively on the device for every dtype
+// (tests/test_gpu_parity.py, tests/test_gpu_halfprec.py).
 template <int DT>
 struct Num;
 
@@ -102,6 +103,7 @@ template <>
 struct Num<SDNET_DTYPE_F32> {
   typedef float In;
   static constexpr float kNear = 2e-3f, kHi = 8.0f, kLo = -13.0f;
+  static constexpr float kNear2 = 2e-3f, kHi2 = 8.0f;  // no second zone
   static __device__ __forceinline__ float act(float x) {
     const float s = 1.0f / (1.0f + expf(-x));
     return fminf(fmaxf(s, kClampLo), kClampHi);
@@ -113,6 +115,7 @@ template <>
 struct Num<SDNET_DTYPE_F16> {
   typedef __half In;
   static constexpr float kNear = 0.02f, kHi = 3.0f, kLo = -11.0f;
+  static constexpr float kNear2 = 0.15f, kHi2 = 5.0f;  // 10-bit mantissa: ties reach 0.073 logit at h = 5
   static __device__ __forceinline__ float act(float x) {
     const float s = __half2float(__float2half_rn(1.0f / (1.0f + expf(-x))));
     return __half2float(__float2half_rn(fminf(fmaxf(s, kClampLo), kClampHi)));
@@ -124,6 +127,7 @@ template <>
 struct Num<SDNET_DTYPE_BF16> {
   typedef __nv_bfloat16 In;
   static constexpr float kNear = 0.1f, kHi = 2.0f, kLo = -13.0f;
+  static constexpr float kNear2 = 0.6f, kHi2 = 4.0f;   // 7-bit mantissa: ties reach 0.22 logit at h = 4
   static __device__ __forceinline__ float act(float x) {
     const float s = __bfloat162float(__float2bfloat16_rn(1.0f / (1.0f + expf(-x))));
     return __bfloat162float(__float2bfloat16_rn(fminf(fmaxf(s, kClampLo), kClampHi)));
@@ -295,6 +299,7 @@ struct RowFeedCvt {
   typedef typename Num<DT>::In In;
   static constexpr int kDepth = 3;
   u32 ring_s, s_own, s_halo, own_ok, halo_ok;
+  bool vec_ok;  // every row of this lane's four columns is 8-byte aligned
   const In* gown;
   const In* ghalo;
   long long pitch;
@@ -316,6 +321,7 @@ struct RowFeedCvt {
     pitch = sh;
     gown = plane + (long long)r0 * sh + col0;
     ghalo = plane + (long long)r0 * sh + halo_col;
+    vec_ok = (reinterpret_cast<uintptr_t>(gown) % 8 == 0) && (sh % 4 == 0);
     own_ok = 0;
     for (int jj = 0; jj < 4; ++jj) own_ok |= (col0 + jj < W ? 1u : 0u) << jj;
     halo_ok = 0;
@@ -339,10 +345,17 @@ struct RowFeedCvt {
     float4 v = make_float4(ninf, ninf, ninf, ninf);
     float2 hv = make_float2(ninf, ninf);
     if (q <= q_last && (unsigned)(row0 + q) < (unsigned)H) {
-      if (own_ok & 1u) v.x = Num<DT>::to_float(__ldg(gown + 0));
-      if (own_ok & 2u) v.y = Num<DT>::to_float(__ldg(gown + 1));
-      if (own_ok & 4u) v.z = Num<DT>::to_float(__ldg(gown + 2));
-      if (own_ok & 8u) v.w = Num<DT>::to_float(__ldg(gown + 3));
+      if (own_ok == 15u && vec_ok) {  // four columns in one 8-byte load
+        const uint2 raw = __ldg(reinterpret_cast<const uint2*>(gown));
+        In e[4];
+        memcpy(e, &raw, 8);
+        v = make_float4(Num<DT>::to_float(e[0]), Num<DT>::to_float(e[1]), Num<DT>::to_float(e[2]), Num<DT>::to_float(e[3]));
+      } else {
+        if (own_ok & 1u) v.x = Num<DT>::to_float(__ldg(gown + 0));
+        if (own_ok & 2u) v.y = Num<DT>::to_float(__ldg(gown + 1));
+        if (own_ok & 4u) v.z = Num<DT>::to_float(__ldg(gown + 2));
+        if (own_ok & 8u) v.w = Num<DT>::to_float(__ldg(gown + 3));
+      }
       if (halo_ok & 1u) hv.x = Num<DT>::to_float(__ldg(ghalo + 0));
       if (halo_ok & 2u) hv.y = Num<DT>::to_float(__ldg(ghalo + 1));
     }
@@ -477,8 +490,8 @@ __device__ __forceinline__ float shared_floor(int fbin, float xscale) {
   if (fbin <= 0) return -CUDART_INF_F;
   const float edge = kBinLo + (float)fbin * (1.0f / kFineScale);
   if (xscale != 1.0f) return edge / xscale;  // pre-activated: keys are strictly monotone in the value
-  if (edge < Num<DT>::kLo || edge > Num<DT>::kHi) return -CUDART_INF_F;
-  return edge - Num<DT>::kNear;
+  if (edge < Num<DT>::kLo || edge > Num<DT>::kHi2) return -CUDART_INF_F;
+  return edge - (edge <= Num<DT>::kHi ? Num<DT>::kNear : Num<DT>::kNear2);
 }
 
 // Where a warp publishes / picks up shared floors.
@@ -568,11 +581,13 @@ __device__ __forceinline__ void flush_candidates(UnitState& st, const u64* buf, 
 template <int R, int DT = SDNET_DTYPE_F32>
 __device__ __forceinline__ u32 classify_row(const float4 ctr, float h0, float h1, float h2, float h3, float floorx) {
   constexpr float kNearTie = Num<DT>::kNear, kHiZone = Num<DT>::kHi, kLoZone = Num<DT>::kLo;
+  constexpr float kNearTie2 = Num<DT>::kNear2, kHiZone2 = Num<DT>::kHi2;
   u32 cmask = 0, amb = 0;
 #define SDNET_CLASSIFY(x, h, j)                                                                        \
   if ((x) > floorx) {                                                                                  \
     if ((x) == (h)) cmask |= 1u << j;                                                                  \
-    else if (((x) >= (h) - kNearTie) || ((h) > kHiZone && (x) > kHiZone - 1.0f) || ((h) < kLoZone))     \
+    else if (((x) >= (h) - kNearTie) || ((h) > kHiZone && (x) >= (h) - kNearTie2) ||                    \
+             ((h) > kHiZone2 && (x) > kHiZone2 - 1.0f) || ((h) < kLoZone))                              \
       amb |= 1u << j;                                                                                  \
   }
   SDNET_CLASSIFY(ctr.x, h0, 0)

@@ -15,7 +15,7 @@ from tests.helpers import assert_packed_equal, make_args, packed_np, plain
 pytestmark = pytest.mark.gpu
 DTYPES = [torch.float16, torch.bfloat16]
 # margins of Num<DT> in csrc/sdnet_decode.cu
-MARGINS = {torch.float16: (0.02, 3.0, -11.0), torch.bfloat16: (0.1, 2.0, -13.0)}
+MARGINS = {torch.float16: (0.02, 3.0, -11.0, 0.15, 5.0), torch.bfloat16: (0.1, 2.0, -13.0, 0.6, 4.0)}
 
 
 def _all_finite_values(dtype, device):
@@ -46,7 +46,7 @@ def test_activation_bit_exact_for_every_value(cuda_device, dtype):
 def test_score_function_monotone_and_margins_hold(cuda_device, dtype):
     """Exhaustive over all 65,536 inputs: S_T is monotone, and outside the near-tie margins the
     kernel assumes (Num<DT>::kNear/kHi/kLo, kSatX) two logits never share a score."""
-    near, hi, lo = MARGINS[dtype]
+    near, hi, lo, near2, hi2 = MARGINS[dtype]
     x = torch.sort(_all_finite_values(dtype, cuda_device).float()).values
     x = x[(x >= -30) & (x <= 30)]
     pad = (-x.numel()) % 64
@@ -58,8 +58,12 @@ def test_score_function_monotone_and_margins_hold(cuda_device, dtype):
     j = np.searchsorted(xs, xs[mid] - near, side="left") - 1  # last index with xs[j] < h - near
     ok = j >= 0
     assert (ss[j[ok]] < ss[mid[ok]]).all()
-    # hi zone: x <= hi - 1 never ties with h > hi
-    assert ss[np.searchsorted(xs, hi - 1.0, side="right") - 1] < ss[np.searchsorted(xs, hi, side="right")]
+    # second zone: h in (hi, hi2] with the wider margin
+    mid2 = np.flatnonzero((xs > hi) & (xs <= hi2))
+    j2 = np.searchsorted(xs, xs[mid2] - near2, side="left") - 1
+    assert (ss[j2] < ss[mid2]).all()
+    # beyond it: x <= hi2 - 1 never ties with h > hi2
+    assert ss[np.searchsorted(xs, hi2 - 1.0, side="right") - 1] < ss[np.searchsorted(xs, hi2, side="right")]
     # saturation: every |x| >= 14 scores like +-14
     top, bot = ss[np.searchsorted(xs, 14.0)], ss[np.searchsorted(xs, -14.0, side="right") - 1]
     assert (ss[xs >= 14.0] == top).all() and (ss[xs <= -14.0] == bot).all()
