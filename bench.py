@@ -132,6 +132,13 @@ def cpu_reference_rate(cfg, mode: str, seconds: float, steps: int | None = None,
     from oracle import torch_port
     from structuredetector_b200.synth import make_raw, split_outputs
 
+    # all the host threads the process may use (torchrun exports OMP_NUM_THREADS=1, which would make
+    # the CPU arm ten times slower than the same code started with plain `python`)
+    try:
+        usable = len(os.sched_getaffinity(0))
+    except AttributeError:
+        usable = os.cpu_count() or 1
+    torch.set_num_threads(max(1, usable))
     raw = make_raw(cfg, mode, batch=CPU_BATCH)
     outs = split_outputs(raw, cfg.labels, cfg.parts)
     labels = {i: f"label{i}" for i in range(cfg.labels)}
