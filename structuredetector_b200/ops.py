@@ -38,9 +38,9 @@ def _view4(t: torch.Tensor) -> SdnetTensor4:
 _DTYPES = {torch.float32: _native.DTYPE_F32, torch.float16: _native.DTYPE_F16, torch.bfloat16: _native.DTYPE_BF16}
 
 
-def _require_cuda_f32(name: str, t: torch.Tensor, allow_pinned_host: bool = False, dtype: torch.dtype | None = None):
-    """Device / rank / dtype checks (the name is historical: fp16 and bf16 are accepted too -- the
-    reference computes the sigmoid in the input dtype, and so do the kernels; nothing is upcast)."""
+def _check_tensor(name: str, t: torch.Tensor, allow_pinned_host: bool = False, dtype: torch.dtype | None = None):
+    """Device / rank / dtype checks.  fp32, fp16 and bf16 are accepted: the reference computes the
+    sigmoid in the input dtype, and so do the kernels; nothing is ever upcast silently."""
     if t.dtype not in _DTYPES:
         raise TypeError(f"{name}: dtype {t.dtype} is not supported by the B200 decode path (float32, float16, bfloat16)")
     if dtype is not None and t.dtype != dtype:
@@ -224,7 +224,7 @@ def decode_packed(outputs: dict, max_objects: int, max_parts: int, conf_thresh: 
     a_hm, p_hm, off = outputs["anchor_hm"], outputs["part_hm"], outputs["offsets"]
     emb = outputs["embeddings"] if group or "embeddings" in outputs else None
     for name, t in (("anchor_hm", a_hm), ("part_hm", p_hm), ("offsets", off)) + ((("embeddings", emb),) if emb is not None else ()):
-        _require_cuda_f32(name, t, dtype=a_hm.dtype)
+        _check_tensor(name, t, dtype=a_hm.dtype)
     B, M, H, W = a_hm.shape
     N = p_hm.shape[1]
     if emb is None:
@@ -241,6 +241,6 @@ def decode_packed(outputs: dict, max_objects: int, max_parts: int, conf_thresh: 
 
 def activate_maps(hm: torch.Tensor) -> torch.Tensor:
     """``clamp(sigmoid(hm), 1e-6, 1-1e-6)`` as a contiguous tensor of hm's dtype (reference utils.py:355-361)."""
-    _require_cuda_f32("heat map", hm)
+    _check_tensor("heat map", hm)
     out = _activate_op(_unit_w_stride(hm))  # fp32 storage of values exactly representable in hm.dtype
     return out if hm.dtype == torch.float32 else out.to(hm.dtype)
