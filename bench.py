@@ -334,7 +334,7 @@ def main():
     achieved = peaks_bytes / (peaks_ms * 1e-3) / 1e9
     traffic = None
     traffic_path = ROOT / "profiles" / "peaks_kernel_traffic.json"
-    if traffic_path.exists():
+    if traffic_path.exists() and args.dtype == "f32":
         try:
             traffic = json.loads(traffic_path.read_text()).get(f"n{world}", {}).get("dram_bytes_per_launch")
         except Exception:  # noqa: BLE001
