@@ -1109,13 +1109,66 @@ constexpr int kTilePitchB = kTileCols * 4;                   // 544 B per ring r
 constexpr int kTileBytes = kGroupRows * kTilePitchB;         // 2176 B per TMA tile (17 x 128 B)
 constexpr int kTileWarps = 4;
 // ring slots (tiles) per warp: 4 = two tiles in flight, 5 CTAs/SM; 3 = one in flight, 6 CTAs/SM
-__host__ __device__ constexpr int tile_smem_per_warp(int ng) { return ((ng * kTileBytes + 32 + kBins * 8 + kBuf * 8) + 127) / 128 * 128; }
+constexpr int kWork = 256;  // per-warp work list of pixels that beat the floor (u16 each)
+__host__ __device__ constexpr int tile_smem_per_warp(int ng) { return ((ng * kTileBytes + 32 + kBins * 8 + kBuf * 8 + kWork * 2) + 127) / 128 * 128; }
 __host__ __device__ constexpr int tile_smem(int ng) { return kTileWarps * tile_smem_per_warp(ng); }
 
 __device__ __forceinline__ void tma_tile_4d(u32 dst, const CUtensorMap* map, int x, int y, int c, int b, u32 bar) {
   asm volatile(
       "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
       ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(c), "r"(b), "r"(bar) : "memory");
+}
+
+// Settle a work list of pixels that beat the floor, one pixel per lane per round.  Entry e:
+// bits 8-9 = row inside the current 4-row group, bits 0-6 = column inside the 128-column panel.
+// The lane reads its pixel's (2R+1)^2 window from the ring with scalar loads (columns outside the
+// image were filled with NaN by the TMA unit and are ignored by fmaxf), classifies it and appends a
+// (logit, index) record to the warp's candidate buffer.
+template <int R, u32 kRows>
+__device__ __forceinline__ void settle_pixels(UnitState& st, const unsigned short* work, int nwork, u32 ring_s, int t0,
+                                              int r_begin, int W, int panel_col0, bool pre, u64* buf, u32* hist,
+                                              int* minx, const SharedFloors& sf, int* count_ptr,
+                                              u64* __restrict__ list, int cap, int K, int lane, float xscale,
+                                              float satx) {
+  constexpr float kNearTie = Num<SDNET_DTYPE_F32>::kNear, kHiZone = Num<SDNET_DTYPE_F32>::kHi,
+                  kLoZone = Num<SDNET_DTYPE_F32>::kLo, kNearTie2 = Num<SDNET_DTYPE_F32>::kNear2,
+                  kHiZone2 = Num<SDNET_DTYPE_F32>::kHi2;
+  for (int base = 0; base < nwork; base += 32) {  // warp-uniform
+    const bool has = base + lane < nwork;
+    const u32 e = has ? work[base + lane] : 0u;
+    const int i = (int)(e >> 8), colp = (int)(e & 0x7fu);
+    const int t = t0 + i;
+    // ring row of the window's first row is t (the centre is t + R); ring column of the pixel is 4 + colp
+    const u32 col_addr = ring_s + (u32)(4 + colp - R) * 4;
+    float h = -CUDART_INF_F, x = 0.f;
+#pragma unroll
+    for (int d = 0; d <= 2 * R; ++d) {
+      const u32 a = col_addr + (((u32)(t + d)) % kRows) * kTilePitchB;
+      float v[2 * R + 1];
+#pragma unroll
+      for (int q = 0; q <= 2 * R; ++q) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[q]) : "r"(a + 4 * q));
+      if (d == R) x = v[R];
+#pragma unroll
+      for (int q = 0; q <= 2 * R; ++q) h = fmaxf(h, v[q]);
+    }
+    bool keep = has;
+    if (!pre && has && x != h) {
+      const bool amb = (x >= h - kNearTie) || (h > kHiZone && x >= h - kNearTie2) ||
+                       (h > kHiZone2 && x > kHiZone2 - 1.0f) || (h < kLoZone);  // same zones as classify_row
+      keep = amb && Num<SDNET_DTYPE_F32>::act(x) == Num<SDNET_DTYPE_F32>::act(h);  // rare, divergent
+    }
+    const u32 m = __ballot_sync(0xffffffffu, keep);
+    if (m) {  // warp-uniform
+      if (st.nbuf + __popc(m) > kBuf) {
+        __syncwarp();
+        flush_candidates(st, buf, hist, minx, sf, count_ptr, list, cap, K, lane, pre, xscale, satx);
+      }
+      if (keep)
+        buf[st.nbuf + __popc(m & ((1u << lane) - 1u))] =
+            ((u64)__float_as_uint(x) << 32) | (u32)((r_begin + t) * W + panel_col0 + colp);
+      st.nbuf += __popc(m);
+    }
+  }
 }
 
 template <int R, int NG>
@@ -1134,6 +1187,7 @@ sdnet_peaks_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_cons
   u32* hist = reinterpret_cast<u32*>(wbase + NG * kTileBytes + 32);
   int* minx = reinterpret_cast<int*>(hist + kBins);
   u64* buf = reinterpret_cast<u64*>(minx + kBins);
+  unsigned short* work = reinterpret_cast<unsigned short*>(buf + kBuf);
   const bool pre = p.pre_activated != 0;
   const float xscale = pre ? kPreScale : 1.0f;
   const float satx = pre ? CUDART_INF_F : kSatX;
@@ -1173,7 +1227,6 @@ sdnet_peaks_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_cons
     const CUtensorMap* tmap = is_anchor ? &tm_anchor : &tm_part;
     const int csel = is_anchor ? c : c - p.M;
     const int K = is_anchor ? p.K : p.P;
-    const int col0 = panel * kPanelW + 4 * lane;
     const int x0 = panel * kPanelW - 4;
     const int nrows = r_end - r_begin;
     const int y0 = r_begin - R;  // image row of ring row 0
@@ -1240,31 +1293,42 @@ sdnet_peaks_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_cons
         m3 = ninf;
       }
       if (__any_sync(0xffffffffu, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) > st.floorx)) {
-        // something in these four rows beats the floor: visit only the rows that do (kept as a
-        // real loop so the row code exists once -- it is large and instruction-cache bound)
-        u32 rowmask4 = (__any_sync(0xffffffffu, m0 > st.floorx) ? 1u : 0u) | (__any_sync(0xffffffffu, m1 > st.floorx) ? 2u : 0u) |
-                       (__any_sync(0xffffffffu, m2 > st.floorx) ? 4u : 0u) | (__any_sync(0xffffffffu, m3 > st.floorx) ? 8u : 0u);
-#pragma unroll 1
-        while (rowmask4) {
-          const int i = __ffs(rowmask4) - 1;
-          rowmask4 &= rowmask4 - 1;
-          const int t = t0 + i;
-          const float4 ctr = lds128(ring_own + ((rowbase + (u32)(t + R)) % kRows) * kTilePitchB);
-          const float floorx = st.floorx;
-          u32 cmask = 0;
-          if (!pre) {
-            float h0, h1, h2, h3;
-            window_max<R, kRows>(ring_own, rowbase, kTilePitchB, t, true, true, h0, h1, h2, h3);
-            cmask = classify_row<R>(ctr, h0, h1, h2, h3, floorx);
-          } else {
-            if (ctr.x > floorx) cmask |= 1u;
-            if (ctr.y > floorx) cmask |= 2u;
-            if (ctr.z > floorx) cmask |= 4u;
-            if (ctr.w > floorx) cmask |= 8u;
+        // Something in these four rows beats the floor.  Pixel-centric slow path: (1) the few pixels
+        // above the floor are compacted into a per-warp work list, (2) each lane then takes ONE listed
+        // pixel and settles it alone -- its own 5x5 window straight from the ring, the near-tie
+        // classification, the append.  Cost is per batch of <= 32 pixels, not per row of 128.
+        const float floorx = st.floorx;
+        int nwork = 0;
+        const u32 lt = (1u << lane) - 1u;
+#pragma unroll
+        for (int i = 0; i < kGroupRows; ++i) {
+          const float mi = i == 0 ? m0 : (i == 1 ? m1 : (i == 2 ? m2 : m3));
+          if (__any_sync(0xffffffffu, mi > floorx)) {  // warp-uniform
+            const float4 ci = i == 0 ? c0 : (i == 1 ? c1 : (i == 2 ? c2 : c3));
+            const u32 cm = (ci.x > floorx ? 1u : 0u) | (ci.y > floorx ? 2u : 0u) | (ci.z > floorx ? 4u : 0u) |
+                           (ci.w > floorx ? 8u : 0u);
+            const u32 cnt = __popc(cm);
+            const u32 b0 = __ballot_sync(0xffffffffu, cnt & 1u), b1 = __ballot_sync(0xffffffffu, cnt & 2u),
+                      b2 = __ballot_sync(0xffffffffu, cnt & 4u);
+            const int total = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
+            if (nwork + total > kWork) {  // rare (plateaus): settle what is listed so far
+              __syncwarp();
+              settle_pixels<R, kRows>(st, work, nwork, ring_s, t0, r_begin, W, panel * kPanelW, pre, buf, hist, minx, sf,
+                                      count_ptr, list, p.cap, K, lane, xscale, satx);
+              nwork = 0;
+            }
+            int pos = nwork + __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt);
+            const u32 tag = ((u32)i << 8) | (u32)(4 * lane);
+            if (cm & 1u) work[pos++] = (unsigned short)(tag + 0);
+            if (cm & 2u) work[pos++] = (unsigned short)(tag + 1);
+            if (cm & 4u) work[pos++] = (unsigned short)(tag + 2);
+            if (cm & 8u) work[pos++] = (unsigned short)(tag + 3);
+            nwork += total;
           }
-          append_row(st, cmask, ctr, (u32)((r_begin + t) * W + col0), buf, hist, minx, sf, count_ptr, list, p.cap, K,
-                     lane, pre, xscale, satx);
         }
+        __syncwarp();
+        settle_pixels<R, kRows>(st, work, nwork, ring_s, t0, r_begin, W, panel * kPanelW, pre, buf, hist, minx, sf,
+                                count_ptr, list, p.cap, K, lane, xscale, satx);
       }
       // every lane's reads of tile g are consumed (the votes above): refill its slot with
       // the tile NG ahead
