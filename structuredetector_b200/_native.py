@@ -9,7 +9,10 @@ from __future__ import annotations
 import ctypes
 from pathlib import Path
 
-LIB_PATH = Path(__file__).resolve().parent / "csrc" / "libsdnet_decode.so"
+import os as _os
+
+# SDNET_DECODE_LIB: load another build of the same library (kernel experiments, tools/xbuild.sh)
+LIB_PATH = Path(_os.environ.get("SDNET_DECODE_LIB") or Path(__file__).resolve().parent / "csrc" / "libsdnet_decode.so").resolve()
 ABI_VERSION = 2
 
 FLAG_PRE_ACTIVATED = 1

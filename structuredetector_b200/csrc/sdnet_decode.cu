@@ -211,13 +211,32 @@ __device__ __forceinline__ void mbar_arrive(u32 bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(u32 bar, u32 bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+#ifndef SDNET_X_WAIT
+#define SDNET_X_WAIT 0
+#endif
 __device__ __forceinline__ void mbar_wait(u32 bar, u32 parity) {
+#if SDNET_X_WAIT == 0
   asm volatile(
       "{\n\t.reg .pred p;\n"
       "WAIT_LOOP:\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
       "@!p bra WAIT_LOOP;\n\t}"
       ::"r"(bar), "r"(parity), "r"(1000u) : "memory");  // suspend-time hint (ns): sleep instead of spinning
+#elif SDNET_X_WAIT == 1
+  asm volatile(
+      "{\n\t.reg .pred p;\n"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@!p bra WAIT_LOOP;\n\t}"
+      ::"r"(bar), "r"(parity) : "memory");
+#else
+  asm volatile(
+      "{\n\t.reg .pred p;\n"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@!p bra WAIT_LOOP;\n\t}"
+      ::"r"(bar), "r"(parity) : "memory");
+#endif
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void bulk_prefetch_l2(const void* src, u32 bytes) {
@@ -1108,10 +1127,10 @@ constexpr int kTileCols = kPanelW + 8;
 constexpr int kTilePitchB = kTileCols * 4;                   // 544 B per ring row
 constexpr int kTileBytes = kGroupRows * kTilePitchB;         // 2176 B per TMA tile (17 x 128 B)
 constexpr int kTileWarps = 4;
-// ring slots (tiles) per warp: 4 = two tiles in flight, 5 CTAs/SM; 3 = one in flight, 6 CTAs/SM
-constexpr int kWork = 256;  // per-warp work list of pixels that beat the floor (u16 each)
-__host__ __device__ constexpr int tile_smem_per_warp(int ng) { return ((ng * kTileBytes + 32 + kBins * 8 + kBuf * 8 + kWork * 2) + 127) / 128 * 128; }
-__host__ __device__ constexpr int tile_smem(int ng) { return kTileWarps * tile_smem_per_warp(ng); }
+constexpr int kTileNG = 4;   // ring slots (tiles) per warp: 16 rows, two or three tiles in flight, 5 CTAs/SM
+constexpr int kWork = 128;   // per-warp work list: one byte per (row of the group, lane) whose four pixels hold one above the floor
+constexpr int kTileSmemPerWarp = ((kTileNG * kTileBytes + 32 + kBins * 8 + kBuf * 8 + kWork) + 127) / 128 * 128;
+constexpr int kTileSmem = kTileWarps * kTileSmemPerWarp;
 
 __device__ __forceinline__ void tma_tile_4d(u32 dst, const CUtensorMap* map, int x, int y, int c, int b, u32 bar) {
   asm volatile(
@@ -1119,43 +1138,47 @@ __device__ __forceinline__ void tma_tile_4d(u32 dst, const CUtensorMap* map, int
       ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(c), "r"(b), "r"(bar) : "memory");
 }
 
-// Settle a work list of pixels that beat the floor, one pixel per lane per round.  Entry e:
-// bits 8-9 = row inside the current 4-row group, bits 0-6 = column inside the 128-column panel.
-// The lane reads its pixel's (2R+1)^2 window from the ring with scalar loads (columns outside the
-// image were filled with NaN by the TMA unit and are ignored by fmaxf), classifies it and appends a
-// (logit, index) record to the warp's candidate buffer.
-template <int R, u32 kRows>
-__device__ __forceinline__ void settle_pixels(UnitState& st, const unsigned short* work, int nwork, u32 ring_s, int t0,
-                                              int r_begin, int W, int panel_col0, bool pre, u64* buf, u32* hist,
-                                              int* minx, const SharedFloors& sf, int* count_ptr,
-                                              u64* __restrict__ list, int cap, int K, int lane, float xscale,
-                                              float satx) {
+// Settle the work list of one 4-row group.  Entry e = (row in group << 5) | lane names one float4
+// of centre pixels holding at least one pixel above the floor; four consecutive lanes take the four
+// pixels of an entry, so records leave in (row, column) = index order.  A lane whose pixel beats the
+// floor reads the pixel's (2R+1)^2 window from the ring with scalar loads (columns and rows outside
+// the image were filled with NaN by the TMA unit and are ignored by fmaxf), classifies it like
+// classify_row and appends a (logit, index) record to the warp's candidate buffer.
+// `row0` = ring row of the window's first row for group row 0 (the centre is R rows further).
+template <int R>
+__device__ __forceinline__ void settle_entries(UnitState& st, const unsigned char* work, int nent, u32 ring_s, u32 row0,
+                                               float floorx, u32 idx0, int W, bool pre, u64* buf, u32* hist, int* minx,
+                                               const SharedFloors& sf, int* count_ptr, u64* __restrict__ list, int cap,
+                                               int K, int lane, float xscale, float satx) {
   constexpr float kNearTie = Num<SDNET_DTYPE_F32>::kNear, kHiZone = Num<SDNET_DTYPE_F32>::kHi,
                   kLoZone = Num<SDNET_DTYPE_F32>::kLo, kNearTie2 = Num<SDNET_DTYPE_F32>::kNear2,
                   kHiZone2 = Num<SDNET_DTYPE_F32>::kHi2;
-  for (int base = 0; base < nwork; base += 32) {  // warp-uniform
-    const bool has = base + lane < nwork;
-    const u32 e = has ? work[base + lane] : 0u;
-    const int i = (int)(e >> 8), colp = (int)(e & 0x7fu);
-    const int t = t0 + i;
-    // ring row of the window's first row is t (the centre is t + R); ring column of the pixel is 4 + colp
-    const u32 col_addr = ring_s + (u32)(4 + colp - R) * 4;
-    float h = -CUDART_INF_F, x = 0.f;
+  constexpr u32 kRowMask = kTileNG * kGroupRows - 1;
+  const int nslots = 4 * nent;
+  for (int base = 0; base < nslots; base += 32) {  // warp-uniform
+    const int slot = base + lane;
+    const u32 e = slot < nslots ? work[slot >> 2] : 0u;
+    const u32 i = e >> 5, colp = 4 * (e & 31u) + (u32)(slot & 3);
+    const u32 col_addr = ring_s + (4 + colp - R) * 4;  // first column of the window
+    float x;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(col_addr + 4 * R + ((row0 + i + R) & kRowMask) * kTilePitchB));
+    bool keep = slot < nslots && x > floorx;
+    if (keep && !pre) {
+      float h = x;
 #pragma unroll
-    for (int d = 0; d <= 2 * R; ++d) {
-      const u32 a = col_addr + (((u32)(t + d)) % kRows) * kTilePitchB;
-      float v[2 * R + 1];
+      for (int d = 0; d <= 2 * R; ++d) {
+        const u32 a = col_addr + ((row0 + i + d) & kRowMask) * kTilePitchB;
+        float v[2 * R + 1];
 #pragma unroll
-      for (int q = 0; q <= 2 * R; ++q) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[q]) : "r"(a + 4 * q));
-      if (d == R) x = v[R];
+        for (int q = 0; q <= 2 * R; ++q) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[q]) : "r"(a + 4 * q));
 #pragma unroll
-      for (int q = 0; q <= 2 * R; ++q) h = fmaxf(h, v[q]);
-    }
-    bool keep = has;
-    if (!pre && has && x != h) {
-      const bool amb = (x >= h - kNearTie) || (h > kHiZone && x >= h - kNearTie2) ||
-                       (h > kHiZone2 && x > kHiZone2 - 1.0f) || (h < kLoZone);  // same zones as classify_row
-      keep = amb && Num<SDNET_DTYPE_F32>::act(x) == Num<SDNET_DTYPE_F32>::act(h);  // rare, divergent
+        for (int q = 0; q <= 2 * R; ++q) h = fmaxf(h, v[q]);
+      }
+      if (x != h) {
+        const bool amb = (x >= h - kNearTie) || (h > kHiZone && x >= h - kNearTie2) ||
+                         (h > kHiZone2 && x > kHiZone2 - 1.0f) || (h < kLoZone);  // same zones as classify_row
+        keep = amb && Num<SDNET_DTYPE_F32>::act(x) == Num<SDNET_DTYPE_F32>::act(h);  // rare
+      }
     }
     const u32 m = __ballot_sync(0xffffffffu, keep);
     if (m) {  // warp-uniform
@@ -1163,21 +1186,20 @@ __device__ __forceinline__ void settle_pixels(UnitState& st, const unsigned shor
         __syncwarp();
         flush_candidates(st, buf, hist, minx, sf, count_ptr, list, cap, K, lane, pre, xscale, satx);
       }
-      if (keep)
-        buf[st.nbuf + __popc(m & ((1u << lane) - 1u))] =
-            ((u64)__float_as_uint(x) << 32) | (u32)((r_begin + t) * W + panel_col0 + colp);
+      if (keep) buf[st.nbuf + __popc(m & ((1u << lane) - 1u))] = ((u64)__float_as_uint(x) << 32) | (idx0 + i * (u32)W + colp);
       st.nbuf += __popc(m);
     }
   }
 }
 
-template <int R, int NG>
-__global__ void __launch_bounds__(kTileWarps * 32, NG == 3 ? 6 : 5)
+template <int R>
+__global__ void __launch_bounds__(kTileWarps * 32, 5)
 sdnet_peaks_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_constant__ CUtensorMap tm_anchor,
                         const __grid_constant__ CUtensorMap tm_part) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  constexpr u32 kRows = NG * kGroupRows;
-  constexpr int kTileSmemPerWarp = tile_smem_per_warp(NG);
+  constexpr int NG = kTileNG;
+  constexpr u32 kRowMask = NG * kGroupRows - 1;
+  static_assert((NG & (NG - 1)) == 0, "slot and parity of a tile come from its running number by mask and shift");
   pdl_launch_dependents();
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -1187,13 +1209,14 @@ sdnet_peaks_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_cons
   u32* hist = reinterpret_cast<u32*>(wbase + NG * kTileBytes + 32);
   int* minx = reinterpret_cast<int*>(hist + kBins);
   u64* buf = reinterpret_cast<u64*>(minx + kBins);
-  unsigned short* work = reinterpret_cast<unsigned short*>(buf + kBuf);
+  unsigned char* work = reinterpret_cast<unsigned char*>(buf + kBuf);
   const bool pre = p.pre_activated != 0;
   const float xscale = pre ? kPreScale : 1.0f;
   const float satx = pre ? CUDART_INF_F : kSatX;
   const int C = p.M + p.N;
   const int H = p.H, W = p.W;
   const u32 ring_own = ring_s + (u32)(4 + 4 * lane) * 4;
+  const u32 lt = (1u << lane) - 1u;
   const float ninf = -CUDART_INF_F;
 
   if (lane == 0) {
@@ -1202,7 +1225,10 @@ sdnet_peaks_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_cons
   }
   __syncwarp();
 
-  u32 phases = 0;  // bit s = parity the next wait on ring slot s must use
+  // Tiles are numbered in one running sequence over all units this warp processes: tile number n
+  // lives in ring slot n % NG (ring rows 4 (n % NG) ..) and is the (n / NG)-th use of that slot, so
+  // the slot's mbarrier is waited with parity (n / NG) & 1.  Every issued tile is waited exactly once.
+  u32 tile_n = 0;
   for (;;) {
     u32 unit = 0;
     if (lane == 0) unit = atomicAdd(p.sched, 1u);
@@ -1229,8 +1255,7 @@ sdnet_peaks_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_cons
     const int K = is_anchor ? p.K : p.P;
     const int x0 = panel * kPanelW - 4;
     const int nrows = r_end - r_begin;
-    const int y0 = r_begin - R;  // image row of ring row 0
-    const int groups = (nrows + 2 * R + kGroupRows - 1) / kGroupRows;
+    const int groups = (nrows + 2 * R + kGroupRows - 1) / kGroupRows;  // tiles of the unit
     const int groups_out = (nrows + kGroupRows - 1) / kGroupRows;
     u64* __restrict__ list = p.lists + (size_t)plane_id * p.cap;
     int* count_ptr = p.counts + plane_id;
@@ -1242,6 +1267,9 @@ sdnet_peaks_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_cons
 
     UnitState st;
     st.floorx = shared_floor(__ldcg(gfloor_ptr), xscale);
+#ifdef SDNET_X_NOSLOW  // timing experiment only: stream the planes, never take the slow path
+    st.floorx = CUDART_INF_F;
+#endif
     st.emitted = 0;
     st.nbuf = 0;
     __syncwarp();  // everyone is done with the previous unit's ring, histogram and buffer
@@ -1249,25 +1277,26 @@ sdnet_peaks_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_cons
     *reinterpret_cast<int4*>(minx + 4 * lane) = make_int4(0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff);
     __syncwarp();
 
-    // tile j of the unit = ring rows 4j..4j+3 = image rows y0+4j..; slot j % NG; every tile that
-    // is issued is waited for exactly once, so one parity bit per slot tracks the phases
+    // tile k of the unit = image rows r_begin - R + 4k ..; running number tile_n + k
+    int y_next = r_begin - R;  // first image row of the next tile to issue
     if (lane == 0) {
       const int first = min(NG, groups);
-      for (int j = 0; j < first; ++j) {
-        mbar_arrive_expect_tx(bars_s + 8 * j, kTileBytes);
-        tma_tile_4d(ring_s + j * kTileBytes, tmap, x0, y0 + kGroupRows * j, csel, b, bars_s + 8 * j);
+      for (int k = 0; k < first; ++k) {
+        const u32 s = (tile_n + (u32)k) & (NG - 1);
+        mbar_arrive_expect_tx(bars_s + 8 * s, kTileBytes);
+        tma_tile_4d(ring_s + s * kTileBytes, tmap, x0, y_next + kGroupRows * k, csel, b, bars_s + 8 * s);
       }
     }
-    constexpr u32 rowbase = 0;
+    y_next += kGroupRows * NG;
     int gfloor_seen = 0;
     const int poll_mask = nrows <= 160 ? 0 : 3;
-    mbar_wait(bars_s, phases & 1u);
-    phases ^= 1u;
-    for (int g = 0; g < groups_out; ++g) {
-      if (g + 1 < groups) {
-        const u32 s1 = (u32)(g + 1) % NG;
-        mbar_wait(bars_s + 8 * s1, (phases >> s1) & 1u);
-        phases ^= 1u << s1;
+    u32 idx0 = (u32)(r_begin * W + panel * kPanelW);  // flat index of the group's row 0, panel column 0
+    mbar_wait(bars_s + 8 * (tile_n & (NG - 1)), (tile_n >> 2) & 1u);
+    for (int g = 0; g < groups_out; ++g, idx0 += (u32)(kGroupRows * W)) {
+      const u32 n = tile_n + (u32)g;  // tile holding the group's first window row
+      if (R == 2 || g + 1 < groups) {
+        const u32 n1 = n + 1;
+        mbar_wait(bars_s + 8 * (n1 & (NG - 1)), (n1 >> 2) & 1u);
       }
       if ((g & poll_mask) == 0) {
         // every 16 rows (every 4 in short strips): apply the plane-wide floor fetched one period ago
@@ -1276,74 +1305,59 @@ sdnet_peaks_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_cons
         st.floorx = fmaxf(st.floorx, shared_floor(gfloor_seen, xscale));
         asm volatile("ld.global.cg.s32 %0, [%1];" : "=r"(gfloor_seen) : "l"(gfloor_ptr) : "memory");
       }
-      const int t0 = g * kGroupRows;
-      // centre row of output row t0+i is ring row t0+i+R
-      const float4 c0 = lds128(ring_own + ((rowbase + (u32)(t0 + R)) % kRows) * kTilePitchB);
-      const float4 c1 = lds128(ring_own + ((rowbase + (u32)(t0 + R + 1)) % kRows) * kTilePitchB);
-      const float4 c2 = lds128(ring_own + ((rowbase + (u32)(t0 + R + 2)) % kRows) * kTilePitchB);
-      const float4 c3 = lds128(ring_own + ((rowbase + (u32)(t0 + R + 3)) % kRows) * kTilePitchB);
-      const int rows_here = min(kGroupRows, nrows - t0);
-      float m0 = fmaxf(fmaxf(c0.x, c0.y), fmaxf(c0.z, c0.w));
-      float m1 = fmaxf(fmaxf(c1.x, c1.y), fmaxf(c1.z, c1.w));
-      float m2 = fmaxf(fmaxf(c2.x, c2.y), fmaxf(c2.z, c2.w));
-      float m3 = fmaxf(fmaxf(c3.x, c3.y), fmaxf(c3.z, c3.w));
-      if (rows_here < kGroupRows) {  // last, partial group of the strip (warp-uniform): rows past it belong to the next strip
-        if (rows_here < 2) m1 = ninf;
-        if (rows_here < 3) m2 = ninf;
-        m3 = ninf;
+      // window rows of group row i are ring rows row0 + i .. row0 + i + 2R; its centre row is row0 + i + R
+      const u32 row0 = (n * kGroupRows) & kRowMask;
+      float4 c0, c1, c2, c3;
+      if (R == 2) {  // centres: the last two rows of this tile's slot, the first two of the next
+        const u32 a01 = ring_own + (row0 + 2) * kTilePitchB, a23 = ring_own + ((row0 + 4) & kRowMask) * kTilePitchB;
+        c0 = lds128(a01); c1 = lds128(a01 + kTilePitchB); c2 = lds128(a23); c3 = lds128(a23 + kTilePitchB);
+      } else {
+        const u32 a012 = ring_own + (row0 + 1) * kTilePitchB, a3 = ring_own + ((row0 + 4) & kRowMask) * kTilePitchB;
+        c0 = lds128(a012); c1 = lds128(a012 + kTilePitchB); c2 = lds128(a012 + 2 * kTilePitchB); c3 = lds128(a3);
       }
-      if (__any_sync(0xffffffffu, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) > st.floorx)) {
-        // Something in these four rows beats the floor.  Pixel-centric slow path: (1) the few pixels
-        // above the floor are compacted into a per-warp work list, (2) each lane then takes ONE listed
-        // pixel and settles it alone -- its own 5x5 window straight from the ring, the near-tie
-        // classification, the append.  Cost is per batch of <= 32 pixels, not per row of 128.
+      const int t0 = g * kGroupRows;
+      if (t0 + kGroupRows > nrows) {  // last, partial group of the strip (warp-uniform): rows past it belong to the next strip
+        const int rows_here = nrows - t0;
+        if (rows_here < 2) c1 = make_float4(ninf, ninf, ninf, ninf);
+        if (rows_here < 3) c2 = make_float4(ninf, ninf, ninf, ninf);
+        c3 = make_float4(ninf, ninf, ninf, ninf);
+      }
+      const float m01 = fmaxf(fmaxf(fmaxf(c0.x, c0.y), fmaxf(c0.z, c0.w)), fmaxf(fmaxf(c1.x, c1.y), fmaxf(c1.z, c1.w)));
+      const float m23 = fmaxf(fmaxf(fmaxf(c2.x, c2.y), fmaxf(c2.z, c2.w)), fmaxf(fmaxf(c3.x, c3.y), fmaxf(c3.z, c3.w)));
+      if (__any_sync(0xffffffffu, fmaxf(m01, m23) > st.floorx)) {
+        // Something in these four rows beats the floor.  Pixel-centric slow path: (1) every (row, lane)
+        // whose four centre pixels hold one above the floor goes on the warp's work list, one ballot
+        // per row, row-major; (2) settle_entries gives each listed pixel a lane of its own.
         const float floorx = st.floorx;
-        int nwork = 0;
-        const u32 lt = (1u << lane) - 1u;
+        int nent = 0;
 #pragma unroll
         for (int i = 0; i < kGroupRows; ++i) {
-          const float mi = i == 0 ? m0 : (i == 1 ? m1 : (i == 2 ? m2 : m3));
-          if (__any_sync(0xffffffffu, mi > floorx)) {  // warp-uniform
-            const float4 ci = i == 0 ? c0 : (i == 1 ? c1 : (i == 2 ? c2 : c3));
-            const u32 cm = (ci.x > floorx ? 1u : 0u) | (ci.y > floorx ? 2u : 0u) | (ci.z > floorx ? 4u : 0u) |
-                           (ci.w > floorx ? 8u : 0u);
-            const u32 cnt = __popc(cm);
-            const u32 b0 = __ballot_sync(0xffffffffu, cnt & 1u), b1 = __ballot_sync(0xffffffffu, cnt & 2u),
-                      b2 = __ballot_sync(0xffffffffu, cnt & 4u);
-            const int total = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
-            if (nwork + total > kWork) {  // rare (plateaus): settle what is listed so far
-              __syncwarp();
-              settle_pixels<R, kRows>(st, work, nwork, ring_s, t0, r_begin, W, panel * kPanelW, pre, buf, hist, minx, sf,
-                                      count_ptr, list, p.cap, K, lane, xscale, satx);
-              nwork = 0;
-            }
-            int pos = nwork + __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt);
-            const u32 tag = ((u32)i << 8) | (u32)(4 * lane);
-            if (cm & 1u) work[pos++] = (unsigned short)(tag + 0);
-            if (cm & 2u) work[pos++] = (unsigned short)(tag + 1);
-            if (cm & 4u) work[pos++] = (unsigned short)(tag + 2);
-            if (cm & 8u) work[pos++] = (unsigned short)(tag + 3);
-            nwork += total;
-          }
+          const float4 ci = i == 0 ? c0 : (i == 1 ? c1 : (i == 2 ? c2 : c3));
+          const bool mine = fmaxf(fmaxf(ci.x, ci.y), fmaxf(ci.z, ci.w)) > floorx;
+          const u32 bm = __ballot_sync(0xffffffffu, mine);
+          if (mine) work[nent + __popc(bm & lt)] = (unsigned char)((i << 5) | lane);
+          nent += __popc(bm);
         }
         __syncwarp();
-        settle_pixels<R, kRows>(st, work, nwork, ring_s, t0, r_begin, W, panel * kPanelW, pre, buf, hist, minx, sf,
-                                count_ptr, list, p.cap, K, lane, xscale, satx);
+        settle_entries<R>(st, work, nent, ring_s, row0, floorx, idx0, W, pre, buf, hist, minx, sf, count_ptr, list, p.cap,
+                          K, lane, xscale, satx);
+        // while the plane has no floor yet, publish early and often; later only in batches
+        if (st.nbuf >= 16 || (st.nbuf > 0 && gfloor_seen <= 0)) {
+          __syncwarp();
+          flush_candidates(st, buf, hist, minx, sf, count_ptr, list, p.cap, K, lane, pre, xscale, satx);
+        }
       }
-      // every lane's reads of tile g are consumed (the votes above): refill its slot with
-      // the tile NG ahead
+      // every lane's reads of the group's first tile are done (the votes above): refill its slot
+      // with the tile NG ahead
       __syncwarp();
       if (lane == 0 && g + NG < groups) {
-        const u32 slot = (u32)g % NG;
-        mbar_arrive_expect_tx(bars_s + 8 * slot, kTileBytes);
-        tma_tile_4d(ring_s + slot * kTileBytes, tmap, x0, y0 + kGroupRows * (g + NG), csel, b, bars_s + 8 * slot);
+        const u32 s = n & (NG - 1);
+        mbar_arrive_expect_tx(bars_s + 8 * s, kTileBytes);
+        tma_tile_4d(ring_s + s * kTileBytes, tmap, x0, y_next, csel, b, bars_s + 8 * s);
       }
-      // while the plane has no floor yet, publish early and often; later only in batches
-      if (st.nbuf >= 16 || (st.nbuf > 0 && gfloor_seen <= 0)) {
-        __syncwarp();
-        flush_candidates(st, buf, hist, minx, sf, count_ptr, list, p.cap, K, lane, pre, xscale, satx);
-      }
+      y_next += kGroupRows;
     }
+    tile_n += (u32)groups;
     if (st.nbuf) {
       __syncwarp();
       flush_candidates(st, buf, hist, minx, sf, count_ptr, list, p.cap, K, lane, pre, xscale, satx);
@@ -2075,13 +2089,7 @@ int launch_decode(const SdnetDecodeParams* p, cudaStream_t stream, cudaEvent_t* 
     pp.strips = (p->H + pp.rows_per_strip - 1) / pp.rows_per_strip;
   };
   if (use_tile) {
-    static const int tile_ng = [] {  // tuning knob, read once: SDNET_TILE_RING = 3 | 4
-      const char* e = getenv("SDNET_TILE_RING");
-      return (e && atoi(e) == 3) ? 3 : 4;
-    }();
-    auto kern = tile_ng == 3 ? (p->radius == 2 ? sdnet_peaks_tile_kernel<2, 3> : sdnet_peaks_tile_kernel<1, 3>)
-                             : (p->radius == 2 ? sdnet_peaks_tile_kernel<2, 4> : sdnet_peaks_tile_kernel<1, 4>);
-    const int kTileSmem = tile_smem(tile_ng);
+    auto kern = p->radius == 2 ? sdnet_peaks_tile_kernel<2> : sdnet_peaks_tile_kernel<1>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem);
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     static int per_sm = 0;
