@@ -1315,25 +1315,21 @@ sdnet_peaks_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_cons
         const u32 a012 = ring_own + (row0 + 1) * kTilePitchB, a3 = ring_own + ((row0 + 4) & kRowMask) * kTilePitchB;
         c0 = lds128(a012); c1 = lds128(a012 + kTilePitchB); c2 = lds128(a012 + 2 * kTilePitchB); c3 = lds128(a3);
       }
-      const int t0 = g * kGroupRows;
-      if (t0 + kGroupRows > nrows) {  // last, partial group of the strip (warp-uniform): rows past it belong to the next strip
-        const int rows_here = nrows - t0;
-        if (rows_here < 2) c1 = make_float4(ninf, ninf, ninf, ninf);
-        if (rows_here < 3) c2 = make_float4(ninf, ninf, ninf, ninf);
-        c3 = make_float4(ninf, ninf, ninf, ninf);
-      }
       const float m01 = fmaxf(fmaxf(fmaxf(c0.x, c0.y), fmaxf(c0.z, c0.w)), fmaxf(fmaxf(c1.x, c1.y), fmaxf(c1.z, c1.w)));
       const float m23 = fmaxf(fmaxf(fmaxf(c2.x, c2.y), fmaxf(c2.z, c2.w)), fmaxf(fmaxf(c3.x, c3.y), fmaxf(c3.z, c3.w)));
       if (__any_sync(0xffffffffu, fmaxf(m01, m23) > st.floorx)) {
         // Something in these four rows beats the floor.  Pixel-centric slow path: (1) every (row, lane)
         // whose four centre pixels hold one above the floor goes on the warp's work list, one ballot
         // per row, row-major; (2) settle_entries gives each listed pixel a lane of its own.
+        // In the last, partial group of a strip the rows past its end belong to the next strip: they
+        // may raise this alarm for nothing but are never listed.
         const float floorx = st.floorx;
+        const int rows_here = nrows - g * kGroupRows;
         int nent = 0;
 #pragma unroll
         for (int i = 0; i < kGroupRows; ++i) {
           const float4 ci = i == 0 ? c0 : (i == 1 ? c1 : (i == 2 ? c2 : c3));
-          const bool mine = fmaxf(fmaxf(ci.x, ci.y), fmaxf(ci.z, ci.w)) > floorx;
+          const bool mine = fmaxf(fmaxf(ci.x, ci.y), fmaxf(ci.z, ci.w)) > floorx && i < rows_here;
           const u32 bm = __ballot_sync(0xffffffffu, mine);
           if (mine) work[nent + __popc(bm & lt)] = (unsigned char)((i << 5) | lane);
           nent += __popc(bm);
@@ -1993,7 +1989,7 @@ EncodeTiledFn encode_tiled_fn() {
 }
 
 // (W, H, channels, B) fp32 view -> tensor map with a 136 x 4 x 1 x 1 box and NaN out-of-bounds fill
-bool make_tile_map(CUtensorMap* map, const SdnetTensor4& t, int B, int Cn, int H, int W) {
+bool make_tile_map(CUtensorMap* map, const SdnetTensor4& t, int B, int Cn, int H, int W, int box_rows = kGroupRows) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) return false;
   const cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Cn, (cuuint64_t)B};
@@ -2002,7 +1998,7 @@ bool make_tile_map(CUtensorMap* map, const SdnetTensor4& t, int B, int Cn, int H
   const cuuint64_t sc = Cn > 1 ? (cuuint64_t)t.stride_c * 4 : sh * (cuuint64_t)H;
   const cuuint64_t sb = B > 1 ? (cuuint64_t)t.stride_b * 4 : sc * (cuuint64_t)Cn;
   const cuuint64_t strides[3] = {sh, sc, sb};
-  const cuuint32_t box[4] = {(cuuint32_t)kTileCols, (cuuint32_t)kGroupRows, 1, 1};
+  const cuuint32_t box[4] = {(cuuint32_t)kTileCols, (cuuint32_t)box_rows, 1, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(t.data), dims, strides, box, estr,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
