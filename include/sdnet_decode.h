@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SDNET_ABI_VERSION 2
+#define SDNET_ABI_VERSION 3
 
 /* element types of the four input tensors */
 #define SDNET_DTYPE_F32 0
@@ -107,6 +107,15 @@ int sdnet_decode_workspace_bytes(int B, int M, int N, int H, int W, int K, int P
  * src/sdnet/utils/utils.py:355-361 clamped_sigmoid, 441-443 nms, 447-467 topk,
  * 347-351 transpose_and_gather, 422-437 hypot): heat maps -> packed detections. */
 int sdnet_decode_launch(const SdnetDecodeParams* params, void* stream);
+
+/* Which peaks kernel sdnet_decode_launch would run for these tensors (shape, strides, alignment, dtype,
+ * flags): one of SDNET_PATH_*, or a negative SDNET_E_*.  Host-only; launches nothing.  The kernels give
+ * identical results; tests use this to know which one they exercised. */
+#define SDNET_PATH_WARP 0           /* per-lane cp.async / converting feed: any shape, stride and alignment */
+#define SDNET_PATH_TILE 1           /* TMA tiles: base and strides multiples of 16 bytes, W % 4 == 0 */
+#define SDNET_PATH_TILE_ROW_PAIRS 2 /* TMA tiles over row pairs: fp16/bf16 with an 8-byte-multiple row pitch (W = 612), H even */
+#define SDNET_PATH_CTA 3            /* warp-specialised 1-D bulk copies (fp32; only with SDNET_PEAKS_PATH=cta) */
+int sdnet_decode_peaks_path(const SdnetDecodeParams* params);
 
 /* Profiling variant (bench.py's roofline leg): same work, but records CUDA events between the
  * three kernels on `stream`, WAITS for completion and returns the device time of each kernel in

@@ -13,7 +13,7 @@ import os as _os
 
 # SDNET_DECODE_LIB: load another build of the same library (kernel experiments, tools/xbuild.sh)
 LIB_PATH = Path(_os.environ.get("SDNET_DECODE_LIB") or Path(__file__).resolve().parent / "csrc" / "libsdnet_decode.so").resolve()
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 FLAG_PRE_ACTIVATED = 1
 FLAG_NO_GROUPING = 2
@@ -32,6 +32,7 @@ EXPORTS = (
     "sdnet_decode_workspace_bytes",
     "sdnet_decode_launch",
     "sdnet_decode_launch_timed",
+    "sdnet_decode_peaks_path",
     "sdnet_activate_launch",
     "sdnet_decode_host_launch",
 )
@@ -110,6 +111,8 @@ def load() -> ctypes.CDLL:
     lib.sdnet_decode_workspace_bytes.argtypes = [ctypes.c_int] * 8 + [ctypes.POINTER(ctypes.c_size_t)]
     lib.sdnet_decode_launch.restype = ctypes.c_int
     lib.sdnet_decode_launch.argtypes = [ctypes.POINTER(SdnetDecodeParams), ctypes.c_void_p]
+    lib.sdnet_decode_peaks_path.restype = ctypes.c_int
+    lib.sdnet_decode_peaks_path.argtypes = [ctypes.POINTER(SdnetDecodeParams)]
     lib.sdnet_decode_launch_timed.restype = ctypes.c_int
     lib.sdnet_decode_launch_timed.argtypes = [ctypes.POINTER(SdnetDecodeParams), ctypes.c_void_p,
                                               ctypes.POINTER(ctypes.c_float)]

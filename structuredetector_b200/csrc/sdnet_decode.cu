@@ -82,6 +82,7 @@ struct PeaksParams {
   // [0, tier1_planes); the remaining planes are cut into `strips` strips so that the last wave of
   // warps is filled with short units instead of idling behind a few long ones
   int tier1_units, tier1_planes;
+  int odd_x;               // tile kernel, row-pair maps: tensor-map x coordinate of an odd row's column 0
 };
 
 // Numerics of the score function per input dtype DT (SDNET_DTYPE_*).
@@ -1128,63 +1129,150 @@ constexpr int kTilePitchB = kTileCols * 4;                   // 544 B per ring r
 constexpr int kTileBytes = kGroupRows * kTilePitchB;         // 2176 B per TMA tile (17 x 128 B)
 constexpr int kTileWarps = 4;
 constexpr int kTileNG = 4;   // ring slots (tiles) per warp: 16 rows, two or three tiles in flight, 5 CTAs/SM
-constexpr int kWork = 128;   // per-warp work list: one byte per (row of the group, lane) whose four pixels hold one above the floor
-constexpr int kTileSmemPerWarp = ((kTileNG * kTileBytes + 32 + kBins * 8 + kBuf * 8 + kWork) + 127) / 128 * 128;
-constexpr int kTileSmem = kTileWarps * kTileSmemPerWarp;
+constexpr int kWork = 128;   // per-warp work list: one byte per (row of the group, lane) whose 16-byte word holds a pixel above the floor
+// S = rows per TMA row (see the kernel).  Under S = 2 a tile arrives as two 2-row boxes and a TMA
+// destination must be 128-byte aligned: the second box sits at +1152 and a slot takes 2304 bytes.
+__host__ __device__ constexpr int tile_slot_bytes(int S) { return S == 1 ? kTileBytes : 2304; }
+__host__ __device__ constexpr int tile_smem_per_warp(int S) {
+  return ((kTileNG * tile_slot_bytes(S) + 32 + kBins * 8 + kBuf * 8 + kWork) + 127) / 128 * 128;
+}
+__host__ __device__ constexpr int tile_smem(int S) { return kTileWarps * tile_smem_per_warp(S); }
+constexpr int kOddBoxOff = 1152;  // S = 2: offset of the odd rows' box inside a slot
+constexpr int kOddShiftB = 8;     // S = 2: a box must start on a 16-byte boundary of global memory and odd rows start 8 bytes
+                                  // off one, so their box starts 4 columns early and their pixels sit 8 bytes further right
+
+// Element geometry of the tile kernel.  A lane owns one 16-byte word per row: 4 fp32 or 8 fp16/bf16
+// pixels, so a warp's panel is 128 or 256 columns and a ring row is 544 bytes either way.
+template <int DT>
+struct TileGeom {
+  static constexpr int kPx = DT == SDNET_DTYPE_F32 ? 4 : 8;  // pixels per lane per row = halo columns each side
+  static constexpr int kEsz = 16 / kPx;                       // bytes per element
+  static constexpr int kPanel = 32 * kPx;                     // columns per warp
+  static constexpr int kCols = kPanel + 2 * kPx;              // columns per tile row
+};
+static_assert(TileGeom<SDNET_DTYPE_F32>::kCols * 4 == kTilePitchB && TileGeom<SDNET_DTYPE_F16>::kCols * 2 == kTilePitchB, "ring row pitch");
 
 __device__ __forceinline__ void tma_tile_4d(u32 dst, const CUtensorMap* map, int x, int y, int c, int b, u32 bar) {
   asm volatile(
       "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
       ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(c), "r"(b), "r"(bar) : "memory");
 }
+__device__ __forceinline__ uint4 lds64x2(u32 addr) {  // 16 bytes from an 8-byte-aligned address
+  uint4 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.z), "=r"(v.w) : "r"(addr + 8));
+  return v;
+}
+__device__ __forceinline__ uint4 lds128u(u32 addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
 
-// Settle the work list of one 4-row group.  Entry e = (row in group << 5) | lane names one float4
-// of centre pixels holding at least one pixel above the floor; four consecutive lanes take the four
+// max of the 4 | 8 elements of one 16-byte word / of four words, as float; NaN elements (the TMA
+// out-of-bounds fill) are ignored by fmaxf and by max.f16x2 / max.bf16x2 alike
+template <int DT>
+struct TileMax;
+template <>
+struct TileMax<SDNET_DTYPE_F32> {
+  static __device__ __forceinline__ float word(const uint4& a) {
+    return fmaxf(fmaxf(__uint_as_float(a.x), __uint_as_float(a.y)), fmaxf(__uint_as_float(a.z), __uint_as_float(a.w)));
+  }
+  static __device__ __forceinline__ float group(const uint4& a, const uint4& b, const uint4& c, const uint4& d) {
+    return fmaxf(fmaxf(word(a), word(b)), fmaxf(word(c), word(d)));
+  }
+  static __device__ __forceinline__ float elem(u32 addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+  }
+};
+template <>
+struct TileMax<SDNET_DTYPE_F16> {
+  static __device__ __forceinline__ __half2 h2(u32 v) { return *reinterpret_cast<const __half2*>(&v); }
+  static __device__ __forceinline__ __half2 word2(const uint4& a) { return __hmax2(__hmax2(h2(a.x), h2(a.y)), __hmax2(h2(a.z), h2(a.w))); }
+  static __device__ __forceinline__ float fold(__half2 m) { return __half2float(__hmax(__low2half(m), __high2half(m))); }
+  static __device__ __forceinline__ float word(const uint4& a) { return fold(word2(a)); }
+  static __device__ __forceinline__ float group(const uint4& a, const uint4& b, const uint4& c, const uint4& d) {
+    return fold(__hmax2(__hmax2(word2(a), word2(b)), __hmax2(word2(c), word2(d))));
+  }
+  static __device__ __forceinline__ float elem(u32 addr) {
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+    return __half2float(__ushort_as_half(v));
+  }
+};
+template <>
+struct TileMax<SDNET_DTYPE_BF16> {
+  static __device__ __forceinline__ __nv_bfloat162 h2(u32 v) { return *reinterpret_cast<const __nv_bfloat162*>(&v); }
+  static __device__ __forceinline__ __nv_bfloat162 word2(const uint4& a) { return __hmax2(__hmax2(h2(a.x), h2(a.y)), __hmax2(h2(a.z), h2(a.w))); }
+  static __device__ __forceinline__ float fold(__nv_bfloat162 m) { return __bfloat162float(__hmax(__low2bfloat16(m), __high2bfloat16(m))); }
+  static __device__ __forceinline__ float word(const uint4& a) { return fold(word2(a)); }
+  static __device__ __forceinline__ float group(const uint4& a, const uint4& b, const uint4& c, const uint4& d) {
+    return fold(__hmax2(__hmax2(word2(a), word2(b)), __hmax2(word2(c), word2(d))));
+  }
+  static __device__ __forceinline__ float elem(u32 addr) {
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+    return __uint_as_float((u32)v << 16);
+  }
+};
+
+// Byte offset of ring row rr (0..15) inside the ring.  S = 1: rows in order.  S = 2 (rows loaded as
+// even/odd pairs, see the kernel): a slot holds rows 0, 2 at +0, +544 and rows 1, 3 at +1152, +1696,
+// the odd rows shifted right by kOddShiftB bytes.
+template <int S>
+__device__ __forceinline__ u32 ring_row_off(u32 rr) {
+  if (S == 1) return rr * kTilePitchB;
+  return (rr >> 2) * tile_slot_bytes(2) + (rr & 1u) * (kOddBoxOff + kOddShiftB) + ((rr >> 1) & 1u) * kTilePitchB;
+}
+
+// Settle the work list of one 4-row group.  Entry e = (row in group << 5) | lane names one 16-byte
+// word of centre pixels holding at least one pixel above the floor; kPx consecutive lanes take the
 // pixels of an entry, so records leave in (row, column) = index order.  A lane whose pixel beats the
 // floor reads the pixel's (2R+1)^2 window from the ring with scalar loads (columns and rows outside
-// the image were filled with NaN by the TMA unit and are ignored by fmaxf), classifies it like
-// classify_row and appends a (logit, index) record to the warp's candidate buffer.
+// the image hold NaN or -inf and never win a max), classifies it like classify_row and appends a
+// (logit, index) record to the warp's candidate buffer.
 // `row0` = ring row of the window's first row for group row 0 (the centre is R rows further).
-template <int R>
+template <int R, int DT, int S>
 __device__ __forceinline__ void settle_entries(UnitState& st, const unsigned char* work, int nent, u32 ring_s, u32 row0,
                                                float floorx, u32 idx0, int W, bool pre, u64* buf, u32* hist, int* minx,
                                                const SharedFloors& sf, int* count_ptr, u64* __restrict__ list, int cap,
                                                int K, int lane, float xscale, float satx) {
-  constexpr float kNearTie = Num<SDNET_DTYPE_F32>::kNear, kHiZone = Num<SDNET_DTYPE_F32>::kHi,
-                  kLoZone = Num<SDNET_DTYPE_F32>::kLo, kNearTie2 = Num<SDNET_DTYPE_F32>::kNear2,
-                  kHiZone2 = Num<SDNET_DTYPE_F32>::kHi2;
+  constexpr float kNearTie = Num<DT>::kNear, kHiZone = Num<DT>::kHi, kLoZone = Num<DT>::kLo, kNearTie2 = Num<DT>::kNear2,
+                  kHiZone2 = Num<DT>::kHi2;
   constexpr u32 kRowMask = kTileNG * kGroupRows - 1;
-  const int nslots = 4 * nent;
+  constexpr int kPx = TileGeom<DT>::kPx, kEsz = TileGeom<DT>::kEsz;
+  const int nslots = kPx * nent;
   for (int base = 0; base < nslots; base += 32) {  // warp-uniform
     const int slot = base + lane;
-    const u32 e = slot < nslots ? work[slot >> 2] : 0u;
-    const u32 i = e >> 5, colp = 4 * (e & 31u) + (u32)(slot & 3);
-    const u32 col_addr = ring_s + (4 + colp - R) * 4;  // first column of the window
-    float x;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(col_addr + 4 * R + ((row0 + i + R) & kRowMask) * kTilePitchB));
+    const u32 e = slot < nslots ? work[slot / kPx] : 0u;
+    const u32 i = e >> 5, colp = kPx * (e & 31u) + (u32)(slot % kPx);
+    const u32 col_addr = ring_s + (kPx + colp - R) * kEsz;  // first column of the window
+    const float x = TileMax<DT>::elem(col_addr + R * kEsz + ring_row_off<S>((row0 + i + R) & kRowMask));
     bool keep = slot < nslots && x > floorx;
     if (keep && !pre) {
       float h = x;
 #pragma unroll
       for (int d = 0; d <= 2 * R; ++d) {
-        const u32 a = col_addr + ((row0 + i + d) & kRowMask) * kTilePitchB;
+        const u32 a = col_addr + ring_row_off<S>((row0 + i + d) & kRowMask);
         float v[2 * R + 1];
 #pragma unroll
-        for (int q = 0; q <= 2 * R; ++q) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[q]) : "r"(a + 4 * q));
+        for (int q = 0; q <= 2 * R; ++q) v[q] = TileMax<DT>::elem(a + kEsz * q);
 #pragma unroll
         for (int q = 0; q <= 2 * R; ++q) h = fmaxf(h, v[q]);
       }
       if (x != h) {
         const bool amb = (x >= h - kNearTie) || (h > kHiZone && x >= h - kNearTie2) ||
                          (h > kHiZone2 && x > kHiZone2 - 1.0f) || (h < kLoZone);  // same zones as classify_row
-        keep = amb && Num<SDNET_DTYPE_F32>::act(x) == Num<SDNET_DTYPE_F32>::act(h);  // rare
+        keep = amb && Num<DT>::act(x) == Num<DT>::act(h);  // rare
       }
     }
     const u32 m = __ballot_sync(0xffffffffu, keep);
     if (m) {  // warp-uniform
       if (st.nbuf + __popc(m) > kBuf) {
         __syncwarp();
-        flush_candidates(st, buf, hist, minx, sf, count_ptr, list, cap, K, lane, pre, xscale, satx);
+        flush_candidates<DT>(st, buf, hist, minx, sf, count_ptr, list, cap, K, lane, pre, xscale, satx);
       }
       if (keep) buf[st.nbuf + __popc(m & ((1u << lane) - 1u))] = ((u64)__float_as_uint(x) << 32) | (idx0 + i * (u32)W + colp);
       st.nbuf += __popc(m);
@@ -1192,21 +1280,62 @@ __device__ __forceinline__ void settle_entries(UnitState& st, const unsigned cha
   }
 }
 
-template <int R>
+// S = 2 only: a tile that touches the left or right image edge has read across a row boundary (see
+// the kernel): overwrite what is not this row's data with -inf.  `slot_s` = the tile's ring slot.
+template <int DT>
+__device__ __forceinline__ void tile_fix_edges(u32 slot_s, int x0, int W, int lane) {
+  constexpr int kPx = TileGeom<DT>::kPx;
+  constexpr u32 kNinf2 = DT == SDNET_DTYPE_F16 ? 0xFC00FC00u : (DT == SDNET_DTYPE_BF16 ? 0xFF80FF80u : 0xFF800000u);
+  if (x0 < 0) {  // odd rows (the second box): the 12 columns left of column 0 hold the end of the row above
+    if (lane < 2) {
+      const u32 a = slot_s + kOddBoxOff + lane * kTilePitchB;
+      asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(a), "r"(kNinf2) : "memory");
+      asm volatile("st.shared.v2.u32 [%0], {%1, %1};" ::"r"(a + 16), "r"(kNinf2) : "memory");
+    }
+  }
+  if (x0 + TileGeom<DT>::kCols > W) {  // even rows (the first box): columns >= W hold the start of the row below
+    // word w of a ring row covers columns x0 + kPx w ..; under S = 2 W is a multiple of kPx/2, not of kPx
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int w = k == 0 ? lane + 1 : 33;  // lane's own centre word; lane 31 also takes the right halo word
+      if (k == 1 && lane != 31) break;
+      const int first = x0 + kPx * w;
+      const u32 a = slot_s + 16 * w;
+      if (first >= W) {
+        asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(a), "r"(kNinf2) : "memory");
+        asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(a + kTilePitchB), "r"(kNinf2) : "memory");
+      } else if (first + kPx / 2 >= W) {
+        asm volatile("st.shared.v2.u32 [%0], {%1, %1};" ::"r"(a + 8), "r"(kNinf2) : "memory");
+        asm volatile("st.shared.v2.u32 [%0], {%1, %1};" ::"r"(a + 8 + kTilePitchB), "r"(kNinf2) : "memory");
+      }
+    }
+  }
+}
+
+// S = rows per TMA row: 1 when the row pitch is a multiple of 16 bytes.  S = 2 serves fp16/bf16 maps
+// whose pitch is an odd multiple of 8 bytes (W = 612): the tensor map then describes PAIRS of image
+// rows as one row of pitch + W elements, a tile is two 2-row boxes -- the even rows at x, the odd rows
+// at pitch + x - 4 (a box has to start on a 16-byte boundary, measured: anything else is an illegal
+// instruction) -- and lands in its slot as rows 0, 2 | 1, 3 with the odd rows 8 bytes further right.
+// At the image edges such a box reads across the row boundary; tile_fix_edges repairs that after the wait.
+template <int R, int DT, int S>
 __global__ void __launch_bounds__(kTileWarps * 32, 5)
 sdnet_peaks_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_constant__ CUtensorMap tm_anchor,
                         const __grid_constant__ CUtensorMap tm_part) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int NG = kTileNG;
   constexpr u32 kRowMask = NG * kGroupRows - 1;
+  constexpr int kPx = TileGeom<DT>::kPx, kPanel = TileGeom<DT>::kPanel;
   static_assert((NG & (NG - 1)) == 0, "slot and parity of a tile come from its running number by mask and shift");
+  static_assert(S == 1 || (R == 2 && DT != SDNET_DTYPE_F32), "row pairs: tiles must start on an even row");
   pdl_launch_dependents();
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  unsigned char* wbase = smem_raw + (size_t)warp * kTileSmemPerWarp;
+  constexpr u32 kSlotB = tile_slot_bytes(S);
+  unsigned char* wbase = smem_raw + (size_t)warp * tile_smem_per_warp(S);
   const u32 ring_s = smem_u32(wbase);
-  const u32 bars_s = ring_s + NG * kTileBytes;
-  u32* hist = reinterpret_cast<u32*>(wbase + NG * kTileBytes + 32);
+  const u32 bars_s = ring_s + NG * kSlotB;
+  u32* hist = reinterpret_cast<u32*>(wbase + NG * kSlotB + 32);
   int* minx = reinterpret_cast<int*>(hist + kBins);
   u64* buf = reinterpret_cast<u64*>(minx + kBins);
   unsigned char* work = reinterpret_cast<unsigned char*>(buf + kBuf);
@@ -1215,9 +1344,8 @@ sdnet_peaks_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_cons
   const float satx = pre ? CUDART_INF_F : kSatX;
   const int C = p.M + p.N;
   const int H = p.H, W = p.W;
-  const u32 ring_own = ring_s + (u32)(4 + 4 * lane) * 4;
+  const u32 ring_own = ring_s + (u32)(16 + 16 * lane);  // this lane's word inside a ring row
   const u32 lt = (1u << lane) - 1u;
-  const float ninf = -CUDART_INF_F;
 
   if (lane == 0) {
     for (int i = 0; i < NG; ++i) mbar_init(bars_s + 8 * i, 1);
@@ -1253,7 +1381,9 @@ sdnet_peaks_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_cons
     const CUtensorMap* tmap = is_anchor ? &tm_anchor : &tm_part;
     const int csel = is_anchor ? c : c - p.M;
     const int K = is_anchor ? p.K : p.P;
-    const int x0 = panel * kPanelW - 4;
+    const int x0 = panel * kPanel - kPx;  // first column of the tile; tensor-map coordinates count 4-byte units
+    const int xc = DT == SDNET_DTYPE_F32 ? x0 : x0 >> 1;
+    const bool edge = S == 2 && (x0 < 0 || x0 + TileGeom<DT>::kCols > W);
     const int nrows = r_end - r_begin;
     const int groups = (nrows + 2 * R + kGroupRows - 1) / kGroupRows;  // tiles of the unit
     const int groups_out = (nrows + kGroupRows - 1) / kGroupRows;
@@ -1266,7 +1396,7 @@ sdnet_peaks_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_cons
     sf.gfloor = gfloor_ptr;
 
     UnitState st;
-    st.floorx = shared_floor(__ldcg(gfloor_ptr), xscale);
+    st.floorx = shared_floor<DT>(__ldcg(gfloor_ptr), xscale);
 #ifdef SDNET_X_NOSLOW  // timing experiment only: stream the planes, never take the slow path
     st.floorx = CUDART_INF_F;
 #endif
@@ -1278,49 +1408,62 @@ sdnet_peaks_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_cons
     __syncwarp();
 
     // tile k of the unit = image rows r_begin - R + 4k ..; running number tile_n + k
+    auto issue = [&](u32 s, int y) {  // lane 0: pull the tile whose first image row is y into slot s
+      mbar_arrive_expect_tx(bars_s + 8 * s, kTileBytes);
+      if (S == 1) {
+        tma_tile_4d(ring_s + s * kSlotB, tmap, xc, y, csel, b, bars_s + 8 * s);
+      } else {  // y is even (r_begin even, R = 2): rows y, y+2 then rows y+1, y+3
+        tma_tile_4d(ring_s + s * kSlotB, tmap, xc, y >> 1, csel, b, bars_s + 8 * s);
+        tma_tile_4d(ring_s + s * kSlotB + kOddBoxOff, tmap, xc + p.odd_x - kOddShiftB / 4, y >> 1, csel, b, bars_s + 8 * s);
+      }
+    };
+    auto wait_tile = [&](u32 n) {
+      mbar_wait(bars_s + 8 * (n & (NG - 1)), (n >> 2) & 1u);
+      if (edge) {  // warp-uniform
+        tile_fix_edges<DT>(ring_s + (n & (NG - 1)) * kSlotB, x0, W, lane);
+        __syncwarp();
+      }
+    };
     int y_next = r_begin - R;  // first image row of the next tile to issue
     if (lane == 0) {
       const int first = min(NG, groups);
-      for (int k = 0; k < first; ++k) {
-        const u32 s = (tile_n + (u32)k) & (NG - 1);
-        mbar_arrive_expect_tx(bars_s + 8 * s, kTileBytes);
-        tma_tile_4d(ring_s + s * kTileBytes, tmap, x0, y_next + kGroupRows * k, csel, b, bars_s + 8 * s);
-      }
+      for (int k = 0; k < first; ++k) issue((tile_n + (u32)k) & (NG - 1), y_next + kGroupRows * k);
     }
     y_next += kGroupRows * NG;
     int gfloor_seen = 0;
     const int poll_mask = nrows <= 160 ? 0 : 3;
-    u32 idx0 = (u32)(r_begin * W + panel * kPanelW);  // flat index of the group's row 0, panel column 0
-    mbar_wait(bars_s + 8 * (tile_n & (NG - 1)), (tile_n >> 2) & 1u);
+    u32 idx0 = (u32)(r_begin * W + panel * kPanel);  // flat index of the group's row 0, panel column 0
+    wait_tile(tile_n);
     for (int g = 0; g < groups_out; ++g, idx0 += (u32)(kGroupRows * W)) {
       const u32 n = tile_n + (u32)g;  // tile holding the group's first window row
-      if (R == 2 || g + 1 < groups) {
-        const u32 n1 = n + 1;
-        mbar_wait(bars_s + 8 * (n1 & (NG - 1)), (n1 >> 2) & 1u);
-      }
+      if (R == 2 || g + 1 < groups) wait_tile(n + 1);
       if ((g & poll_mask) == 0) {
         // every 16 rows (every 4 in short strips): apply the plane-wide floor fetched one period ago
         // and start the next fetch.  The load writes straight into the register it will be read
         // from a period later, so its latency is never waited for.
-        st.floorx = fmaxf(st.floorx, shared_floor(gfloor_seen, xscale));
+        st.floorx = fmaxf(st.floorx, shared_floor<DT>(gfloor_seen, xscale));
         asm volatile("ld.global.cg.s32 %0, [%1];" : "=r"(gfloor_seen) : "l"(gfloor_ptr) : "memory");
       }
       // window rows of group row i are ring rows row0 + i .. row0 + i + 2R; its centre row is row0 + i + R
       const u32 row0 = (n * kGroupRows) & kRowMask;
-      float4 c0, c1, c2, c3;
-      if (R == 2) {  // centres: the last two rows of this tile's slot, the first two of the next
-        const u32 a01 = ring_own + (row0 + 2) * kTilePitchB, a23 = ring_own + ((row0 + 4) & kRowMask) * kTilePitchB;
-        c0 = lds128(a01); c1 = lds128(a01 + kTilePitchB); c2 = lds128(a23); c3 = lds128(a23 + kTilePitchB);
-      } else {
+      uint4 c0, c1, c2, c3;
+      if (R == 2) {  // centres: rows 2, 3 of this tile's slot and rows 0, 1 of the next
+        const u32 a01 = ring_own + (n & (NG - 1)) * kSlotB, a23 = ring_own + ((n + 1) & (NG - 1)) * kSlotB;
+        if (S == 1) {
+          c0 = lds128u(a01 + 2 * kTilePitchB); c1 = lds128u(a01 + 3 * kTilePitchB);
+          c2 = lds128u(a23); c3 = lds128u(a23 + kTilePitchB);
+        } else {  // a slot holds rows 0, 2 in its first box and rows 1, 3 in its second
+          c0 = lds128u(a01 + kTilePitchB); c1 = lds64x2(a01 + kOddBoxOff + kOddShiftB + kTilePitchB);
+          c2 = lds128u(a23); c3 = lds64x2(a23 + kOddBoxOff + kOddShiftB);
+        }
+      } else {  // S == 1
         const u32 a012 = ring_own + (row0 + 1) * kTilePitchB, a3 = ring_own + ((row0 + 4) & kRowMask) * kTilePitchB;
-        c0 = lds128(a012); c1 = lds128(a012 + kTilePitchB); c2 = lds128(a012 + 2 * kTilePitchB); c3 = lds128(a3);
+        c0 = lds128u(a012); c1 = lds128u(a012 + kTilePitchB); c2 = lds128u(a012 + 2 * kTilePitchB); c3 = lds128u(a3);
       }
-      const float m01 = fmaxf(fmaxf(fmaxf(c0.x, c0.y), fmaxf(c0.z, c0.w)), fmaxf(fmaxf(c1.x, c1.y), fmaxf(c1.z, c1.w)));
-      const float m23 = fmaxf(fmaxf(fmaxf(c2.x, c2.y), fmaxf(c2.z, c2.w)), fmaxf(fmaxf(c3.x, c3.y), fmaxf(c3.z, c3.w)));
-      if (__any_sync(0xffffffffu, fmaxf(m01, m23) > st.floorx)) {
+      if (__any_sync(0xffffffffu, TileMax<DT>::group(c0, c1, c2, c3) > st.floorx)) {
         // Something in these four rows beats the floor.  Pixel-centric slow path: (1) every (row, lane)
-        // whose four centre pixels hold one above the floor goes on the warp's work list, one ballot
-        // per row, row-major; (2) settle_entries gives each listed pixel a lane of its own.
+        // whose word of centre pixels holds one above the floor goes on the warp's work list, one
+        // ballot per row, row-major; (2) settle_entries gives each listed pixel a lane of its own.
         // In the last, partial group of a strip the rows past its end belong to the next strip: they
         // may raise this alarm for nothing but are never listed.
         const float floorx = st.floorx;
@@ -1328,35 +1471,34 @@ sdnet_peaks_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_cons
         int nent = 0;
 #pragma unroll
         for (int i = 0; i < kGroupRows; ++i) {
-          const float4 ci = i == 0 ? c0 : (i == 1 ? c1 : (i == 2 ? c2 : c3));
-          const bool mine = fmaxf(fmaxf(ci.x, ci.y), fmaxf(ci.z, ci.w)) > floorx && i < rows_here;
+          const uint4 ci = i == 0 ? c0 : (i == 1 ? c1 : (i == 2 ? c2 : c3));
+          const bool mine = TileMax<DT>::word(ci) > floorx && i < rows_here;
           const u32 bm = __ballot_sync(0xffffffffu, mine);
           if (mine) work[nent + __popc(bm & lt)] = (unsigned char)((i << 5) | lane);
           nent += __popc(bm);
         }
         __syncwarp();
-        settle_entries<R>(st, work, nent, ring_s, row0, floorx, idx0, W, pre, buf, hist, minx, sf, count_ptr, list, p.cap,
-                          K, lane, xscale, satx);
+        settle_entries<R, DT, S>(st, work, nent, ring_s, row0, floorx, idx0, W, pre, buf, hist, minx, sf, count_ptr, list,
+                                 p.cap, K, lane, xscale, satx);
         // while the plane has no floor yet, publish early and often; later only in batches
         if (st.nbuf >= 16 || (st.nbuf > 0 && gfloor_seen <= 0)) {
           __syncwarp();
-          flush_candidates(st, buf, hist, minx, sf, count_ptr, list, p.cap, K, lane, pre, xscale, satx);
+          flush_candidates<DT>(st, buf, hist, minx, sf, count_ptr, list, p.cap, K, lane, pre, xscale, satx);
         }
       }
       // every lane's reads of the group's first tile are done (the votes above): refill its slot
       // with the tile NG ahead
       __syncwarp();
       if (lane == 0 && g + NG < groups) {
-        const u32 s = n & (NG - 1);
-        mbar_arrive_expect_tx(bars_s + 8 * s, kTileBytes);
-        tma_tile_4d(ring_s + s * kTileBytes, tmap, x0, y_next, csel, b, bars_s + 8 * s);
+        if (edge) fence_proxy_async();  // the slot was patched with ordinary stores
+        issue(n & (NG - 1), y_next);
       }
       y_next += kGroupRows;
     }
     tile_n += (u32)groups;
     if (st.nbuf) {
       __syncwarp();
-      flush_candidates(st, buf, hist, minx, sf, count_ptr, list, p.cap, K, lane, pre, xscale, satx);
+      flush_candidates<DT>(st, buf, hist, minx, sf, count_ptr, list, p.cap, K, lane, pre, xscale, satx);
     }
   }
 }
@@ -1988,21 +2130,74 @@ EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
-// (W, H, channels, B) fp32 view -> tensor map with a 136 x 4 x 1 x 1 box and NaN out-of-bounds fill
-bool make_tile_map(CUtensorMap* map, const SdnetTensor4& t, int B, int Cn, int H, int W, int box_rows = kGroupRows) {
+// How the tile kernel can read a view: 0 = not at all (take the per-lane kernel), 1 = plain rows (pitch
+// a multiple of 16 bytes), 2 = row pairs (fp16/bf16 with an 8-byte-multiple pitch, e.g. W = 612).
+int tile_rows_per_tma_row(const SdnetTensor4& t, int dtype, int H, int W, int radius) {
+  const int px = dtype == SDNET_DTYPE_F32 ? 4 : 8;  // elements per 16 bytes
+  if ((uintptr_t)t.data % 16 != 0 || t.stride_b % px != 0 || t.stride_c % px != 0 || t.stride_h < W || W % 4 != 0) return 0;
+  if (t.stride_h % px == 0) return 1;
+  if (dtype != SDNET_DTYPE_F32 && t.stride_h % 8 == 4 && H % 2 == 0 && radius == 2) return 2;
+  return 0;
+}
+
+// (W, H, channels, B) view -> tensor map with a (128|256 + halo) x 4 x 1 x 1 box and NaN out-of-bounds
+// fill; rows_per_tma_row = 2: (pitch + W, H/2, channels, B) with a 2-row box (see the tile kernel)
+bool make_tile_map(CUtensorMap* map, const SdnetTensor4& t, int dtype, int B, int Cn, int H, int W, int rows_per_tma_row) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) return false;
-  const cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Cn, (cuuint64_t)B};
+  // A box side is limited to 256 elements and a fp16/bf16 tile row has 272, so those maps describe
+  // PAIRS of elements as one 32-bit float.  Every stride and W are even there, coordinates are halved
+  // in the kernel, and the out-of-bounds fill of a float32 map -- measured 0x7FF77FF7 on B200
+  // (tools/probes/tma_fill.cu) -- reads as two NaNs in fp16 and in bf16 alike.
+  const cuuint64_t esz = dtype == SDNET_DTYPE_F32 ? 4 : 2, per = 4 / esz;
+  const int S = rows_per_tma_row;
+  const cuuint64_t dims[4] = {(cuuint64_t)(S == 1 ? W : t.stride_h + W) / per, (cuuint64_t)(H / S), (cuuint64_t)Cn, (cuuint64_t)B};
   // strides of size-1 dimensions are arbitrary in torch: make them canonical
-  const cuuint64_t sh = (cuuint64_t)t.stride_h * 4;
-  const cuuint64_t sc = Cn > 1 ? (cuuint64_t)t.stride_c * 4 : sh * (cuuint64_t)H;
-  const cuuint64_t sb = B > 1 ? (cuuint64_t)t.stride_b * 4 : sc * (cuuint64_t)Cn;
-  const cuuint64_t strides[3] = {sh, sc, sb};
-  const cuuint32_t box[4] = {(cuuint32_t)kTileCols, (cuuint32_t)box_rows, 1, 1};
+  const cuuint64_t sh = (cuuint64_t)t.stride_h * esz;
+  const cuuint64_t sc = Cn > 1 ? (cuuint64_t)t.stride_c * esz : sh * (cuuint64_t)H;
+  const cuuint64_t sb = B > 1 ? (cuuint64_t)t.stride_b * esz : sc * (cuuint64_t)Cn;
+  const cuuint64_t strides[3] = {sh * S, sc, sb};
+  const cuuint32_t box[4] = {(cuuint32_t)(kTilePitchB / 4), (cuuint32_t)(kGroupRows / S), 1, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(t.data), dims, strides, box, estr,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA) == CUDA_SUCCESS;
+}
+
+// the tile kernel instantiation for (radius, dtype, rows per TMA row)
+typedef void (*TileKernel)(const PeaksParams, const CUtensorMap, const CUtensorMap);
+TileKernel tile_kernel_for(int radius, int dtype, int S) {
+  if (dtype == SDNET_DTYPE_F32) return radius == 2 ? sdnet_peaks_tile_kernel<2, SDNET_DTYPE_F32, 1> : sdnet_peaks_tile_kernel<1, SDNET_DTYPE_F32, 1>;
+  if (dtype == SDNET_DTYPE_F16) {
+    if (S == 2) return sdnet_peaks_tile_kernel<2, SDNET_DTYPE_F16, 2>;
+    return radius == 2 ? sdnet_peaks_tile_kernel<2, SDNET_DTYPE_F16, 1> : sdnet_peaks_tile_kernel<1, SDNET_DTYPE_F16, 1>;
+  }
+  if (S == 2) return sdnet_peaks_tile_kernel<2, SDNET_DTYPE_BF16, 2>;
+  return radius == 2 ? sdnet_peaks_tile_kernel<2, SDNET_DTYPE_BF16, 1> : sdnet_peaks_tile_kernel<1, SDNET_DTYPE_BF16, 1>;
+}
+
+// Which peaks kernel a decode of these tensors runs (SDNET_PATH_*), encoding the tensor maps on the way.
+int select_peaks_path(const SdnetDecodeParams* p, CUtensorMap* tm_anchor, CUtensorMap* tm_part, int* tile_s_out) {
+  static const int path_override = [] {  // tuning knob, read once: SDNET_PEAKS_PATH = tile | cta | warp
+    const char* e = getenv("SDNET_PEAKS_PATH");
+    if (!e) return 0;
+    return e[0] == 't' ? 1 : (e[0] == 'c' ? 2 : (e[0] == 'w' ? 3 : 0));
+  }();
+  if ((p->flags & SDNET_FLAG_WARP_KERNEL) || path_override == 3) return SDNET_PATH_WARP;
+  const bool is_f32 = p->dtype == SDNET_DTYPE_F32;  // the warp-specialised kernel is fp32-only
+  int tile_s = tile_rows_per_tma_row(p->anchor_hm, p->dtype, p->H, p->W, p->radius);
+  if (tile_s != tile_rows_per_tma_row(p->part_hm, p->dtype, p->H, p->W, p->radius) ||
+      (tile_s == 2 && p->anchor_hm.stride_h != p->part_hm.stride_h))
+    tile_s = 0;
+  if (tile_s != 0 && path_override != 2 &&
+      make_tile_map(tm_anchor, p->anchor_hm, p->dtype, p->B, p->M, p->H, p->W, tile_s) &&
+      make_tile_map(tm_part, p->part_hm, p->dtype, p->B, p->N, p->H, p->W, tile_s)) {
+    *tile_s_out = tile_s;
+    return tile_s == 2 ? SDNET_PATH_TILE_ROW_PAIRS : SDNET_PATH_TILE;
+  }
+  const bool aligned = view_aligned(p->anchor_hm, p->W) && view_aligned(p->part_hm, p->W);
+  if (is_f32 && aligned && p->W <= kPanelW * kMaxConsumers) return SDNET_PATH_CTA;
+  return SDNET_PATH_WARP;
 }
 
 template <typename Kern>
@@ -2052,21 +2247,12 @@ int launch_decode(const SdnetDecodeParams* p, cudaStream_t stream, cudaEvent_t* 
   pp.tier1_units = 0;
   pp.tier1_planes = 0;
   const int sms = device_sm_count();
-  const bool aligned = view_aligned(p->anchor_hm, p->W) && view_aligned(p->part_hm, p->W);
-  static const int path_override = [] {  // tuning knob, read once: SDNET_PEAKS_PATH = tile | cta | warp
-    const char* e = getenv("SDNET_PEAKS_PATH");
-    if (!e) return 0;
-    return e[0] == 't' ? 1 : (e[0] == 'c' ? 2 : (e[0] == 'w' ? 3 : 0));
-  }();
   CUtensorMap tm_anchor, tm_part;
-  const bool is_f32 = p->dtype == SDNET_DTYPE_F32;  // the TMA kernels are fp32-only; fp16/bf16 take the converting feed
-  bool use_tile = is_f32 && aligned && !(p->flags & SDNET_FLAG_WARP_KERNEL) && path_override != 2 && path_override != 3 &&
-                  (long long)p->anchor_hm.stride_h * 4 >= (long long)p->W * 4;
-  if (use_tile)
-    use_tile = make_tile_map(&tm_anchor, p->anchor_hm, p->B, p->M, p->H, p->W) &&
-               make_tile_map(&tm_part, p->part_hm, p->B, p->N, p->H, p->W);
-  const bool use_cta = is_f32 && !use_tile && aligned && p->W <= kPanelW * kMaxConsumers && !(p->flags & SDNET_FLAG_WARP_KERNEL) &&
-                       path_override != 3;
+  int tile_s = 0;
+  const int path = select_peaks_path(p, &tm_anchor, &tm_part, &tile_s);
+  const bool use_tile = path == SDNET_PATH_TILE || path == SDNET_PATH_TILE_ROW_PAIRS, use_cta = path == SDNET_PATH_CTA;
+  const bool is_f32 = p->dtype == SDNET_DTYPE_F32;
+  pp.odd_x = (int)(p->anchor_hm.stride_h / (is_f32 ? 1 : 2));  // in tensor-map elements
   static const int tier2_strips = [] {  // tuning knob, read once: SDNET_TIER2_STRIPS = n (default 2)
     const char* e = getenv("SDNET_TIER2_STRIPS");
     return e && atoi(e) > 0 ? atoi(e) : 2;
@@ -2082,17 +2268,21 @@ int launch_decode(const SdnetDecodeParams* p, cudaStream_t stream, cudaEvent_t* 
     if (strips > max_strips) strips = max_strips;
     if (strips < 1) strips = 1;
     pp.rows_per_strip = (p->H + strips - 1) / strips;
+    if (use_tile && tile_s == 2) pp.rows_per_strip = (pp.rows_per_strip + 1) & ~1;  // row pairs: strips start on even rows
     pp.strips = (p->H + pp.rows_per_strip - 1) / pp.rows_per_strip;
   };
   if (use_tile) {
-    auto kern = p->radius == 2 ? sdnet_peaks_tile_kernel<2> : sdnet_peaks_tile_kernel<1>;
+    const TileKernel kern = tile_kernel_for(p->radius, p->dtype, tile_s);
+    const int kPanelCols = is_f32 ? TileGeom<SDNET_DTYPE_F32>::kPanel : TileGeom<SDNET_DTYPE_F16>::kPanel;
+    const int kTileSmem = tile_smem(tile_s);
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem);
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    static int per_sm = 0;
+    static int per_sm_cache[3][3][3] = {};  // [dtype][rows per TMA row][radius]; 0 = not asked yet
+    int& per_sm = per_sm_cache[p->dtype][tile_s][p->radius];
     if (per_sm == 0 &&
         (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTileWarps * 32, kTileSmem) != cudaSuccess || per_sm < 1))
       per_sm = 1;
-    pp.panels = (p->W + kPanelW - 1) / kPanelW;
+    pp.panels = (p->W + kPanelCols - 1) / kPanelCols;
     const long long resident_warps = (long long)sms * per_sm * kTileWarps;
     // long units prune best (measured: 128 images, 1 strip 0.169 ms, 7 strips 0.221 ms): split planes
     // into strips only while there are fewer units than resident warps
@@ -2256,6 +2446,14 @@ int sdnet_decode_workspace_bytes(int B, int M, int N, int H, int W, int K, int P
   if ((long long)H * W >= (1ll << 24)) return SDNET_E_SHAPE;
   *out_bytes = plan_workspace(B, M, N, H, W, K, P).total;
   return 0;
+}
+
+int sdnet_decode_peaks_path(const SdnetDecodeParams* params) {
+  const int rc = validate(params);
+  if (rc != 0) return rc;
+  CUtensorMap a, b;
+  int tile_s = 0;
+  return select_peaks_path(params, &a, &b, &tile_s);
 }
 
 int sdnet_decode_launch(const SdnetDecodeParams* params, void* stream) {

@@ -17,6 +17,7 @@ from dataclasses import dataclass
 import torch
 
 from . import _native
+PEAKS_PATHS = ("warp", "tile", "tile_row_pairs", "cta")  # SDNET_PATH_* in include/sdnet_decode.h
 from ._native import (FLAG_EXACT_SELECT, FLAG_NO_GROUPING, FLAG_PRE_ACTIVATED, FLAG_WARP_KERNEL, SdnetDecodeParams,
                       SdnetTensor4)
 
@@ -146,6 +147,14 @@ class DecodePlan:
         _native.check(rc, "sdnet_decode_launch")
         return self.out
 
+    def peaks_path(self, anchor_hm, part_hm, offsets, embeddings, radius=2, flags=0) -> str:
+        """Which peaks kernel these tensors would run: "warp" | "tile" | "tile_row_pairs" | "cta"."""
+        self._bind_inputs(anchor_hm, part_hm, offsets, embeddings, 0.0, 0.0, radius, flags)
+        rc = self.lib.sdnet_decode_peaks_path(ctypes.byref(self.params))
+        if rc < 0:  # non-negative values are SDNET_PATH_*, not CUDA errors
+            _native.check(rc, "sdnet_decode_peaks_path")
+        return PEAKS_PATHS[rc]
+
     def run_timed(self, anchor_hm, part_hm, offsets, embeddings, conf_f32, dist_abs_f32, radius=2, flags=0):
         """Synchronous profiling run: returns (peaks_ms, exact_select_ms, tail_ms) device times."""
         self._bind_inputs(anchor_hm, part_hm, offsets, embeddings, conf_f32, dist_abs_f32, radius, flags)
@@ -237,6 +246,15 @@ def decode_packed(outputs: dict, max_objects: int, max_parts: int, conf_thresh: 
     blob = _decode_op(a_hm, p_hm, off, emb, int(max_objects), int(max_parts), _f32(conf_thresh, a_hm.dtype),
                       _f32(float(dist_thresh) * min(W, H)), int(radius), int(flags))
     return _carve(blob, B, int(max_objects), int(max_parts), M + N)
+
+
+def peaks_path(outputs: dict, max_objects: int, max_parts: int, *, radius: int = 2, warp_kernel: bool = False) -> str:
+    """Name of the peaks kernel ``decode_packed`` runs for these tensors (host-only query)."""
+    a_hm, p_hm, off, emb = map(_unit_w_stride, (outputs["anchor_hm"], outputs["part_hm"], outputs["offsets"],
+                                                outputs["embeddings"]))
+    B, M, H, W = a_hm.shape
+    plan = DecodePlan(a_hm.device, B, M, p_hm.shape[1], H, W, int(max_objects), int(max_parts), a_hm.dtype)
+    return plan.peaks_path(a_hm, p_hm, off, emb, radius, FLAG_WARP_KERNEL if warp_kernel else 0)
 
 
 def activate_maps(hm: torch.Tensor) -> torch.Tensor:

@@ -92,16 +92,51 @@ def test_decode_matches_oracle(cuda_device, dtype, name, mode, batch):
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("h,w,k,p", [(9, 8, 72, 10), (37, 53, 40, 20), (64, 130, 100, 100), (33, 257, 64, 64)])
 def test_odd_shapes_exact_select_and_radius(cuda_device, dtype, h, w, k, p):
-    cfg = DecodeConfig("oddhalf", 2, 3, 2, h, w, k, p, cfg_id=19)
-    raw = make_raw(cfg, "ties").to(dtype)
-    outs = split_outputs(raw.to(cuda_device), cfg.labels, cfg.parts)
-    f32 = raw.float().numpy()
-    for kw, okw in (({}, {}), ({"exact_select": True}, {}), ({"radius": 1}, {"radius": 1})):
-        got = packed_np(ops.decode_packed(outs, k, p, 0.4, 0.1, **kw))
-        want = O.decode_packed(f32[:, :3], f32[:, 3:5], f32[:, 5:7], f32[:, 7:], k, p, 0.4, 0.1,
-                               activation_fn=_device_activation(dtype, cuda_device),
-                               conf_cmp=float(torch.tensor(0.4, dtype=dtype)), **okw)
-        assert_packed_equal(got, want, what=f"{dtype} {h}x{w} {kw}")
+    _check_shape(cuda_device, dtype, h, w, k, p)
+
+
+# TMA tile kernel: 16-byte-multiple row pitch (plain rows: 264, 512, 520) and 8-byte-multiple pitch
+# (row pairs: 12, 20, 252, 260, 516, 620 -- last panels of 4, 4 and 108 valid columns, strips whose
+# height has to be rounded to an even number of rows at 106 x 20)
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("h,w,k,p", [(16, 12, 50, 50), (106, 20, 100, 64), (10, 252, 64, 64), (34, 260, 100, 100),
+                                     (20, 516, 100, 100), (40, 620, 100, 100), (18, 264, 100, 100), (12, 512, 64, 64),
+                                     (7, 520, 100, 100)])
+def test_tile_kernel_shapes(cuda_device, dtype, h, w, k, p):
+    want_path = "tile" if w % 8 == 0 else "tile_row_pairs"
+    _check_shape(cuda_device, dtype, h, w, k, p, modes=("ties", "noise"), want_path=want_path)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_kernel_selection_for_reduced_precision(cuda_device, dtype):
+    """Which peaks kernel runs (host-side query through the C ABI): cfg3/cfg5 maps (W = 612, 1224-byte
+    rows) take TMA tiles over row pairs, 16-byte-multiple pitches plain tiles, the rest the per-lane kernel."""
+    def path(h, w, **kw):
+        cfg = DecodeConfig("sel", 1, 2, 1, h, w, 10, 10, cfg_id=3)
+        raw = torch.zeros(1, 7, h, w, dtype=dtype, device=cuda_device)
+        return ops.peaks_path(split_outputs(raw, cfg.labels, cfg.parts), 10, 10, **kw)
+    assert path(512, 612) == "tile_row_pairs"
+    assert path(128, 128) == "tile" and path(256, 256) == "tile"
+    assert path(511, 612) == "warp"            # odd H: no row pairs
+    assert path(512, 612, radius=1) == "warp"   # row pairs need tiles that start on an even row
+    assert path(64, 130) == "warp" and path(37, 53) == "warp"
+    assert path(512, 612, warp_kernel=True) == "warp"
+
+
+def _check_shape(cuda_device, dtype, h, w, k, p, modes=("ties",), want_path=None):
+    for mode in modes:
+        cfg = DecodeConfig("oddhalf", 2, 3, 2, h, w, k, p, cfg_id=19)
+        raw = make_raw(cfg, mode).to(dtype)
+        outs = split_outputs(raw.to(cuda_device), cfg.labels, cfg.parts)
+        if want_path is not None:
+            assert ops.peaks_path(outs, k, p) == want_path
+        f32 = raw.float().numpy()
+        for kw, okw in (({}, {}), ({"exact_select": True}, {}), ({"radius": 1}, {"radius": 1}), ({"warp_kernel": True}, {})):
+            got = packed_np(ops.decode_packed(outs, k, p, 0.4, 0.1, **kw))
+            want = O.decode_packed(f32[:, :3], f32[:, 3:5], f32[:, 5:7], f32[:, 7:], k, p, 0.4, 0.1,
+                                   activation_fn=_device_activation(dtype, cuda_device),
+                                   conf_cmp=float(torch.tensor(0.4, dtype=dtype)), **okw)
+            assert_packed_equal(got, want, what=f"{dtype} {h}x{w} {mode} {kw}")
 
 
 @pytest.mark.parametrize("dtype", DTYPES)

@@ -99,6 +99,9 @@ def test_decode_matches_oracle(cuda_device, name, mode, batch, warp_kernel):
     got, want = _decode_both(cfg, raw, cuda_device, warp_kernel=warp_kernel)
     assert_packed_equal(got, want, what=f"{name}/{mode}")
     assert int(got["diag"][:, 1].sum()) == 0 or mode == "ties"
+    # every config's fp32 maps are 16-byte aligned: the default path is the TMA tile kernel
+    outs = split_outputs(raw[:1].to(cuda_device), cfg.labels, cfg.parts)
+    assert ops.peaks_path(outs, cfg.max_objects, cfg.max_parts, warp_kernel=warp_kernel) == ("warp" if warp_kernel else "tile")
 
 
 @pytest.mark.parametrize("name,mode,batch", [("cfg1", "noise", 2), ("cfg1", "ties", 2), ("cfg3", "blobs", 1), ("cfg4", "noise", 1)])
