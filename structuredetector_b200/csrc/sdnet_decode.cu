@@ -2000,21 +2000,39 @@ __global__ void __launch_bounds__(2 * kTeamThreads) sdnet_tail_kernel(const __gr
   __syncthreads();
 
   // ---- grouping: every part to its nearest anchor (first minimum), gated by the distance threshold
+  // (reference: hypot utils.py:422-437, min(dim=1) decoders.py:99).  A part is shared by g lanes of one
+  // warp, lane `sub` taking anchors sub, sub + g, ...  The square root is monotone, so the smallest
+  // distance is the root of the smallest squared distance m2 -- but two different squares can round to
+  // the same root and the reference's min() then keeps the FIRST anchor.  Hence two sweeps without a
+  // root in the loop: m2, then the first anchor whose square lies within 1e-6 of m2 (a root can only
+  // tie if its square is within 2^-22 relative) AND whose root equals root(m2).
   const float2* origin = reinterpret_cast<const float2*>(s_sel[1]);
-  for (int s = threadIdx.x; s < p.P; s += blockDim.x) {
+  int g = 32;
+  while (g > 1 && p.P * g > (int)blockDim.x) g >>= 1;
+  const int sub = threadIdx.x & (g - 1), per_pass = blockDim.x / g;
+  for (int s0 = 0; s0 < p.P; s0 += per_pass) {  // block-uniform
+    const int s = s0 + (int)threadIdx.x / g;
+    const bool live = s < p.P;
     int slot = -1;
-    if (!p.no_grouping) {
-      const float qx = origin[s].x, qy = origin[s].y;
-      float best = CUDART_INF_F;
-      int arg = 0;
-      for (int a = 0; a < p.K; ++a) {
+    if (!p.no_grouping) {  // kernel-uniform
+      const float qx = live ? origin[s].x : 0.f, qy = live ? origin[s].y : 0.f;
+      float m2 = CUDART_INF_F;
+      for (int a = sub; a < p.K; a += g) {
         const float dx = __fsub_rn(qx, s_ax[a]), dy = __fsub_rn(qy, s_ay[a]);
-        const float d = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
-        if (d < best) { best = d; arg = a; }
+        m2 = fminf(m2, __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
       }
+      for (int w = g >> 1; w > 0; w >>= 1) m2 = fminf(m2, __shfl_xor_sync(0xffffffffu, m2, w));
+      const float best = __fsqrt_rn(m2), near = m2 * 1.000001f;
+      int arg = 0x7fffffff;
+      for (int a = sub; a < p.K; a += g) {
+        const float dx = __fsub_rn(qx, s_ax[a]), dy = __fsub_rn(qy, s_ay[a]);
+        const float sq = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+        if (sq <= near && __fsqrt_rn(sq) == best) { arg = a; break; }
+      }
+      for (int w = g >> 1; w > 0; w >>= 1) arg = min(arg, __shfl_xor_sync(0xffffffffu, arg, w));
       slot = (best < p.dist_abs) ? arg : -1;
     }
-    store_out(p, p.assign + (size_t)b * p.P + s, slot);
+    if (live && sub == 0) store_out(p, p.assign + (size_t)b * p.P + s, slot);
   }
   if (threadIdx.x < 2) store_out(p, p.out_counts + (size_t)b * 2 + threadIdx.x, s_cnt[threadIdx.x]);
   if (p.diag) {
