@@ -48,6 +48,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--pipeline", type=int, default=2,
+                    help="decodes in flight: consecutive steps alternate between this many plans/streams")
     ap.add_argument("--gather", choices=("fused", "nccl"), default="fused",
                     help="N > 1: tail kernel stores into every peer (symmetric memory) + barrier, or ncclAllGather")
     return ap.parse_args()
@@ -275,7 +277,24 @@ def main():
         gathered = torch.empty(world * blob_bytes, dtype=torch.uint8, device=device)
         gather_kind = "ncclAllGather of packed detections (every rank holds all results)"
 
+    # Software pipeline over batches: consecutive steps alternate between `depth` plans (own workspace,
+    # own outputs, own gather buffer) on `depth` streams, so one batch's tail kernel and gather overlap
+    # the next batch's peaks kernel.  --pipeline 1 = strictly one decode at a time.
+    depth = max(1, args.pipeline)
+    pipe = None
+    if depth > 1:
+        if fused is not None:
+            extra = [FusedGatherPlan(device, cfg.batch, M, N, H, W, K, P) for _ in range(depth - 1)]
+            pipe = ops.DecodePipeline(device, depth, lambda i: fused if i == 0 else extra[i - 1])
+        elif world == 1:
+            pipe = ops.DecodePipeline(device, depth, lambda i: plan if i == 0 else ops.DecodePlan(device, shard, M, N, H, W, K, P, tdtype))
+        else:
+            depth = 1  # the ncclAllGather baseline stays serial
+
     def step():
+        if pipe is not None:
+            pipe.submit(outs["anchor_hm"], outs["part_hm"], outs["offsets"], outs["embeddings"], conf32, dist32)
+            return
         if fused is not None:
             fused.run(outs["anchor_hm"], outs["part_hm"], outs["offsets"], outs["embeddings"], conf32, dist32)
             return
@@ -298,8 +317,12 @@ def main():
     with ClockSampler(physical_gpu_index(local_rank)) as clocks:
         fence()
         ev0.record()
+        if pipe is not None:
+            pipe.after(ev0)
         for _ in range(args.steps):
             step()
+        if pipe is not None:
+            pipe.drain()
         ev1.record()
         fence()
     ms_total = ev0.elapsed_time(ev1)
@@ -413,8 +436,11 @@ def main():
                 "workload": workload_name(cfg) if args.dtype == "f32" else workload_name(cfg).replace("fp32", args.dtype),
                 "mode": args.mode, "images_per_rank": shard, "parallelism": f"batch-shard x{world}",
                 "gather": gather_kind,
-                "l2": f"inputs larger than L2 ({raw.numel() * 4 / 1e9:.2f} GB per rank, no flush needed)",
+                "l2": f"inputs larger than L2 ({raw.numel() * esize / 1e9:.2f} GB per rank, no flush needed)",
                 "unique_images": int(min(UNIQUE_IMAGES, cfg.batch)),
+                "pipeline": (f"{depth} decodes in flight: consecutive steps alternate between {depth} plans (own workspace, outputs"
+                             f"{' and gather buffer' if world > 1 else ''}) on {depth} streams; every step is a full decode of the batch")
+                            if depth > 1 else "1 (each step waits for the one before)",
             },
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,

@@ -138,11 +138,12 @@ class DecodePlan:
         p.radius, p.flags = radius, flags
 
     def run(self, anchor_hm, part_hm, offsets, embeddings, conf_f32, dist_abs_f32, radius=2, flags=0,
-            stream: int | None = None) -> PackedDetections:
-        """Enqueue one decode on ``stream`` (default: torch's current stream). Asynchronous."""
+            stream=None) -> PackedDetections:
+        """Enqueue one decode on ``stream`` (a torch stream or raw handle; default: torch's current stream). Asynchronous."""
         self._bind_inputs(anchor_hm, part_hm, offsets, embeddings, conf_f32, dist_abs_f32, radius, flags)
         if stream is None:
-            stream = torch.cuda.current_stream(self.device).cuda_stream
+            stream = torch.cuda.current_stream(self.device)
+        stream = getattr(stream, "cuda_stream", stream)  # a torch.cuda.Stream or a raw cudaStream_t
         rc = self.lib.sdnet_decode_launch(ctypes.byref(self.params), ctypes.c_void_p(stream))
         _native.check(rc, "sdnet_decode_launch")
         return self.out
@@ -175,6 +176,47 @@ class DecodePlan:
                                                ctypes.c_void_p(stream))
         _native.check(rc, "sdnet_decode_host_launch")
         return self.out
+
+
+class DecodePipeline:
+    """Several decodes in flight: ``depth`` plans (each with its own workspace and outputs) on ``depth``
+    CUDA streams, used round-robin.  While one batch is in its short, latency-bound tail kernel the next
+    batch's peaks kernel already streams its heat maps, so a stream of batches runs at the peaks kernel's
+    rate.  ``submit`` returns the slot's outputs and an event; a slot's outputs are overwritten
+    ``depth`` submits later, so consume them (or wait on the event and copy) before that.
+
+    ``make_plan(i)`` builds slot i's plan: anything with ``.run(..., stream=)`` (``DecodePlan``,
+    ``parallel.FusedGatherPlan``)."""
+
+    def __init__(self, device, depth: int, make_plan):
+        self.device = torch.device(device)
+        self.plans = [make_plan(i) for i in range(depth)]
+        self.streams = [torch.cuda.Stream(self.device) for _ in range(depth)]
+        self.events = [torch.cuda.Event() for _ in range(depth)]
+        self._next = 0
+
+    @classmethod
+    def for_shape(cls, device, depth, B, M, N, H, W, K, P, dtype: torch.dtype = torch.float32):
+        return cls(device, depth, lambda _i: DecodePlan(device, B, M, N, H, W, K, P, dtype))
+
+    def after(self, event: torch.cuda.Event):
+        """Make every slot's stream wait for ``event`` (e.g. the producer of the inputs)."""
+        for st in self.streams:
+            st.wait_event(event)
+
+    def submit(self, anchor_hm, part_hm, offsets, embeddings, conf_f32, dist_abs_f32, radius=2, flags=0):
+        k = self._next
+        self._next = (k + 1) % len(self.plans)
+        out = self.plans[k].run(anchor_hm, part_hm, offsets, embeddings, conf_f32, dist_abs_f32, radius, flags,
+                                stream=self.streams[k])
+        self.events[k].record(self.streams[k])
+        return out, self.events[k]
+
+    def drain(self, stream: torch.cuda.Stream | None = None):
+        """Make ``stream`` (default: the current one) wait for everything submitted so far."""
+        stream = stream if stream is not None else torch.cuda.current_stream(self.device)
+        for st in self.streams:
+            stream.wait_stream(st)
 
 
 def _f32(value: float, dtype: torch.dtype = torch.float32) -> float:

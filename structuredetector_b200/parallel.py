@@ -114,8 +114,13 @@ class FusedGatherPlan:
             prm.dest_delta[j] = int(ptrs[j]) - int(ptrs[self.rank])
         self.handle.barrier()  # everyone is mapped before the first remote store
 
-    def run(self, anchor_hm, part_hm, offsets, embeddings, conf_f32, dist_abs_f32, radius=2, flags=0) -> ops.PackedDetections:
-        """Enqueue decode + remote stores + the barrier on the current stream; returns the global result."""
-        self.plan.run(anchor_hm, part_hm, offsets, embeddings, conf_f32, dist_abs_f32, radius, flags)
-        self.handle.barrier()
+    def run(self, anchor_hm, part_hm, offsets, embeddings, conf_f32, dist_abs_f32, radius=2, flags=0,
+            stream: torch.cuda.Stream | None = None) -> ops.PackedDetections:
+        """Enqueue decode + remote stores + the barrier on ``stream`` (default: the current one); returns
+        the global result.  Every rank must call its plans in the same order."""
+        if stream is None:
+            stream = torch.cuda.current_stream(self.plan.device)
+        self.plan.run(anchor_hm, part_hm, offsets, embeddings, conf_f32, dist_abs_f32, radius, flags, stream=stream)
+        with torch.cuda.stream(stream):
+            self.handle.barrier()
         return self.result

@@ -189,3 +189,27 @@ def test_randomised_shapes_and_thresholds(cuda_device):
         got, want = _decode_both(cfg, raw, cuda_device, conf=conf, dist=dist, radius=radius,
                                  warp_kernel=bool(case % 7 == 3), exact_select=bool(case % 11 == 5))
         assert_packed_equal(got, want, what=f"fuzz {case}: {h}x{w} M{m} N{n} K{k} P{p} {mode} conf{conf} dist{dist} r{radius}")
+
+
+def test_pipeline_of_decodes_matches_serial(cuda_device):
+    """ops.DecodePipeline: three decodes in flight on three streams give what one-at-a-time decodes give."""
+    cfg = CONFIGS["cfg2"]
+    raws = [make_raw(cfg, mode, batch=4).to(cuda_device) for mode in ("noise", "blobs", "ties", "noise", "blobs")]
+    conf32, dist32 = ops._f32(cfg.conf_threshold), ops._f32(cfg.dist_thresh * min(cfg.width, cfg.height))
+    pipe = ops.DecodePipeline.for_shape(cuda_device, 3, 4, cfg.labels, cfg.parts, cfg.height, cfg.width, cfg.max_objects,
+                                        cfg.max_parts)
+    done = torch.cuda.Event()
+    done.record()
+    pipe.after(done)
+    got = []
+    for raw in raws:
+        o = split_outputs(raw, cfg.labels, cfg.parts)
+        out, ev = pipe.submit(o["anchor_hm"], o["part_hm"], o["offsets"], o["embeddings"], conf32, dist32)
+        ev.synchronize()
+        got.append(out.blob.clone())
+    for raw, blob in zip(raws, got):
+        want = ops.decode_packed(split_outputs(raw, cfg.labels, cfg.parts), cfg.max_objects, cfg.max_parts,
+                                 cfg.conf_threshold, cfg.dist_thresh)
+        torch.cuda.synchronize()
+        n = blob.numel() - want.diag.numel() * 4  # everything but the trailing diagnostics is deterministic
+        assert torch.equal(blob[:n], want.blob[:n])
