@@ -1186,6 +1186,10 @@ struct TileMax<SDNET_DTYPE_F32> {
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
     return v;
   }
+  // one element in its storage format (here: the float's bits), max in that format, back to float
+  static __device__ __forceinline__ u32 raw(u32 addr) { return __float_as_uint(elem(addr)); }
+  static __device__ __forceinline__ u32 rmax(u32 a, u32 b) { return __float_as_uint(fmaxf(__uint_as_float(a), __uint_as_float(b))); }
+  static __device__ __forceinline__ float rfloat(u32 r) { return __uint_as_float(r); }
 };
 template <>
 struct TileMax<SDNET_DTYPE_F16> {
@@ -1201,6 +1205,17 @@ struct TileMax<SDNET_DTYPE_F16> {
     asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
     return __half2float(__ushort_as_half(v));
   }
+  // storage format: the 16 bits in the low half of a register (high half +0); max.f16x2 ignores NaN
+  static __device__ __forceinline__ u32 raw(u32 addr) {
+    u32 v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+  }
+  static __device__ __forceinline__ u32 rmax(u32 a, u32 b) {
+    const __half2 m = __hmax2(h2(a), h2(b));
+    return *reinterpret_cast<const u32*>(&m);
+  }
+  static __device__ __forceinline__ float rfloat(u32 r) { return __half2float(__ushort_as_half((unsigned short)r)); }
 };
 template <>
 struct TileMax<SDNET_DTYPE_BF16> {
@@ -1216,6 +1231,16 @@ struct TileMax<SDNET_DTYPE_BF16> {
     asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
     return __uint_as_float((u32)v << 16);
   }
+  static __device__ __forceinline__ u32 raw(u32 addr) {
+    u32 v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+  }
+  static __device__ __forceinline__ u32 rmax(u32 a, u32 b) {
+    const __nv_bfloat162 m = __hmax2(h2(a), h2(b));
+    return *reinterpret_cast<const u32*>(&m);
+  }
+  static __device__ __forceinline__ float rfloat(u32 r) { return __uint_as_float(r << 16); }
 };
 
 // Byte offset of ring row rr (0..15) inside the ring.  S = 1: rows in order.  S = 2 (rows loaded as
@@ -1252,16 +1277,21 @@ __device__ __forceinline__ void settle_entries(UnitState& st, const unsigned cha
     const float x = TileMax<DT>::elem(col_addr + R * kEsz + ring_row_off<S>((row0 + i + R) & kRowMask));
     bool keep = slot < nslots && x > floorx;
     if (keep && !pre) {
-      float h = x;
+      // window max in the storage format (no conversions for fp16/bf16), one accumulator per window row
+      u32 hr[2 * R + 1];
 #pragma unroll
       for (int d = 0; d <= 2 * R; ++d) {
         const u32 a = col_addr + ring_row_off<S>((row0 + i + d) & kRowMask);
-        float v[2 * R + 1];
+        u32 v[2 * R + 1];
 #pragma unroll
-        for (int q = 0; q <= 2 * R; ++q) v[q] = TileMax<DT>::elem(a + kEsz * q);
+        for (int q = 0; q <= 2 * R; ++q) v[q] = TileMax<DT>::raw(a + kEsz * q);
+        hr[d] = v[0];
 #pragma unroll
-        for (int q = 0; q <= 2 * R; ++q) h = fmaxf(h, v[q]);
+        for (int q = 1; q <= 2 * R; ++q) hr[d] = TileMax<DT>::rmax(hr[d], v[q]);
       }
+#pragma unroll
+      for (int d = 1; d <= 2 * R; ++d) hr[0] = TileMax<DT>::rmax(hr[0], hr[d]);
+      const float h = fmaxf(x, TileMax<DT>::rfloat(hr[0]));  // an all-NaN window cannot happen: the centre is in it
       if (x != h) {
         const bool amb = (x >= h - kNearTie) || (h > kHiZone && x >= h - kNearTie2) ||
                          (h > kHiZone2 && x > kHiZone2 - 1.0f) || (h < kLoZone);  // same zones as classify_row
