@@ -364,7 +364,9 @@ def main():
             traffic = None
     step_s = ms_per_step * 1e-3
     roofline = {
-        "bound": "hbm", "kernel": "sdnet_peaks_tile_kernel" if args.dtype == "f32" else "sdnet_peaks_kernel (converting feed)", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+        "bound": "hbm", "kernel": {"tile": "sdnet_peaks_tile_kernel (TMA tiles)", "tile_row_pairs": "sdnet_peaks_tile_kernel (TMA tiles over row pairs)",
+                                  "cta": "sdnet_peaks_cta_kernel", "warp": "sdnet_peaks_kernel (per-lane feed)"}[
+                           plan.peaks_path(outs["anchor_hm"], outs["part_hm"], outs["offsets"], outs["embeddings"])], "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
         "frac": achieved / peak_gbs, "traffic": traffic, "peak_source": peak_src,
         "kernel_ms": {"peaks": peaks_ms, "exact_select": exact_ms, "tail": tail_ms},
         "kernel_share_of_step": peaks_ms / (peaks_ms + exact_ms + tail_ms),
