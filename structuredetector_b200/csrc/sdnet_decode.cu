@@ -1461,14 +1461,14 @@ sdnet_peaks_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_cons
     }
     y_next += kGroupRows * NG;
     int gfloor_seen = 0;
-    const int poll_mask = nrows <= 160 ? 0 : 3;
+    constexpr int poll_mask = 3;  // measured at 128-row strips: polling every group 0.179 ms, every 4th 0.136 ms, every 8th 0.146 ms
     u32 idx0 = (u32)(r_begin * W + panel * kPanel);  // flat index of the group's row 0, panel column 0
     wait_tile(tile_n);
     for (int g = 0; g < groups_out; ++g, idx0 += (u32)(kGroupRows * W)) {
       const u32 n = tile_n + (u32)g;  // tile holding the group's first window row
       if (R == 2 || g + 1 < groups) wait_tile(n + 1);
       if ((g & poll_mask) == 0) {
-        // every 16 rows (every 4 in short strips): apply the plane-wide floor fetched one period ago
+        // every 16 rows: apply the plane-wide floor fetched one period ago
         // and start the next fetch.  The load writes straight into the register it will be read
         // from a period later, so its latency is never waited for.
         st.floorx = fmaxf(st.floorx, shared_floor<DT>(gfloor_seen, xscale));
