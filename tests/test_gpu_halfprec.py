@@ -168,3 +168,28 @@ def test_drop_in_decoder_with_reduced_precision(cuda_device, dtype):
                       (cfg.width, cfg.height), (4 * cfg.width, 4 * cfg.height))
     assert plain(meta["annotation"]) == objs
     np.testing.assert_array_equal(meta["topk_anchor"][0].cpu().numpy(), want["anchor_scores_masked"])
+
+
+@pytest.mark.parametrize("dtype,w,wp,path", [
+    (torch.float32, 128, 132, "tile"), (torch.float32, 300, 308, "tile"),
+    (torch.float16, 256, 264, "tile"), (torch.bfloat16, 264, 272, "tile"),
+    (torch.float16, 260, 268, "tile_row_pairs"), (torch.bfloat16, 252, 260, "tile_row_pairs"),
+    (torch.float16, 516, 524, "tile_row_pairs"), (torch.float16, 612, 620, "tile_row_pairs"),
+    (torch.float16, 130, 140, "warp"),
+])
+def test_padded_row_pitch_never_leaks(cuda_device, dtype, w, wp, path):
+    """Row pitch larger than W (views of a wider allocation): the padding holds +30 logits that would win
+    every top-K if a tile ever let them in -- the row-pair tiles physically read them and must blank them."""
+    cfg = DecodeConfig("padded", 2, 2, 1, 34, w, 100, 100, cfg_id=23)
+    raw = make_raw(cfg, "noise").to(dtype).to(cuda_device)
+    wide = torch.full((raw.shape[0], raw.shape[1], cfg.height, wp), 30.0, dtype=dtype, device=cuda_device)
+    wide[..., :w] = raw
+    outs_pad = split_outputs(wide[..., :w], cfg.labels, cfg.parts)
+    assert outs_pad["anchor_hm"].stride(2) == wp
+    assert ops.peaks_path(outs_pad, 100, 100) == path
+    got = ops.decode_packed(outs_pad, 100, 100, 0.4, 0.1)
+    want = ops.decode_packed(split_outputs(raw, cfg.labels, cfg.parts), 100, 100, 0.4, 0.1, warp_kernel=True)
+    torch.cuda.synchronize()
+    n = got.blob.numel() - got.diag.numel() * 4
+    assert torch.equal(got.blob[:n], want.blob[:n])
+    assert float(got.anchor_out[..., 2].max()) < 0.9999  # no +30 logit (score 1 - 1e-6) got in
