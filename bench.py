@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--global-batch", type=int, default=None, help="override cfg5's 1024 (debug only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-objects", action="store_true", help="skip the Decoder -> Python objects leg")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--pipeline", type=int, default=2,
                     help="decodes in flight: consecutive steps alternate between this many plans/streams")
@@ -378,6 +379,31 @@ def main():
         "frac_of_8tbs_contract": shard * cfg.contract_bytes_per_image * esize / 4 / step_s / 8e12,
     }
 
+    # ---- the reference-facing Python call: device tensors -> list[ImageAnnotation] (decode + ONE D2H copy +
+    # Python object assembly), reported separately; rank 0, bounded sample
+    objects = None
+    if rank == 0 and not args.no_objects:
+        from types import SimpleNamespace
+
+        from structuredetector_b200 import Decoder
+
+        n_obj = min(shard, 128)
+        dec = Decoder(SimpleNamespace(_r_labels={i: f"label{i}" for i in range(M)}, _r_parts={i: f"part{i}" for i in range(N)},
+                                      anchor_name="anchor", down_ratio=4.0, max_objects=K, max_parts=P,
+                                      conf_threshold=cfg.conf_threshold, decoder_dist_thresh=cfg.dist_thresh))
+        sample = {k: v[:n_obj] for k, v in outs.items()}
+        dec(sample)
+        torch.cuda.synchronize(device)
+        t0 = time.perf_counter()
+        reps_obj = 3
+        for _ in range(reps_obj):
+            anns = dec(sample)
+        dt = (time.perf_counter() - t0) / reps_obj
+        objects = {"value": n_obj / dt, "unit": "images/s", "ms_per_image": dt / n_obj * 1e3,
+                   "objects_per_image": sum(len(a.objects) for a in anns) / n_obj,
+                   "parts_per_image": sum(a.nb_parts for a in anns) / n_obj,
+                   "sample": f"Decoder(args)(outputs) on {n_obj} images resident on the device -> list[ImageAnnotation], wall clock, 1 Python thread"}
+
     # ---- end to end through the C ABI with HOST buffers: pinned inputs -> packed results on the host
     e2e = None
     if not args.no_e2e:
@@ -447,6 +473,7 @@ def main():
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
             "e2e": e2e,
+            "python_objects": objects,
             "gpu_launches": ops.gpu_launches_per_decode() * args.steps,
             "clocks": clocks.summary(),
             "detections": {"anchors_above_conf": counts[0], "parts_above_conf": counts[1],
