@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SDNET_ABI_VERSION 3
+#define SDNET_ABI_VERSION 4
 
 /* element types of the four input tensors */
 #define SDNET_DTYPE_F32 0
@@ -132,6 +132,35 @@ int sdnet_activate_launch(const SdnetTensor4* in, int dtype, int B, int C, int H
  * selected peaks.  Outputs stay on the device.  Uses `stream` plus one internal
  * copy stream per call. */
 int sdnet_decode_host_launch(const SdnetDecodeParams* params, void* staging, size_t staging_bytes, void* stream);
+
+/* ---- the step after the path: location matching of the reference evaluator, on the packed detections ----
+ * Evaluator.eval_anchor (src/sdnet/model/evaluator.py:244-284) and Evaluator.eval_part (:286-334) for a
+ * whole batch: per image and label, detections in score order each look for their nearest ground truth
+ * of the same label (first minimum); a detection is a true positive if that distance is below the
+ * image's threshold and no earlier detection claimed the same ground truth.  All arithmetic is the
+ * reference's Python-float (double) arithmetic: x = (double)x_f32 * sx * rx, dist = hypot(dx, dy). */
+#define SDNET_MAX_GT 1024
+typedef struct SdnetMatchParams {
+  uint32_t struct_size; /* sizeof(SdnetMatchParams) */
+  int32_t B, M, N, K, P; /* images, anchor classes, part kinds, anchor slots, part slots */
+  int32_t max_gt_anchors, max_gt_parts; /* row lengths of the ground-truth arrays, <= SDNET_MAX_GT */
+  double conf;   /* objects: score > conf (decoders.py:116); raw parts: not score < conf (decoders.py:153) */
+  double sx, sy; /* heat-map -> network-input scale, in/out (decoders.py:139) */
+  const float* anchor_out;     /* (B, K, 4) as written by sdnet_decode_launch */
+  const float* part_out;       /* (B, P, 6) */
+  const double* image_scale;   /* (B, 4): img_w/args.width, img_h/args.height, min(img_size)*dist_threshold, min(img_size)
+                                  (evaluator.py:245-250) */
+  const double* gt_anchors;    /* (B, max_gt_anchors, 3): x, y, label index, network-input frame, annotation order */
+  const int32_t* n_gt_anchors; /* (B) */
+  const double* gt_parts;      /* (B, max_gt_parts, 3): every part of every ground-truth object, annotation order */
+  const int32_t* n_gt_parts;   /* (B) */
+  int32_t* anchor_stats;       /* (B, M, 3): ndet, npos, tp */
+  int32_t* part_stats;         /* (B, N, 3) */
+  double* anchor_acc;          /* (B, K): min_dist / min(img_size) of the true positives, NaN elsewhere (slot = score order) */
+  double* part_acc;            /* (B, P) */
+} SdnetMatchParams;
+
+int sdnet_match_launch(const SdnetMatchParams* params, void* stream);
 
 #ifdef __cplusplus
 }

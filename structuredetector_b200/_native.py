@@ -13,7 +13,7 @@ import os as _os
 
 # SDNET_DECODE_LIB: load another build of the same library (kernel experiments, tools/xbuild.sh)
 LIB_PATH = Path(_os.environ.get("SDNET_DECODE_LIB") or Path(__file__).resolve().parent / "csrc" / "libsdnet_decode.so").resolve()
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 FLAG_PRE_ACTIVATED = 1
 FLAG_NO_GROUPING = 2
@@ -25,6 +25,7 @@ DTYPE_BF16 = 2
 MAX_TOPK = 1024
 MAX_CHANNELS = 255
 MAX_DEST = 16
+MAX_GT = 1024  # SDNET_MAX_GT
 
 EXPORTS = (
     "sdnet_abi_version",
@@ -33,6 +34,7 @@ EXPORTS = (
     "sdnet_decode_launch",
     "sdnet_decode_launch_timed",
     "sdnet_decode_peaks_path",
+    "sdnet_match_launch",
     "sdnet_activate_launch",
     "sdnet_decode_host_launch",
 )
@@ -83,6 +85,20 @@ class SdnetDecodeParams(ctypes.Structure):
     ]
 
 
+class SdnetMatchParams(ctypes.Structure):
+    _fields_ = [
+        ("struct_size", ctypes.c_uint32),
+        ("B", ctypes.c_int32), ("M", ctypes.c_int32), ("N", ctypes.c_int32), ("K", ctypes.c_int32), ("P", ctypes.c_int32),
+        ("max_gt_anchors", ctypes.c_int32), ("max_gt_parts", ctypes.c_int32),
+        ("conf", ctypes.c_double), ("sx", ctypes.c_double), ("sy", ctypes.c_double),
+        ("anchor_out", ctypes.c_void_p), ("part_out", ctypes.c_void_p), ("image_scale", ctypes.c_void_p),
+        ("gt_anchors", ctypes.c_void_p), ("n_gt_anchors", ctypes.c_void_p),
+        ("gt_parts", ctypes.c_void_p), ("n_gt_parts", ctypes.c_void_p),
+        ("anchor_stats", ctypes.c_void_p), ("part_stats", ctypes.c_void_p),
+        ("anchor_acc", ctypes.c_void_p), ("part_acc", ctypes.c_void_p),
+    ]
+
+
 class NativeLibraryError(RuntimeError):
     pass
 
@@ -111,6 +127,8 @@ def load() -> ctypes.CDLL:
     lib.sdnet_decode_workspace_bytes.argtypes = [ctypes.c_int] * 8 + [ctypes.POINTER(ctypes.c_size_t)]
     lib.sdnet_decode_launch.restype = ctypes.c_int
     lib.sdnet_decode_launch.argtypes = [ctypes.POINTER(SdnetDecodeParams), ctypes.c_void_p]
+    lib.sdnet_match_launch.restype = ctypes.c_int
+    lib.sdnet_match_launch.argtypes = [ctypes.POINTER(SdnetMatchParams), ctypes.c_void_p]
     lib.sdnet_decode_peaks_path.restype = ctypes.c_int
     lib.sdnet_decode_peaks_path.argtypes = [ctypes.POINTER(SdnetDecodeParams)]
     lib.sdnet_decode_launch_timed.restype = ctypes.c_int

@@ -1,0 +1,126 @@
+"""Evaluator matching: the CPU restatement against the reference's golden output (CPU),
+the CUDA kernel against both (GPU)."""
+import json
+from pathlib import Path
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import evaluator_oracle as EO
+
+GOLDEN = Path(__file__).parent / "golden"
+INDEX = json.loads((GOLDEN / "index.json").read_text())
+EVAL = json.loads((GOLDEN / "eval.json").read_text())
+
+
+def _names(name):
+    _, m, n, _, _ = INDEX[name]["shape"]
+    return [f"label{i}" for i in range(m)], [f"part{i}" for i in range(n)]
+
+
+@pytest.mark.parametrize("name", sorted(EVAL))
+def test_oracle_reproduces_reference_evaluator(name):
+    labels, kinds = _names(name)
+    got = EO.evaluate_batch(INDEX[name]["annotation"], INDEX[name]["raw_parts"], EVAL[name], labels, kinds)
+    for key in ("anchor", "part"):
+        for label, want in EVAL[name]["result"][key].items():
+            tp, npos, ndet, acc = got[key][label]
+            assert (tp, npos, ndet) == (want["tp"], want["npos"], want["ndet"]), (name, key, label)
+            assert acc == want["acc"], (name, key, label)  # same Python-float arithmetic: bit-exact
+
+
+def test_live_reference_evaluator_agrees_with_fixture():
+    ref = Path("/root/reference/src")
+    if not ref.exists():
+        pytest.skip("reference not present (GPU box)")
+    import subprocess, sys
+    out = subprocess.run([sys.executable, str(GOLDEN / "make_golden_eval.py"), "--check"], capture_output=True, text=True,
+                         env={"PYTHONDONTWRITEBYTECODE": "1", "PATH": "/usr/bin:/bin"}, cwd=str(GOLDEN.parent.parent))
+    assert out.returncode == 0, out.stderr[-2000:]
+
+
+def _annotations(case):
+    from structuredetector_b200 import ImageAnnotation, Keypoint, Object
+    anns = []
+    for image in case["images"]:
+        objs = [Object(name, Keypoint("stem", x, y), [Keypoint(k, px, py) for k, px, py in kps]) for name, x, y, kps in image["gt"]]
+        anns.append(ImageAnnotation("gt", objs, img_size=tuple(image["img_size"])))
+    return anns
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(EVAL))
+def test_cuda_matching_reproduces_reference_evaluator(cuda_device, name):
+    """Decode the stored raw input on the GPU, match on the GPU, compare with what the reference's
+    Decoder + Evaluator produced on CPU: counts exact; localisation errors to 1e-9 relative (positions are
+    bit-identical fp32, the distance is a double hypot on both sides)."""
+    from structuredetector_b200 import ops
+    from structuredetector_b200.evaluator import Evaluator
+    from structuredetector_b200.synth import split_outputs
+    meta, case = INDEX[name], EVAL[name]
+    _, m, n, h, w = meta["shape"]
+    labels, kinds = _names(name)
+    raw = torch.from_numpy(np.load(GOLDEN / f"{name}.npz")["raw"]).to(cuda_device)
+    packed = ops.decode_packed(split_outputs(raw, m, n), meta["K"], meta["P"], meta["conf"], meta["dist"])
+    args = SimpleNamespace(labels={l: i for i, l in enumerate(labels)}, parts={k: i for i, k in enumerate(kinds)},
+                           width=case["width"], height=case["height"], dist_threshold=case["dist_threshold"],
+                           conf_threshold=meta["conf"], down_ratio=meta["down_ratio"])
+    ev = Evaluator(args)
+    ev.accumulate_packed(packed, _annotations(case), (w, h))
+    for key, evals in (("anchor", ev.anchor_eval), ("part", ev.part_eval)):
+        for label, want in case["result"][key].items():
+            got = evals[label]
+            assert (got.tp, got.npos, got.ndet) == (want["tp"], want["npos"], want["ndet"]), (name, key, label)
+            np.testing.assert_allclose(got.acc, want["acc"], rtol=1e-9, atol=0)
+    # formulas of Evaluation (evaluator.py:40-75)
+    total = ev.kps_eval.reduce()
+    assert total.tp == sum(r["tp"] for k in ("anchor", "part") for r in case["result"][k].values())
+    assert 0.0 <= total.f1_score <= 1.0 and 0.0 <= total.recall <= 1.0
+
+
+@pytest.mark.gpu
+def test_cuda_matching_against_oracle_on_dense_batch(cuda_device):
+    """cfg2-sized noise batch with seeded ground truth: the kernel against the CPU restatement."""
+    from structuredetector_b200 import Decoder, ImageAnnotation, Keypoint, Object, ops
+    from structuredetector_b200.evaluator import Evaluator
+    from structuredetector_b200.synth import CONFIGS, make_raw, split_outputs
+    from tests.helpers import make_args
+    cfg = CONFIGS["cfg2"]
+    raw = make_raw(cfg, "noise", batch=6).to(cuda_device)
+    outs = split_outputs(raw, cfg.labels, cfg.parts)
+    dargs = make_args(cfg)
+    meta = Decoder(dargs)(outs, return_metadata=True)
+    packed = ops.decode_packed(outs, cfg.max_objects, cfg.max_parts, cfg.conf_threshold, cfg.dist_thresh)
+    labels, kinds = list(dargs._r_labels.values()), list(dargs._r_parts.values())
+    rng = np.random.default_rng(11)
+    anns, plain_gt = [], []
+    for ann in meta["annotation"]:
+        objs = []
+        for o in ann.objects:
+            if rng.random() < 0.7:
+                kps = [Keypoint(p.kind, p.x + rng.normal(0, 3), p.y + rng.normal(0, 3)) for p in o.parts if rng.random() < 0.7]
+                objs.append(Object(o.name, Keypoint("a", o.anchor.x + rng.normal(0, 4), o.anchor.y + rng.normal(0, 4)), kps))
+        anns.append(ImageAnnotation("gt", objs, img_size=(1931, 1297)))
+        plain_gt.append([(o.name, o.anchor.x, o.anchor.y, [(p.kind, p.x, p.y) for p in o.parts]) for o in objs])
+    args = SimpleNamespace(labels={l: i for i, l in enumerate(labels)}, parts={k: i for i, k in enumerate(kinds)},
+                           width=4 * cfg.width, height=4 * cfg.height, dist_threshold=0.02,
+                           conf_threshold=cfg.conf_threshold, down_ratio=4.0)
+    ev = Evaluator(args)
+    ev.accumulate_packed(packed, anns, (cfg.width, cfg.height))
+    want = {"anchor": {l: [0, 0, 0, []] for l in labels}, "part": {k: [0, 0, 0, []] for k in kinds}}
+    for ann, raw_parts, gts in zip(meta["annotation"], meta["raw_parts"], plain_gt):
+        res = EO.evaluate_image([(o.name, o.anchor.x, o.anchor.y, o.anchor.score) for o in ann.objects],
+                                [(p.kind, p.x, p.y, p.score) for p in raw_parts], gts, (1931, 1297),
+                                (args.width, args.height), args.dist_threshold, labels, kinds)
+        for key in want:
+            for label, (tp, npos, ndet, acc) in res[key].items():
+                t = want[key][label]
+                t[0] += tp; t[1] += npos; t[2] += ndet; t[3] += acc
+    for key, evals in (("anchor", ev.anchor_eval), ("part", ev.part_eval)):
+        for label, (tp, npos, ndet, acc) in want[key].items():
+            got = evals[label]
+            assert (got.tp, got.npos, got.ndet) == (tp, npos, ndet), (key, label)
+            np.testing.assert_allclose(got.acc, acc, rtol=1e-9, atol=0)
+    assert ev.anchor_eval.reduce().tp > 50 and ev.part_eval.reduce().tp > 50
