@@ -366,7 +366,7 @@ def main():
     step_s = ms_per_step * 1e-3
     roofline = {
         "bound": "hbm", "kernel": {"tile": "sdnet_peaks_tile_kernel (TMA tiles)", "tile_row_pairs": "sdnet_peaks_tile_kernel (TMA tiles over row pairs)",
-                                  "cta": "sdnet_peaks_cta_kernel", "warp": "sdnet_peaks_kernel (per-lane feed)"}[
+                                  "warp": "sdnet_peaks_kernel (per-lane feed)"}[
                            plan.peaks_path(outs["anchor_hm"], outs["part_hm"], outs["offsets"], outs["embeddings"])], "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
         "frac": achieved / peak_gbs, "traffic": traffic, "peak_source": peak_src,
         "kernel_ms": {"peaks": peaks_ms, "exact_select": exact_ms, "tail": tail_ms},

@@ -114,7 +114,6 @@ int sdnet_decode_launch(const SdnetDecodeParams* params, void* stream);
 #define SDNET_PATH_WARP 0           /* per-lane cp.async / converting feed: any shape, stride and alignment */
 #define SDNET_PATH_TILE 1           /* TMA tiles: base and strides multiples of 16 bytes, W % 4 == 0 */
 #define SDNET_PATH_TILE_ROW_PAIRS 2 /* TMA tiles over row pairs: fp16/bf16 with an 8-byte-multiple row pitch (W = 612), H even */
-#define SDNET_PATH_CTA 3            /* warp-specialised 1-D bulk copies (fp32; only with SDNET_PEAKS_PATH=cta) */
 int sdnet_decode_peaks_path(const SdnetDecodeParams* params);
 
 /* Profiling variant (bench.py's roofline leg): same work, but records CUDA events between the

@@ -13,7 +13,7 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent
 REPO = ROOT.parent
 SOURCES = [ROOT / "csrc" / "sdnet_decode.cu"]
-HEADERS = [REPO / "include" / "sdnet_decode.h"]
+HEADERS = [REPO / "include" / "sdnet_decode.h", *sorted((ROOT / "csrc").glob("*.cuh"))]
 OUTPUT = ROOT / "csrc" / "libsdnet_decode.so"
 
 NVCC_FLAGS = [
@@ -44,7 +44,7 @@ def is_stale() -> bool:
 def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and not is_stale():
         return OUTPUT
-    cmd = [nvcc_path(), *NVCC_FLAGS, f"-I{REPO / 'include'}", "-o", str(OUTPUT), *map(str, SOURCES)]
+    cmd = [nvcc_path(), *NVCC_FLAGS, f"-I{REPO / 'include'}", f"-I{ROOT / 'csrc'}", "-o", str(OUTPUT), *map(str, SOURCES)]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd))

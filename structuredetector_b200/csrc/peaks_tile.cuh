@@ -1,0 +1,427 @@
+// peaks_tile.cuh -- sdnet_peaks_tile_kernel: the default peaks kernel (TMA tensor-map tiles, autonomous warps).
+#pragma once
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// peaks kernel, TMA-tile form (the default fast path; needs 16 B-aligned rows)
+//
+// Every warp is an autonomous pipeline over one (plane, row strip, 128-column panel) unit.
+// An elected lane pulls 4-row x 136-column tiles (the panel plus four columns either side)
+// into the warp's private shared-memory ring with 2-D tensor-map bulk copies (TMA, SASS
+// UTMALDG), completion on one mbarrier per ring slot.  The tensor map is encoded with NaN
+// out-of-bounds fill: fmaxf ignores a NaN operand and every ordered comparison with NaN is
+// false, so out-of-image rows and columns behave exactly like max_pool2d's -inf padding with
+// no edge code at all.  Per group of four output rows the warp waits on one barrier, reads its
+// four centre rows (4 x LDS.128), takes the max of the 16 values and votes "does anything here
+// beat the pruning floor?"; only then does it look at single rows.  No warp ever waits for
+// another warp.
+// ---------------------------------------------------------------------------------------------
+constexpr int kGroupRows = 4;                                // output rows per TMA tile and per fast-path test
+constexpr int kTileCols = kPanelW + 8;
+constexpr int kTilePitchB = kTileCols * 4;                   // 544 B per ring row
+constexpr int kTileBytes = kGroupRows * kTilePitchB;         // 2176 B per TMA tile (17 x 128 B)
+constexpr int kTileWarps = 4;
+constexpr int kTileNG = 4;   // ring slots (tiles) per warp: 16 rows, two or three tiles in flight, 5 CTAs/SM
+constexpr int kWork = 128;   // per-warp work list: one byte per (row of the group, lane) whose 16-byte word holds a pixel above the floor
+// S = rows per TMA row (see the kernel).  Under S = 2 a tile arrives as two 2-row boxes and a TMA
+// destination must be 128-byte aligned: the second box sits at +1152 and a slot takes 2304 bytes.
+__host__ __device__ constexpr int tile_slot_bytes(int S) { return S == 1 ? kTileBytes : 2304; }
+__host__ __device__ constexpr int tile_smem_per_warp(int S) {
+  return ((kTileNG * tile_slot_bytes(S) + 32 + kBins * 8 + kBuf * 8 + kWork) + 127) / 128 * 128;
+}
+__host__ __device__ constexpr int tile_smem(int S) { return kTileWarps * tile_smem_per_warp(S); }
+constexpr int kOddBoxOff = 1152;  // S = 2: offset of the odd rows' box inside a slot
+constexpr int kOddShiftB = 8;     // S = 2: a box must start on a 16-byte boundary of global memory and odd rows start 8 bytes
+                                  // off one, so their box starts 4 columns early and their pixels sit 8 bytes further right
+
+// Element geometry of the tile kernel.  A lane owns one 16-byte word per row: 4 fp32 or 8 fp16/bf16
+// pixels, so a warp's panel is 128 or 256 columns and a ring row is 544 bytes either way.
+template <int DT>
+struct TileGeom {
+  static constexpr int kPx = DT == SDNET_DTYPE_F32 ? 4 : 8;  // pixels per lane per row = halo columns each side
+  static constexpr int kEsz = 16 / kPx;                       // bytes per element
+  static constexpr int kPanel = 32 * kPx;                     // columns per warp
+  static constexpr int kCols = kPanel + 2 * kPx;              // columns per tile row
+};
+static_assert(TileGeom<SDNET_DTYPE_F32>::kCols * 4 == kTilePitchB && TileGeom<SDNET_DTYPE_F16>::kCols * 2 == kTilePitchB, "ring row pitch");
+
+__device__ __forceinline__ void tma_tile_4d(u32 dst, const CUtensorMap* map, int x, int y, int c, int b, u32 bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+      ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(c), "r"(b), "r"(bar) : "memory");
+}
+__device__ __forceinline__ uint4 lds64x2(u32 addr) {  // 16 bytes from an 8-byte-aligned address
+  uint4 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.z), "=r"(v.w) : "r"(addr + 8));
+  return v;
+}
+__device__ __forceinline__ uint4 lds128u(u32 addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+
+// max of the 4 | 8 elements of one 16-byte word / of four words, as float; NaN elements (the TMA
+// out-of-bounds fill) are ignored by fmaxf and by max.f16x2 / max.bf16x2 alike
+template <int DT>
+struct TileMax;
+template <>
+struct TileMax<SDNET_DTYPE_F32> {
+  static __device__ __forceinline__ float word(const uint4& a) {
+    return fmaxf(fmaxf(__uint_as_float(a.x), __uint_as_float(a.y)), fmaxf(__uint_as_float(a.z), __uint_as_float(a.w)));
+  }
+  static __device__ __forceinline__ float group(const uint4& a, const uint4& b, const uint4& c, const uint4& d) {
+    return fmaxf(fmaxf(word(a), word(b)), fmaxf(word(c), word(d)));
+  }
+  static __device__ __forceinline__ float elem(u32 addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+  }
+  // one element in its storage format (here: the float's bits), max in that format, back to float
+  static __device__ __forceinline__ u32 raw(u32 addr) { return __float_as_uint(elem(addr)); }
+  static __device__ __forceinline__ u32 rmax(u32 a, u32 b) { return __float_as_uint(fmaxf(__uint_as_float(a), __uint_as_float(b))); }
+  static __device__ __forceinline__ float rfloat(u32 r) { return __uint_as_float(r); }
+};
+template <>
+struct TileMax<SDNET_DTYPE_F16> {
+  static __device__ __forceinline__ __half2 h2(u32 v) { return *reinterpret_cast<const __half2*>(&v); }
+  static __device__ __forceinline__ __half2 word2(const uint4& a) { return __hmax2(__hmax2(h2(a.x), h2(a.y)), __hmax2(h2(a.z), h2(a.w))); }
+  static __device__ __forceinline__ float fold(__half2 m) { return __half2float(__hmax(__low2half(m), __high2half(m))); }
+  static __device__ __forceinline__ float word(const uint4& a) { return fold(word2(a)); }
+  static __device__ __forceinline__ float group(const uint4& a, const uint4& b, const uint4& c, const uint4& d) {
+    return fold(__hmax2(__hmax2(word2(a), word2(b)), __hmax2(word2(c), word2(d))));
+  }
+  static __device__ __forceinline__ float elem(u32 addr) {
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+    return __half2float(__ushort_as_half(v));
+  }
+  // storage format: the 16 bits in the low half of a register (high half +0); max.f16x2 ignores NaN
+  static __device__ __forceinline__ u32 raw(u32 addr) {
+    u32 v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+  }
+  static __device__ __forceinline__ u32 rmax(u32 a, u32 b) {
+    const __half2 m = __hmax2(h2(a), h2(b));
+    return *reinterpret_cast<const u32*>(&m);
+  }
+  static __device__ __forceinline__ float rfloat(u32 r) { return __half2float(__ushort_as_half((unsigned short)r)); }
+};
+template <>
+struct TileMax<SDNET_DTYPE_BF16> {
+  static __device__ __forceinline__ __nv_bfloat162 h2(u32 v) { return *reinterpret_cast<const __nv_bfloat162*>(&v); }
+  static __device__ __forceinline__ __nv_bfloat162 word2(const uint4& a) { return __hmax2(__hmax2(h2(a.x), h2(a.y)), __hmax2(h2(a.z), h2(a.w))); }
+  static __device__ __forceinline__ float fold(__nv_bfloat162 m) { return __bfloat162float(__hmax(__low2bfloat16(m), __high2bfloat16(m))); }
+  static __device__ __forceinline__ float word(const uint4& a) { return fold(word2(a)); }
+  static __device__ __forceinline__ float group(const uint4& a, const uint4& b, const uint4& c, const uint4& d) {
+    return fold(__hmax2(__hmax2(word2(a), word2(b)), __hmax2(word2(c), word2(d))));
+  }
+  static __device__ __forceinline__ float elem(u32 addr) {
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+    return __uint_as_float((u32)v << 16);
+  }
+  static __device__ __forceinline__ u32 raw(u32 addr) {
+    u32 v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+  }
+  static __device__ __forceinline__ u32 rmax(u32 a, u32 b) {
+    const __nv_bfloat162 m = __hmax2(h2(a), h2(b));
+    return *reinterpret_cast<const u32*>(&m);
+  }
+  static __device__ __forceinline__ float rfloat(u32 r) { return __uint_as_float(r << 16); }
+};
+
+// Byte offset of ring row rr (0..15) inside the ring.  S = 1: rows in order.  S = 2 (rows loaded as
+// even/odd pairs, see the kernel): a slot holds rows 0, 2 at +0, +544 and rows 1, 3 at +1152, +1696,
+// the odd rows shifted right by kOddShiftB bytes.
+template <int S>
+__device__ __forceinline__ u32 ring_row_off(u32 rr) {
+  if (S == 1) return rr * kTilePitchB;
+  return (rr >> 2) * tile_slot_bytes(2) + (rr & 1u) * (kOddBoxOff + kOddShiftB) + ((rr >> 1) & 1u) * kTilePitchB;
+}
+
+// Settle the work list of one 4-row group.  Entry e = (row in group << 5) | lane names one 16-byte
+// word of centre pixels holding at least one pixel above the floor; kPx consecutive lanes take the
+// pixels of an entry, so records leave in (row, column) = index order.  A lane whose pixel beats the
+// floor reads the pixel's (2R+1)^2 window from the ring with scalar loads (columns and rows outside
+// the image hold NaN or -inf and never win a max), classifies it like classify_row and appends a
+// (logit, index) record to the warp's candidate buffer.
+// `row0` = ring row of the window's first row for group row 0 (the centre is R rows further).
+template <int R, int DT, int S>
+__device__ __forceinline__ void settle_entries(UnitState& st, const unsigned char* work, int nent, u32 ring_s, u32 row0,
+                                               float floorx, u32 idx0, int W, bool pre, u64* buf, u32* hist, int* minx,
+                                               const SharedFloors& sf, int* count_ptr, u64* __restrict__ list, int cap,
+                                               int K, int lane, float xscale, float satx) {
+  constexpr float kNearTie = Num<DT>::kNear, kHiZone = Num<DT>::kHi, kLoZone = Num<DT>::kLo, kNearTie2 = Num<DT>::kNear2,
+                  kHiZone2 = Num<DT>::kHi2;
+  constexpr u32 kRowMask = kTileNG * kGroupRows - 1;
+  constexpr int kPx = TileGeom<DT>::kPx, kEsz = TileGeom<DT>::kEsz;
+  const int nslots = kPx * nent;
+  for (int base = 0; base < nslots; base += 32) {  // warp-uniform
+    const int slot = base + lane;
+    const u32 e = slot < nslots ? work[slot / kPx] : 0u;
+    const u32 i = e >> 5, colp = kPx * (e & 31u) + (u32)(slot % kPx);
+    const u32 col_addr = ring_s + (kPx + colp - R) * kEsz;  // first column of the window
+    const float x = TileMax<DT>::elem(col_addr + R * kEsz + ring_row_off<S>((row0 + i + R) & kRowMask));
+    bool keep = slot < nslots && x > floorx;
+    if (keep && !pre) {
+      // window max in the storage format (no conversions for fp16/bf16), one accumulator per window row
+      u32 hr[2 * R + 1];
+#pragma unroll
+      for (int d = 0; d <= 2 * R; ++d) {
+        const u32 a = col_addr + ring_row_off<S>((row0 + i + d) & kRowMask);
+        u32 v[2 * R + 1];
+#pragma unroll
+        for (int q = 0; q <= 2 * R; ++q) v[q] = TileMax<DT>::raw(a + kEsz * q);
+        hr[d] = v[0];
+#pragma unroll
+        for (int q = 1; q <= 2 * R; ++q) hr[d] = TileMax<DT>::rmax(hr[d], v[q]);
+      }
+#pragma unroll
+      for (int d = 1; d <= 2 * R; ++d) hr[0] = TileMax<DT>::rmax(hr[0], hr[d]);
+      const float h = fmaxf(x, TileMax<DT>::rfloat(hr[0]));  // an all-NaN window cannot happen: the centre is in it
+      if (x != h) {
+        const bool amb = (x >= h - kNearTie) || (h > kHiZone && x >= h - kNearTie2) ||
+                         (h > kHiZone2 && x > kHiZone2 - 1.0f) || (h < kLoZone);  // same zones as classify_row
+        keep = amb && Num<DT>::act(x) == Num<DT>::act(h);  // rare
+      }
+    }
+    const u32 m = __ballot_sync(0xffffffffu, keep);
+    if (m) {  // warp-uniform
+      if (st.nbuf + __popc(m) > kBuf) {
+        __syncwarp();
+        flush_candidates<DT>(st, buf, hist, minx, sf, count_ptr, list, cap, K, lane, pre, xscale, satx);
+      }
+      if (keep) buf[st.nbuf + __popc(m & ((1u << lane) - 1u))] = ((u64)__float_as_uint(x) << 32) | (idx0 + i * (u32)W + colp);
+      st.nbuf += __popc(m);
+    }
+  }
+}
+
+// S = 2 only: a tile that touches the left or right image edge has read across a row boundary (see
+// the kernel): overwrite what is not this row's data with -inf.  `slot_s` = the tile's ring slot.
+template <int DT>
+__device__ __forceinline__ void tile_fix_edges(u32 slot_s, int x0, int W, int lane) {
+  constexpr int kPx = TileGeom<DT>::kPx;
+  constexpr u32 kNinf2 = DT == SDNET_DTYPE_F16 ? 0xFC00FC00u : (DT == SDNET_DTYPE_BF16 ? 0xFF80FF80u : 0xFF800000u);
+  if (x0 < 0) {  // odd rows (the second box): the 12 columns left of column 0 hold the end of the row above
+    if (lane < 2) {
+      const u32 a = slot_s + kOddBoxOff + lane * kTilePitchB;
+      asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(a), "r"(kNinf2) : "memory");
+      asm volatile("st.shared.v2.u32 [%0], {%1, %1};" ::"r"(a + 16), "r"(kNinf2) : "memory");
+    }
+  }
+  if (x0 + TileGeom<DT>::kCols > W) {  // even rows (the first box): columns >= W hold the start of the row below
+    // word w of a ring row covers columns x0 + kPx w ..; under S = 2 W is a multiple of kPx/2, not of kPx
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int w = k == 0 ? lane + 1 : 33;  // lane's own centre word; lane 31 also takes the right halo word
+      if (k == 1 && lane != 31) break;
+      const int first = x0 + kPx * w;
+      const u32 a = slot_s + 16 * w;
+      if (first >= W) {
+        asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(a), "r"(kNinf2) : "memory");
+        asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(a + kTilePitchB), "r"(kNinf2) : "memory");
+      } else if (first + kPx / 2 >= W) {
+        asm volatile("st.shared.v2.u32 [%0], {%1, %1};" ::"r"(a + 8), "r"(kNinf2) : "memory");
+        asm volatile("st.shared.v2.u32 [%0], {%1, %1};" ::"r"(a + 8 + kTilePitchB), "r"(kNinf2) : "memory");
+      }
+    }
+  }
+}
+
+// S = rows per TMA row: 1 when the row pitch is a multiple of 16 bytes.  S = 2 serves fp16/bf16 maps
+// whose pitch is an odd multiple of 8 bytes (W = 612): the tensor map then describes PAIRS of image
+// rows as one row of pitch + W elements, a tile is two 2-row boxes -- the even rows at x, the odd rows
+// at pitch + x - 4 (a box has to start on a 16-byte boundary, measured: anything else is an illegal
+// instruction) -- and lands in its slot as rows 0, 2 | 1, 3 with the odd rows 8 bytes further right.
+// At the image edges such a box reads across the row boundary; tile_fix_edges repairs that after the wait.
+template <int R, int DT, int S>
+__global__ void __launch_bounds__(kTileWarps * 32, 5)
+sdnet_peaks_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_constant__ CUtensorMap tm_anchor,
+                        const __grid_constant__ CUtensorMap tm_part) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int NG = kTileNG;
+  constexpr u32 kRowMask = NG * kGroupRows - 1;
+  constexpr int kPx = TileGeom<DT>::kPx, kPanel = TileGeom<DT>::kPanel;
+  static_assert((NG & (NG - 1)) == 0, "slot and parity of a tile come from its running number by mask and shift");
+  static_assert(S == 1 || (R == 2 && DT != SDNET_DTYPE_F32), "row pairs: tiles must start on an even row");
+  pdl_launch_dependents();
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  constexpr u32 kSlotB = tile_slot_bytes(S);
+  unsigned char* wbase = smem_raw + (size_t)warp * tile_smem_per_warp(S);
+  const u32 ring_s = smem_u32(wbase);
+  const u32 bars_s = ring_s + NG * kSlotB;
+  u32* hist = reinterpret_cast<u32*>(wbase + NG * kSlotB + 32);
+  int* minx = reinterpret_cast<int*>(hist + kBins);
+  u64* buf = reinterpret_cast<u64*>(minx + kBins);
+  unsigned char* work = reinterpret_cast<unsigned char*>(buf + kBuf);
+  const bool pre = p.pre_activated != 0;
+  const float xscale = pre ? kPreScale : 1.0f;
+  const float satx = pre ? CUDART_INF_F : kSatX;
+  const int C = p.M + p.N;
+  const int H = p.H, W = p.W;
+  const u32 ring_own = ring_s + (u32)(16 + 16 * lane);  // this lane's word inside a ring row
+  const u32 lt = (1u << lane) - 1u;
+
+  if (lane == 0) {
+    for (int i = 0; i < NG; ++i) mbar_init(bars_s + 8 * i, 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
+
+  // Tiles are numbered in one running sequence over all units this warp processes: tile number n
+  // lives in ring slot n % NG (ring rows 4 (n % NG) ..) and is the (n / NG)-th use of that slot, so
+  // the slot's mbarrier is waited with parity (n / NG) & 1.  Every issued tile is waited exactly once.
+  u32 tile_n = 0;
+  for (;;) {
+    u32 unit = 0;
+    if (lane == 0) unit = atomicAdd(p.sched, 1u);
+    unit = __shfl_sync(0xffffffffu, unit, 0);
+    if (unit >= (u32)p.units) break;
+    int panel, plane_id, r_begin, r_end;
+    if (unit < (u32)p.tier1_units) {
+      panel = unit % p.panels;
+      plane_id = unit / p.panels;
+      r_begin = 0;
+      r_end = H;
+    } else {
+      const u32 u2 = unit - (u32)p.tier1_units;
+      panel = u2 % p.panels;
+      const int t1 = u2 / p.panels;
+      plane_id = p.tier1_planes + t1 / p.strips;
+      r_begin = (t1 % p.strips) * p.rows_per_strip;
+      r_end = min(H, r_begin + p.rows_per_strip);
+    }
+    const int b = plane_id / C, c = plane_id % C;
+    const bool is_anchor = c < p.M;
+    const CUtensorMap* tmap = is_anchor ? &tm_anchor : &tm_part;
+    const int csel = is_anchor ? c : c - p.M;
+    const int K = is_anchor ? p.K : p.P;
+    const int x0 = panel * kPanel - kPx;  // first column of the tile; tensor-map coordinates count 4-byte units
+    const int xc = DT == SDNET_DTYPE_F32 ? x0 : x0 >> 1;
+    const bool edge = S == 2 && (x0 < 0 || x0 + TileGeom<DT>::kCols > W);
+    const int nrows = r_end - r_begin;
+    const int groups = (nrows + 2 * R + kGroupRows - 1) / kGroupRows;  // tiles of the unit
+    const int groups_out = (nrows + kGroupRows - 1) / kGroupRows;
+    u64* __restrict__ list = p.lists + (size_t)plane_id * p.cap;
+    int* count_ptr = p.counts + plane_id;
+    int* gfloor_ptr = p.gfloor + plane_id;
+    SharedFloors sf;
+    sf.ghist = p.ghist + (size_t)plane_id * kFineBins;
+    sf.gfloor = gfloor_ptr;
+
+    UnitState st;
+    st.floorx = shared_floor<DT>(__ldcg(gfloor_ptr), xscale);
+    st.emitted = 0;
+    st.nbuf = 0;
+    __syncwarp();  // everyone is done with the previous unit's ring, histogram and buffer
+    *reinterpret_cast<uint4*>(hist + 4 * lane) = make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<int4*>(minx + 4 * lane) = make_int4(0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff);
+    __syncwarp();
+
+    // tile k of the unit = image rows r_begin - R + 4k ..; running number tile_n + k
+    auto issue = [&](u32 s, int y) {  // lane 0: pull the tile whose first image row is y into slot s
+      mbar_arrive_expect_tx(bars_s + 8 * s, kTileBytes);
+      if (S == 1) {
+        tma_tile_4d(ring_s + s * kSlotB, tmap, xc, y, csel, b, bars_s + 8 * s);
+      } else {  // y is even (r_begin even, R = 2): rows y, y+2 then rows y+1, y+3
+        tma_tile_4d(ring_s + s * kSlotB, tmap, xc, y >> 1, csel, b, bars_s + 8 * s);
+        tma_tile_4d(ring_s + s * kSlotB + kOddBoxOff, tmap, xc + p.odd_x - kOddShiftB / 4, y >> 1, csel, b, bars_s + 8 * s);
+      }
+    };
+    auto wait_tile = [&](u32 n) {
+      mbar_wait(bars_s + 8 * (n & (NG - 1)), (n >> 2) & 1u);
+      if (edge) {  // warp-uniform
+        tile_fix_edges<DT>(ring_s + (n & (NG - 1)) * kSlotB, x0, W, lane);
+        __syncwarp();
+      }
+    };
+    int y_next = r_begin - R;  // first image row of the next tile to issue
+    if (lane == 0) {
+      const int first = min(NG, groups);
+      for (int k = 0; k < first; ++k) issue((tile_n + (u32)k) & (NG - 1), y_next + kGroupRows * k);
+    }
+    y_next += kGroupRows * NG;
+    int gfloor_seen = 0;
+    constexpr int poll_mask = 3;  // measured at 128-row strips: polling every group 0.179 ms, every 4th 0.136 ms, every 8th 0.146 ms
+    u32 idx0 = (u32)(r_begin * W + panel * kPanel);  // flat index of the group's row 0, panel column 0
+    wait_tile(tile_n);
+    for (int g = 0; g < groups_out; ++g, idx0 += (u32)(kGroupRows * W)) {
+      const u32 n = tile_n + (u32)g;  // tile holding the group's first window row
+      if (R == 2 || g + 1 < groups) wait_tile(n + 1);
+      if ((g & poll_mask) == 0) {
+        // every 16 rows: apply the plane-wide floor fetched one period ago
+        // and start the next fetch.  The load writes straight into the register it will be read
+        // from a period later, so its latency is never waited for.
+        st.floorx = fmaxf(st.floorx, shared_floor<DT>(gfloor_seen, xscale));
+        asm volatile("ld.global.cg.s32 %0, [%1];" : "=r"(gfloor_seen) : "l"(gfloor_ptr) : "memory");
+      }
+      // window rows of group row i are ring rows row0 + i .. row0 + i + 2R; its centre row is row0 + i + R
+      const u32 row0 = (n * kGroupRows) & kRowMask;
+      uint4 c0, c1, c2, c3;
+      if (R == 2) {  // centres: rows 2, 3 of this tile's slot and rows 0, 1 of the next
+        const u32 a01 = ring_own + (n & (NG - 1)) * kSlotB, a23 = ring_own + ((n + 1) & (NG - 1)) * kSlotB;
+        if (S == 1) {
+          c0 = lds128u(a01 + 2 * kTilePitchB); c1 = lds128u(a01 + 3 * kTilePitchB);
+          c2 = lds128u(a23); c3 = lds128u(a23 + kTilePitchB);
+        } else {  // a slot holds rows 0, 2 in its first box and rows 1, 3 in its second
+          c0 = lds128u(a01 + kTilePitchB); c1 = lds64x2(a01 + kOddBoxOff + kOddShiftB + kTilePitchB);
+          c2 = lds128u(a23); c3 = lds64x2(a23 + kOddBoxOff + kOddShiftB);
+        }
+      } else {  // S == 1
+        const u32 a012 = ring_own + (row0 + 1) * kTilePitchB, a3 = ring_own + ((row0 + 4) & kRowMask) * kTilePitchB;
+        c0 = lds128u(a012); c1 = lds128u(a012 + kTilePitchB); c2 = lds128u(a012 + 2 * kTilePitchB); c3 = lds128u(a3);
+      }
+      if (__any_sync(0xffffffffu, TileMax<DT>::group(c0, c1, c2, c3) > st.floorx)) {
+        // Something in these four rows beats the floor.  Pixel-centric slow path: (1) every (row, lane)
+        // whose word of centre pixels holds one above the floor goes on the warp's work list, one
+        // ballot per row, row-major; (2) settle_entries gives each listed pixel a lane of its own.
+        // In the last, partial group of a strip the rows past its end belong to the next strip: they
+        // may raise this alarm for nothing but are never listed.
+        const float floorx = st.floorx;
+        const int rows_here = nrows - g * kGroupRows;
+        int nent = 0;
+#pragma unroll
+        for (int i = 0; i < kGroupRows; ++i) {
+          const uint4 ci = i == 0 ? c0 : (i == 1 ? c1 : (i == 2 ? c2 : c3));
+          const bool mine = TileMax<DT>::word(ci) > floorx && i < rows_here;
+          const u32 bm = __ballot_sync(0xffffffffu, mine);
+          if (mine) work[nent + __popc(bm & lt)] = (unsigned char)((i << 5) | lane);
+          nent += __popc(bm);
+        }
+        __syncwarp();
+        settle_entries<R, DT, S>(st, work, nent, ring_s, row0, floorx, idx0, W, pre, buf, hist, minx, sf, count_ptr, list,
+                                 p.cap, K, lane, xscale, satx);
+        // while the plane has no floor yet, publish early and often; later only in batches
+        if (st.nbuf >= 16 || (st.nbuf > 0 && gfloor_seen <= 0)) {
+          __syncwarp();
+          flush_candidates<DT>(st, buf, hist, minx, sf, count_ptr, list, p.cap, K, lane, pre, xscale, satx);
+        }
+      }
+      // every lane's reads of the group's first tile are done (the votes above): refill its slot
+      // with the tile NG ahead
+      __syncwarp();
+      if (lane == 0 && g + NG < groups) {
+        if (edge) fence_proxy_async();  // the slot was patched with ordinary stores
+        issue(n & (NG - 1), y_next);
+      }
+      y_next += kGroupRows;
+    }
+    tile_n += (u32)groups;
+    if (st.nbuf) {
+      __syncwarp();
+      flush_candidates<DT>(st, buf, hist, minx, sf, count_ptr, list, p.cap, K, lane, pre, xscale, satx);
+    }
+  }
+}
+
+
+}  // namespace

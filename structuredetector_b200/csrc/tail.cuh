@@ -1,0 +1,356 @@
+// tail.cuh -- sdnet_tail_kernel (per-image select, sort, gather, grouping, packed stores) and sdnet_activate_kernel.
+#pragma once
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// tail kernel: select + sort + gather + group, one CTA per image
+// ---------------------------------------------------------------------------------------------
+struct TailParams {
+  View4 offsets, embeddings;
+  int B, M, N, H, W, K, P;
+  int cap;
+  int pre_activated, no_grouping;
+  float conf, dist_abs;
+  const u64* lists;
+  const int* counts;
+  float* anchor_out;
+  float* part_out;
+  long long* anchor_inds;
+  long long* part_inds;
+  float* part_emb;
+  int* assign;
+  int* out_counts;
+  int* diag;
+  const int* exact_flags;  // [planes] 1 if the exact select rewrote the list
+  int n_dest;              // fused gather: every output is stored n_dest times, at ptr + dest_delta[j]
+  long long dest_delta[SDNET_MAX_DEST];
+};
+
+// Store one output value locally (n_dest == 0) or into every destination copy of the output blob
+// (fused detection gather: peer-mapped symmetric memory, plain st.global over NVLink).
+template <typename T>
+__device__ __forceinline__ void store_out(const TailParams& p, T* ptr, const T& v) {
+  if (p.n_dest == 0) {
+    *ptr = v;
+  } else {
+    for (int j = 0; j < p.n_dest; ++j) *reinterpret_cast<T*>(reinterpret_cast<char*>(ptr) + p.dest_delta[j]) = v;
+  }
+}
+
+__device__ __forceinline__ u64 make_comp(u64 rec, int c_local) {
+  // rec = key:32 | idx:32  ->  key:32 | (255-c):8 | (0xFFFFFF-idx):24 ; larger = earlier in the output
+  const u32 key = (u32)(rec >> 32);
+  const u32 idx = (u32)rec;
+  return ((u64)key << 32) | ((u64)(255u - (u32)c_local) << 24) | (u64)(0xFFFFFFu - idx);
+}
+
+// The tail CTA is split into two teams of kTeamThreads threads that work concurrently: team 0
+// selects the anchors, team 1 the parts; each has its own sort buffer and syncs on its own named
+// barrier.  They meet once, before the grouping.
+constexpr int kTeamThreads = 256;
+
+struct Team {
+  int tid;    // thread index inside the team
+  int id;     // 0 = anchors, 1 = parts
+  __device__ __forceinline__ void sync() const {
+    asm volatile("bar.sync %0, %1;" ::"r"(id + 1), "r"(kTeamThreads) : "memory");
+  }
+};
+
+__device__ void bitonic_sort_desc(const Team& tm, u64* s, int n /* power of two */) {
+  for (int k = 2; k <= n; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tm.tid; i < n; i += kTeamThreads) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const u64 a = s[i], b = s[ixj];
+          const bool desc = (i & k) == 0;
+          if (desc ? (a < b) : (a > b)) { s[i] = b; s[ixj] = a; }
+        }
+      }
+      tm.sync();
+    }
+  }
+}
+
+// Select the `want` largest composites of planes [c0, c0+nc) of image b into s_sel (sorted
+// descending).  Returns the number selected (< want only when fewer candidates exist).
+__device__ int select_group(const Team& tm, const TailParams& p, int b, int c0, int nc, int want, u64* s_sel,
+                            u32* s_hist, int* s_misc) {
+  const int C = p.M + p.N;
+  const int tid = tm.tid;
+  // total candidates
+  if (tid == 0) {
+    int tot = 0;
+    for (int c = 0; c < nc; ++c) tot += min(p.counts[(size_t)b * C + c0 + c], p.cap);
+    s_misc[0] = tot;
+    s_misc[1] = 0;  // collected
+  }
+  tm.sync();
+  const int total = s_misc[0];
+  u64 prefix = 0;   // value of the top `bits` bits that boundary elements share
+  int bits = 0;
+  // radix-refine until what is left (everything certainly selected + the boundary bucket) is a
+  // small sort: the bitonic network below costs O(n log^2 n) and dominated this kernel when it
+  // was handed the full 2048-element buffer
+  const int target = min(kSortN, max(want + 64, 128));
+  if (total > target) {
+    int need = want;      // how many still have to come from the boundary bucket
+    int certain = 0;      // elements strictly above the boundary bucket
+    for (int level = 0; level < 8; ++level) {
+      const int shift = 56 - 8 * level;
+      for (int i = tid; i < 256; i += kTeamThreads) s_hist[i] = 0;
+      tm.sync();
+      for (int c = 0; c < nc; ++c) {
+        const int n = min(p.counts[(size_t)b * C + c0 + c], p.cap);
+        const u64* list = p.lists + ((size_t)b * C + c0 + c) * p.cap;
+        for (int i = tid; i < n; i += kTeamThreads) {
+          const u64 v = make_comp(list[i], c);
+          if (bits == 0 || (v >> (64 - bits)) == prefix) atomicAdd(&s_hist[(u32)(v >> shift) & 0xffu], 1u);
+        }
+      }
+      tm.sync();
+      if (tid < 32) {
+        // lane l owns digits 8l..8l+7; suffix-scan from the top
+        u32 loc[8], sum = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { loc[q] = s_hist[8 * tid + q]; sum += loc[q]; }
+        u32 suf = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          u32 t = __shfl_down_sync(0xffffffffu, suf, d);
+          if (tid + d < 32) suf += t;
+        }
+        const u32 mask = __ballot_sync(0xffffffffu, suf >= (u32)need);
+        const int L = 31 - __clz(mask);  // mask != 0 because the bucket holds >= need elements
+        if (tid == L) {
+          u32 above = suf - sum;
+          int dsel = 8 * L;
+          for (int q = 7; q >= 0; --q) {
+            if (above + loc[q] >= (u32)need) { dsel = 8 * L + q; break; }
+            above += loc[q];
+          }
+          s_misc[2] = dsel;
+          s_misc[3] = (int)above;                 // elements in this bucket with a larger digit
+          s_misc[4] = (int)s_hist[dsel];          // size of the new boundary bucket
+        }
+      }
+      tm.sync();
+      const int dsel = s_misc[2], above = s_misc[3], binc = s_misc[4];
+      certain += above;
+      need -= above;
+      prefix = (prefix << 8) | (u64)dsel;
+      bits += 8;
+      tm.sync();
+      if (certain + binc <= target) break;  // everything at or above the boundary bucket is a small sort
+    }
+  }
+  // collect: all elements whose top `bits` bits are >= prefix
+  for (int c = 0; c < nc; ++c) {
+    const int n = min(p.counts[(size_t)b * C + c0 + c], p.cap);
+    const u64* list = p.lists + ((size_t)b * C + c0 + c) * p.cap;
+    for (int i = tid; i < n; i += kTeamThreads) {
+      const u64 v = make_comp(list[i], c);
+      if (bits == 0 || (v >> (64 - bits)) >= prefix) {
+        const int slot = atomicAdd(&s_misc[1], 1);
+        if (slot < kSortN) s_sel[slot] = v;
+      }
+    }
+  }
+  tm.sync();
+  const int got = min(s_misc[1], kSortN);
+  int n2 = 32;
+  while (n2 < got) n2 <<= 1;
+  for (int i = got + tid; i < n2; i += kTeamThreads) s_sel[i] = 0;
+  tm.sync();
+  bitonic_sort_desc(tm, s_sel, n2);
+  return min(got, want);
+}
+
+// Slots [have, want) of a group are the zero-valued entries torch.topk pads with: under
+// (value desc, index asc) they are the lowest-index pixels of the group's first plane that
+// did not survive NMS.  All of them lie below index `want`.
+__device__ void zero_fill(const Team& tm, const TailParams& p, int b, int c0, int have, int want, u64* s_sel,
+                          u32* s_bits) {
+  const int C = p.M + p.N;
+  const int tid = tm.tid;
+  const int words = (want + 31) / 32;
+  for (int i = tid; i < words; i += kTeamThreads) s_bits[i] = 0;
+  tm.sync();
+  const int n = min(p.counts[(size_t)b * C + c0], p.cap);
+  const u64* list = p.lists + ((size_t)b * C + c0) * p.cap;
+  for (int i = tid; i < n; i += kTeamThreads) {
+    const u32 idx = (u32)list[i];
+    if (idx < (u32)want) atomicOr(&s_bits[idx >> 5], 1u << (idx & 31));
+  }
+  tm.sync();
+  for (int s = have + tid; s < want; s += kTeamThreads) {
+    int rank = s - have;  // rank-th non-peak index
+    int w = 0;
+    for (; w < words; ++w) {
+      const int z = 32 - __popc(s_bits[w]);
+      if (rank < z) break;
+      rank -= z;
+    }
+    const u32 free_mask = ~s_bits[w];
+    const u32 bit = __fns(free_mask, 0, rank + 1);
+    const u32 idx = (u32)(w * 32) + bit;
+    // key 0 (score 0.0), class 0
+    s_sel[s] = ((u64)255u << 24) | (u64)(0xFFFFFFu - idx);
+  }
+  tm.sync();
+}
+
+__device__ __forceinline__ float key_to_score(u32 key, bool pre) {
+  if (!pre) return __uint_as_float(key);
+  const u32 bits = (key == 0) ? 0u : ((key & 0x80000000u) ? (key & 0x7fffffffu) : ~key);
+  return __uint_as_float(bits);
+}
+
+template <int DT>
+__global__ void __launch_bounds__(2 * kTeamThreads) sdnet_tail_kernel(const __grid_constant__ TailParams p) {
+  __shared__ u64 s_sel[2][kSortN];
+  __shared__ u32 s_hist[2][256];
+  __shared__ int s_misc[2][8];
+  __shared__ float s_ax[SDNET_MAX_TOPK], s_ay[SDNET_MAX_TOPK];
+  __shared__ int s_cnt[2];
+  const int b = blockIdx.x;
+  Team tm;
+  tm.id = threadIdx.x / kTeamThreads;
+  tm.tid = threadIdx.x % kTeamThreads;
+  const int W = p.W;
+  const bool pre = p.pre_activated != 0;
+  if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
+  pdl_wait();  // candidate lists (peaks kernel, possibly rewritten by the exact select) are final
+  __syncthreads();
+  typedef typename Num<DT>::In In;
+  const In* offx = static_cast<const In*>(p.offsets.data) + (long long)b * p.offsets.sb;
+  const In* offy = offx + p.offsets.sc;
+  const long long osh = p.offsets.sh;
+  u64* sel = s_sel[tm.id];
+
+  if (tm.id == 0) {
+    // ---- anchors
+    const int have = select_group(tm, p, b, 0, p.M, p.K, sel, s_hist[0], s_misc[0]);
+    if (have < p.K) zero_fill(tm, p, b, 0, have, p.K, sel, s_hist[0]);
+    int n_valid = 0;
+    for (int s = tm.tid; s < p.K; s += kTeamThreads) {
+      const u64 v = sel[s];
+      const int cls = 255 - (int)((v >> 24) & 0xffu);
+      const u32 idx = 0xFFFFFFu - (u32)(v & 0xFFFFFFu);
+      const int yy = idx / W, xx = idx - yy * W;
+      const float score = key_to_score((u32)(v >> 32), pre);
+      const float x = __fadd_rn((float)xx, Num<DT>::to_float(__ldg(offx + (long long)yy * osh + xx)));
+      const float y = __fadd_rn((float)yy, Num<DT>::to_float(__ldg(offy + (long long)yy * osh + xx)));
+      store_out(p, reinterpret_cast<float4*>(p.anchor_out) + (size_t)b * p.K + s, make_float4(x, y, score, (float)cls));
+      store_out(p, p.anchor_inds + (size_t)b * p.K + s, (long long)idx);
+      const bool valid = score > p.conf;
+      // masked anchors sit at (+1e6, +1e6): decoders.py:85-86
+      s_ax[s] = valid ? x : kFar;
+      s_ay[s] = valid ? y : kFar;
+      n_valid += valid ? 1 : 0;
+    }
+    if (n_valid) atomicAdd(&s_cnt[0], n_valid);
+  } else {
+    // ---- parts
+    const int have = select_group(tm, p, b, p.M, p.N, p.P, sel, s_hist[1], s_misc[1]);
+    if (have < p.P) zero_fill(tm, p, b, p.M, have, p.P, sel, s_hist[1]);
+    const In* embx = p.embeddings.data ? static_cast<const In*>(p.embeddings.data) + (long long)b * p.embeddings.sb : nullptr;
+    const In* emby = embx ? embx + p.embeddings.sc : nullptr;
+    const long long esh = p.embeddings.sh;
+    int n_valid = 0;
+    for (int s = tm.tid; s < p.P; s += kTeamThreads) {
+      const u64 v = sel[s];
+      const int cls = 255 - (int)((v >> 24) & 0xffu);
+      const u32 idx = 0xFFFFFFu - (u32)(v & 0xFFFFFFu);
+      const int yy = idx / W, xx = idx - yy * W;
+      const float score = key_to_score((u32)(v >> 32), pre);
+      const float x = __fadd_rn((float)xx, Num<DT>::to_float(__ldg(offx + (long long)yy * osh + xx)));
+      const float y = __fadd_rn((float)yy, Num<DT>::to_float(__ldg(offy + (long long)yy * osh + xx)));
+      float ex = 0.f, ey = 0.f;
+      if (embx) {
+        ex = Num<DT>::to_float(__ldg(embx + (long long)yy * esh + xx));
+        ey = Num<DT>::to_float(__ldg(emby + (long long)yy * esh + xx));
+      }
+      const float ox = __fadd_rn(x, ex), oy = __fadd_rn(y, ey);
+      float2* po = reinterpret_cast<float2*>(p.part_out + ((size_t)b * p.P + s) * 6);
+      store_out(p, po + 0, make_float2(x, y));
+      store_out(p, po + 1, make_float2(score, (float)cls));
+      store_out(p, po + 2, make_float2(ox, oy));
+      store_out(p, p.part_inds + (size_t)b * p.P + s, (long long)idx);
+      if (p.part_emb) store_out(p, reinterpret_cast<float2*>(p.part_emb) + (size_t)b * p.P + s, make_float2(ex, ey));
+      const bool valid = score > p.conf;
+      n_valid += valid ? 1 : 0;
+      // masked parts sit at (-1e6, -1e6): decoders.py:80-81.  The slot's composite is no longer
+      // needed: keep the part's origin there for the grouping pass.
+      reinterpret_cast<float2*>(sel)[s] = make_float2(valid ? ox : -kFar, valid ? oy : -kFar);
+    }
+    if (n_valid) atomicAdd(&s_cnt[1], n_valid);
+  }
+  __syncthreads();
+
+  // ---- grouping: every part to its nearest anchor (first minimum), gated by the distance threshold
+  // (reference: hypot utils.py:422-437, min(dim=1) decoders.py:99).  A part is shared by g lanes of one
+  // warp, lane `sub` taking anchors sub, sub + g, ...  The square root is monotone, so the smallest
+  // distance is the root of the smallest squared distance m2 -- but two different squares can round to
+  // the same root and the reference's min() then keeps the FIRST anchor.  Hence two sweeps without a
+  // root in the loop: m2, then the first anchor whose square lies within 1e-6 of m2 (a root can only
+  // tie if its square is within 2^-22 relative) AND whose root equals root(m2).
+  const float2* origin = reinterpret_cast<const float2*>(s_sel[1]);
+  int g = 32;
+  while (g > 1 && p.P * g > (int)blockDim.x) g >>= 1;
+  const int sub = threadIdx.x & (g - 1), per_pass = blockDim.x / g;
+  for (int s0 = 0; s0 < p.P; s0 += per_pass) {  // block-uniform
+    const int s = s0 + (int)threadIdx.x / g;
+    const bool live = s < p.P;
+    int slot = -1;
+    if (!p.no_grouping) {  // kernel-uniform
+      const float qx = live ? origin[s].x : 0.f, qy = live ? origin[s].y : 0.f;
+      float m2 = CUDART_INF_F;
+      for (int a = sub; a < p.K; a += g) {
+        const float dx = __fsub_rn(qx, s_ax[a]), dy = __fsub_rn(qy, s_ay[a]);
+        m2 = fminf(m2, __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+      }
+      for (int w = g >> 1; w > 0; w >>= 1) m2 = fminf(m2, __shfl_xor_sync(0xffffffffu, m2, w));
+      const float best = __fsqrt_rn(m2), near = m2 * 1.000001f;
+      int arg = 0x7fffffff;
+      for (int a = sub; a < p.K; a += g) {
+        const float dx = __fsub_rn(qx, s_ax[a]), dy = __fsub_rn(qy, s_ay[a]);
+        const float sq = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
+        if (sq <= near && __fsqrt_rn(sq) == best) { arg = a; break; }
+      }
+      for (int w = g >> 1; w > 0; w >>= 1) arg = min(arg, __shfl_xor_sync(0xffffffffu, arg, w));
+      slot = (best < p.dist_abs) ? arg : -1;
+    }
+    if (live && sub == 0) store_out(p, p.assign + (size_t)b * p.P + s, slot);
+  }
+  if (threadIdx.x < 2) store_out(p, p.out_counts + (size_t)b * 2 + threadIdx.x, s_cnt[threadIdx.x]);
+  if (p.diag) {
+    const int C = p.M + p.N;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      store_out(p, p.diag + ((size_t)b * C + c) * 2 + 0, p.counts[(size_t)b * C + c]);
+      store_out(p, p.diag + ((size_t)b * C + c) * 2 + 1, p.exact_flags[(size_t)b * C + c]);
+    }
+  }
+  if (p.n_dest) __threadfence_system();  // peer stores performed before the kernel retires
+}
+
+// ---------------------------------------------------------------------------------------------
+// metadata: clamped-sigmoid maps
+// ---------------------------------------------------------------------------------------------
+template <int DT>
+__global__ void sdnet_activate_kernel(View4 in, int C, int H, int W, size_t total, float* __restrict__ out) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W);
+    size_t t = i / W;
+    const int y = (int)(t % H);
+    t /= H;
+    const int c = (int)(t % C);
+    const long long b = (long long)(t / C);
+    out[i] = Num<DT>::act(ld_in<DT>(in.data, b * in.sb + (long long)c * in.sc + (long long)y * in.sh + x));
+  }
+}
+
+
+}  // namespace

@@ -17,7 +17,7 @@ from dataclasses import dataclass
 import torch
 
 from . import _native
-PEAKS_PATHS = ("warp", "tile", "tile_row_pairs", "cta")  # SDNET_PATH_* in include/sdnet_decode.h
+PEAKS_PATHS = ("warp", "tile", "tile_row_pairs")  # SDNET_PATH_* in include/sdnet_decode.h
 from ._native import (FLAG_EXACT_SELECT, FLAG_NO_GROUPING, FLAG_PRE_ACTIVATED, FLAG_WARP_KERNEL, SdnetDecodeParams,
                       SdnetTensor4)
 
@@ -149,7 +149,7 @@ class DecodePlan:
         return self.out
 
     def peaks_path(self, anchor_hm, part_hm, offsets, embeddings, radius=2, flags=0) -> str:
-        """Which peaks kernel these tensors would run: "warp" | "tile" | "tile_row_pairs" | "cta"."""
+        """Which peaks kernel these tensors would run: "warp" | "tile" | "tile_row_pairs"."""
         self._bind_inputs(anchor_hm, part_hm, offsets, embeddings, 0.0, 0.0, radius, flags)
         rc = self.lib.sdnet_decode_peaks_path(ctypes.byref(self.params))
         if rc < 0:  # non-negative values are SDNET_PATH_*, not CUDA errors

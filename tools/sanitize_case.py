@@ -12,5 +12,5 @@ for (h, w, k) in ((40, 132, 30), (37, 53, 20), (24, 1028, 40)):
             pk = ops.decode_packed(outs, k, k, 0.4, 0.1, **kw)
         torch.cuda.synchronize()
 import os
-os.environ["SDNET_PEAKS_PATH"] = "cta"
+os.environ["SDNET_PEAKS_PATH"] = "tile"
 print("ok", int(pk.counts.sum()))
