@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SDNET_ABI_VERSION 4
+#define SDNET_ABI_VERSION 5
 
 /* element types of the four input tensors */
 #define SDNET_DTYPE_F32 0
@@ -124,6 +124,12 @@ int sdnet_decode_launch_timed(const SdnetDecodeParams* params, void* stream, flo
 /* clamp(sigmoid(x), 1e-6, 1-1e-6) of a (B, C, H, W) view into a contiguous fp32 tensor:
  * the `anchor_hm_sig` / `part_hm_sig` metadata maps (decoders.py:44,60,163-164). */
 int sdnet_activate_launch(const SdnetTensor4* in, int dtype, int B, int C, int H, int W, float* out, void* stream);
+
+/* nms(clamped_sigmoid(x)) of a (B, C, H, W) view into a contiguous fp32 tensor: the score where it equals
+ * the maximum score of its (2 radius + 1)^2 window, 0 elsewhere -- the reference's RawDecoder
+ * (src/sdnet/cli/convert_coreml.py:12-19; utils.py:355-361,441-443), i.e. the heat maps CoreMLDecoder
+ * expects (decoders.py:211,226; SDNET_FLAG_PRE_ACTIVATED). */
+int sdnet_suppress_launch(const SdnetTensor4* in, int dtype, int B, int C, int H, int W, int radius, float* out, void* stream);
 
 /* Same as sdnet_decode_launch but the four input tensors live in (pinned) HOST memory:
  * the heat-map planes are staged to `staging` (device, >= B*(M+N)*H*W*4 bytes) in

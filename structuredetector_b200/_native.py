@@ -13,7 +13,7 @@ import os as _os
 
 # SDNET_DECODE_LIB: load another build of the same library (kernel experiments, tools/xbuild.sh)
 LIB_PATH = Path(_os.environ.get("SDNET_DECODE_LIB") or Path(__file__).resolve().parent / "csrc" / "libsdnet_decode.so").resolve()
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 FLAG_PRE_ACTIVATED = 1
 FLAG_NO_GROUPING = 2
@@ -36,6 +36,7 @@ EXPORTS = (
     "sdnet_decode_peaks_path",
     "sdnet_match_launch",
     "sdnet_activate_launch",
+    "sdnet_suppress_launch",
     "sdnet_decode_host_launch",
 )
 
@@ -134,6 +135,8 @@ def load() -> ctypes.CDLL:
     lib.sdnet_decode_launch_timed.restype = ctypes.c_int
     lib.sdnet_decode_launch_timed.argtypes = [ctypes.POINTER(SdnetDecodeParams), ctypes.c_void_p,
                                               ctypes.POINTER(ctypes.c_float)]
+    lib.sdnet_suppress_launch.restype = ctypes.c_int
+    lib.sdnet_suppress_launch.argtypes = [ctypes.POINTER(SdnetTensor4)] + [ctypes.c_int] * 6 + [ctypes.c_void_p, ctypes.c_void_p]
     lib.sdnet_activate_launch.restype = ctypes.c_int
     lib.sdnet_activate_launch.argtypes = [ctypes.POINTER(SdnetTensor4), ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                           ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]

@@ -36,6 +36,7 @@
 #include "exact_select.cuh"
 #include "tail.cuh"
 #include "match.cuh"
+#include "suppress.cuh"
 
 namespace {
 
@@ -475,6 +476,27 @@ int sdnet_activate_launch(const SdnetTensor4* in, int dtype, int B, int C, int H
   if (dtype == SDNET_DTYPE_F16) sdnet_activate_kernel<SDNET_DTYPE_F16><<<dim3((unsigned)blocks), dim3(256), 0, st>>>(to_view(*in), C, H, W, total, out);
   else if (dtype == SDNET_DTYPE_BF16) sdnet_activate_kernel<SDNET_DTYPE_BF16><<<dim3((unsigned)blocks), dim3(256), 0, st>>>(to_view(*in), C, H, W, total, out);
   else sdnet_activate_kernel<SDNET_DTYPE_F32><<<dim3((unsigned)blocks), dim3(256), 0, st>>>(to_view(*in), C, H, W, total, out);
+  return (int)cudaGetLastError();
+}
+
+int sdnet_suppress_launch(const SdnetTensor4* in, int dtype, int B, int C, int H, int W, int radius, float* out, void* stream) {
+  if (!in || !in->data || !out) return SDNET_E_NULL;
+  if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return SDNET_E_SHAPE;
+  if (in->stride_w != 1) return SDNET_E_STRIDE;
+  if (dtype != SDNET_DTYPE_F32 && dtype != SDNET_DTYPE_F16 && dtype != SDNET_DTYPE_BF16) return SDNET_E_DTYPE;
+  if (radius != 1 && radius != 2) return SDNET_E_RADIUS;
+  const int panels = (W + kPanelW - 1) / kPanelW, strips = (H + kSupStripRows - 1) / kSupStripRows;
+  const long long units = (long long)panels * strips * C * B;
+  const long long blocks = (units + kSupWarps - 1) / kSupWarps;
+  if (blocks > 0x7fffffffll) return SDNET_E_SHAPE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const dim3 grid((unsigned)blocks), block(kSupWarps * 32);
+  const View4 v = to_view(*in);
+#define SDNET_SUPPRESS(R, DT) sdnet_suppress_kernel<R, DT><<<grid, block, 0, st>>>(v, C, H, W, panels, strips, units, out)
+  if (dtype == SDNET_DTYPE_F16) { if (radius == 2) SDNET_SUPPRESS(2, SDNET_DTYPE_F16); else SDNET_SUPPRESS(1, SDNET_DTYPE_F16); }
+  else if (dtype == SDNET_DTYPE_BF16) { if (radius == 2) SDNET_SUPPRESS(2, SDNET_DTYPE_BF16); else SDNET_SUPPRESS(1, SDNET_DTYPE_BF16); }
+  else { if (radius == 2) SDNET_SUPPRESS(2, SDNET_DTYPE_F32); else SDNET_SUPPRESS(1, SDNET_DTYPE_F32); }
+#undef SDNET_SUPPRESS
   return (int)cudaGetLastError();
 }
 

@@ -1,0 +1,134 @@
+// suppress.cuh -- sdnet_suppress_kernel: dense sigmoid + peak-NMS maps, the reference's RawDecoder
+// (src/sdnet/cli/convert_coreml.py:12-19: nms(clamped_sigmoid(x)), src/sdnet/utils/utils.py:355-361,441-443),
+// i.e. the pre-activated heat maps CoreMLDecoder consumes (src/sdnet/data/decoders.py:211,226).
+#pragma once
+
+namespace {
+
+// out = S(x) where S(x) equals the maximum of S over the (2R+1)^2 window (-inf padding), else 0.
+// S is monotone, so the window maximum is taken on raw logits and the exact score is evaluated only for
+// survivors and for pixels within the near-tie margins of Num<DT> -- the same classification as the peaks
+// kernels.  HBM-bound: one read of the logits, one write of the maps, nothing staged in shared memory:
+// a warp walks a 128-column panel of one plane strip top to bottom, each lane holding four columns; the
+// horizontal maxima come from the neighbours' registers by shuffle (panel-edge columns from two extra
+// loads), the vertical ones from a register window of the last 2R+1 rows; rows are loaded two ahead.
+constexpr int kSupWarps = 8, kSupStripRows = 64;
+
+template <int DT>
+__device__ __forceinline__ float4 sup_load4(const void* base, long long row_off, int x, int W, bool row_ok, bool vec_ok) {
+  float4 v = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);  // max_pool2d pads with -inf
+  if (!row_ok || x >= W) return v;
+  if (DT == SDNET_DTYPE_F32 && vec_ok && x + 3 < W) return __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(base) + row_off + x));
+  v.x = ld_in<DT>(base, row_off + x);
+  if (x + 1 < W) v.y = ld_in<DT>(base, row_off + x + 1);
+  if (x + 2 < W) v.z = ld_in<DT>(base, row_off + x + 2);
+  if (x + 3 < W) v.w = ld_in<DT>(base, row_off + x + 3);
+  return v;
+}
+
+template <int DT>
+__device__ __forceinline__ float sup_score(float x, float h) {
+  constexpr float kNearTie = Num<DT>::kNear, kHiZone = Num<DT>::kHi, kLoZone = Num<DT>::kLo, kNearTie2 = Num<DT>::kNear2,
+                  kHiZone2 = Num<DT>::kHi2;
+  if (x == h) return Num<DT>::act(x);
+  if ((x >= h - kNearTie) || (h > kHiZone && x >= h - kNearTie2) || (h > kHiZone2 && x > kHiZone2 - 1.0f) || (h < kLoZone)) {
+    const float sx = Num<DT>::act(x);
+    if (sx == Num<DT>::act(h)) return sx;
+  }
+  return 0.0f;
+}
+
+template <int R, int DT>
+__global__ void __launch_bounds__(kSupWarps * 32) sdnet_suppress_kernel(View4 in, int C, int H, int W, int panels, int strips,
+                                                                         long long units, float* __restrict__ out) {
+  constexpr int kWin = 2 * R + 1;
+  const int lane = threadIdx.x & 31;
+  const long long unit = (long long)blockIdx.x * kSupWarps + (threadIdx.x >> 5);
+  if (unit >= units) return;
+  const int panel = (int)(unit % panels);
+  long long t = unit / panels;
+  const int strip = (int)(t % strips);
+  t /= strips;
+  const int c = (int)(t % C);
+  const long long b = t / C;
+  const long long plane = b * in.sb + (long long)c * in.sc;
+  const int x = panel * kPanelW + 4 * lane;
+  const int r_begin = strip * kSupStripRows, r_end = min(H, r_begin + kSupStripRows);
+  // fp32: a lane's four columns in one 16-byte load when base and pitches allow (an 8-byte load of four
+  // fp16/bf16 elements measured slower than four 2-byte loads here: 0.89 vs 0.76 ms)
+  const bool vec_ok = DT == SDNET_DTYPE_F32 && ((reinterpret_cast<uintptr_t>(in.data) | (uintptr_t)(in.sb * 4) | (uintptr_t)(in.sc * 4) |
+                                                  (uintptr_t)(in.sh * 4)) & 15) == 0;
+  const bool out_vec = (W & 3) == 0;
+  float* out_plane = out + (b * C + c) * (long long)H * W;
+  // halo columns of the panel: lane 0 fetches the R columns left of it, lane 31 the R columns right
+  const int hx = lane == 0 ? x - R : x + 4;
+  const bool halo_lane = lane == 0 || lane == 31;
+
+  float4 hwin[kWin];  // horizontal maxima of the last 2R+1 rows, hwin[kWin-1] the newest
+  float4 cwin[R + 1]; // centre values of the last R+1 rows, cwin[R] the newest
+#pragma unroll
+  for (int i = 0; i < kWin; ++i) hwin[i] = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
+#pragma unroll
+  for (int i = 0; i <= R; ++i) cwin[i] = hwin[0];
+
+  auto fetch = [&](int y, float4& v, float& h0, float& h1) {
+    const bool ok = y >= 0 && y < H;
+    const long long off = plane + (long long)y * in.sh;
+    v = sup_load4<DT>(in.data, off, x, W, ok, vec_ok);
+    h0 = h1 = -CUDART_INF_F;
+    if (halo_lane && ok) {
+      if (hx >= 0 && hx < W) h0 = ld_in<DT>(in.data, off + hx);
+      if (R == 2 && hx + 1 >= 0 && hx + 1 < W) h1 = ld_in<DT>(in.data, off + hx + 1);
+    }
+  };
+  // two rows in flight
+  float4 va, vb;
+  float a0, a1, b0, b1;
+  fetch(r_begin - R, va, a0, a1);
+  fetch(r_begin - R + 1, vb, b0, b1);
+  for (int y = r_begin - R; y < r_end + R; ++y) {
+    const float4 v = va;
+    const float e_h0 = a0, e_h1 = a1;
+    va = vb; a0 = b0; a1 = b1;
+    fetch(y + 2, vb, b0, b1);
+    // neighbours' columns: e = [l0 l1 | v.x v.y v.z v.w | r0 r1] (R = 2), [l1 | v | r0] (R = 1)
+    float l0 = __shfl_up_sync(0xffffffffu, v.z, 1), l1 = __shfl_up_sync(0xffffffffu, v.w, 1);
+    float r0 = __shfl_down_sync(0xffffffffu, v.x, 1), r1 = __shfl_down_sync(0xffffffffu, v.y, 1);
+    if (lane == 0) { l0 = R == 2 ? e_h0 : -CUDART_INF_F; l1 = R == 2 ? e_h1 : e_h0; }
+    if (lane == 31) { r0 = e_h0; r1 = R == 2 ? e_h1 : -CUDART_INF_F; }
+    float4 hm;
+    if (R == 2) {
+      const float c12 = fmaxf(l1, v.x), c34 = fmaxf(v.y, v.z), c56 = fmaxf(v.w, r0);
+      hm = make_float4(max3(l0, c12, c34), max3(c12, c34, v.w), max3(v.x, c34, c56), max3(c34, c56, r1));
+    } else {
+      hm = make_float4(max3(l1, v.x, v.y), max3(v.x, v.y, v.z), max3(v.y, v.z, v.w), max3(v.z, v.w, r0));
+    }
+#pragma unroll
+    for (int i = 0; i + 1 < kWin; ++i) hwin[i] = hwin[i + 1];
+    hwin[kWin - 1] = hm;
+#pragma unroll
+    for (int i = 0; i < R; ++i) cwin[i] = cwin[i + 1];
+    cwin[R] = v;
+    const int yo = y - R;  // the row whose window is now complete
+    if (yo >= r_begin && x < W) {
+      float4 h = hwin[0];
+#pragma unroll
+      for (int i = 1; i < kWin; ++i) {
+        h.x = fmaxf(h.x, hwin[i].x); h.y = fmaxf(h.y, hwin[i].y); h.z = fmaxf(h.z, hwin[i].z); h.w = fmaxf(h.w, hwin[i].w);
+      }
+      const float4 ctr = cwin[0];
+      const float4 s = make_float4(sup_score<DT>(ctr.x, h.x), sup_score<DT>(ctr.y, h.y), sup_score<DT>(ctr.z, h.z), sup_score<DT>(ctr.w, h.w));
+      float* dst = out_plane + (long long)yo * W + x;
+      if (out_vec) {
+        *reinterpret_cast<float4*>(dst) = s;
+      } else {
+        dst[0] = s.x;
+        if (x + 1 < W) dst[1] = s.y;
+        if (x + 2 < W) dst[2] = s.z;
+        if (x + 3 < W) dst[3] = s.w;
+      }
+    }
+  }
+}
+
+}  // namespace

@@ -18,7 +18,7 @@ import torch
 from . import ops
 from .annotations import ImageAnnotation, Keypoint, Object
 
-__all__ = ["Decoder", "CoreMLDecoder", "KeypointDecoder"]
+__all__ = ["Decoder", "CoreMLDecoder", "KeypointDecoder", "RawDecoder"]
 
 
 @contextlib.contextmanager
@@ -192,3 +192,16 @@ class KeypointDecoder(_DecoderBase):
                     keypoints.append(Keypoint(kind=names[int(cls)], x=x, y=y, score=score))
             annotations.append(keypoints)
         return annotations
+
+
+class RawDecoder:
+    """``RawDecoder(nb_hms)(raw)``: the network's raw ``(B, M+N+4, H, W)`` output with its first ``nb_hms``
+    channels replaced by ``nms(clamped_sigmoid(.))`` -- what the reference bakes into its exported model
+    (reference: src/sdnet/cli/convert_coreml.py:12-19) and ``CoreMLDecoder`` then consumes."""
+
+    def __init__(self, nb_hms: int) -> None:
+        self.nb_hms = nb_hms
+
+    def __call__(self, input: torch.Tensor) -> torch.Tensor:
+        heatmaps = ops.suppress_maps(input[:, : self.nb_hms])
+        return torch.cat(tensors=(heatmaps, input[:, self.nb_hms:]), dim=1)

@@ -263,6 +263,24 @@ def _(hm):
     return hm.new_empty(hm.shape, dtype=torch.float32)
 
 
+@torch.library.custom_op("sdnet_b200::suppress", mutates_args=(), device_types="cuda")
+def _suppress_op(hm: torch.Tensor, radius: int) -> torch.Tensor:
+    B, C, H, W = hm.shape
+    out = torch.empty((B, C, H, W), dtype=torch.float32, device=hm.device)
+    view = _view4(hm)
+    with torch.cuda.device(hm.device):
+        rc = _native.load().sdnet_suppress_launch(ctypes.byref(view), _DTYPES[hm.dtype], B, C, H, W, radius,
+                                                  ctypes.c_void_p(out.data_ptr()),
+                                                  ctypes.c_void_p(torch.cuda.current_stream(hm.device).cuda_stream))
+    _native.check(rc, "sdnet_suppress_launch")
+    return out
+
+
+@_suppress_op.register_fake
+def _(hm, radius):
+    return hm.new_empty(hm.shape, dtype=torch.float32)
+
+
 def _unit_w_stride(t: torch.Tensor) -> torch.Tensor:
     # a layout fix on the device, not a fallback: the kernels need the innermost stride to be 1
     return t if t.stride(3) == 1 else t.contiguous()
@@ -303,4 +321,12 @@ def activate_maps(hm: torch.Tensor) -> torch.Tensor:
     """``clamp(sigmoid(hm), 1e-6, 1-1e-6)`` as a contiguous tensor of hm's dtype (reference utils.py:355-361)."""
     _check_tensor("heat map", hm)
     out = _activate_op(_unit_w_stride(hm))  # fp32 storage of values exactly representable in hm.dtype
+    return out if hm.dtype == torch.float32 else out.to(hm.dtype)
+
+
+def suppress_maps(hm: torch.Tensor, radius: int = 2) -> torch.Tensor:
+    """``nms(clamped_sigmoid(hm))`` (reference utils.py:355-361,441-443) as a contiguous tensor of hm's dtype:
+    the score at the peaks of every (2 radius + 1)^2 window, 0 elsewhere."""
+    _check_tensor("heat map", hm)
+    out = _suppress_op(_unit_w_stride(hm), int(radius))
     return out if hm.dtype == torch.float32 else out.to(hm.dtype)
