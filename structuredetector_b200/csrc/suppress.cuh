@@ -12,7 +12,9 @@ namespace {
 // a warp walks a 128-column panel of one plane strip top to bottom, each lane holding four columns; the
 // horizontal maxima come from the neighbours' registers by shuffle (panel-edge columns from two extra
 // loads), the vertical ones from a register window of the last 2R+1 rows; rows are loaded two ahead.
-constexpr int kSupWarps = 8, kSupStripRows = 64;
+// rows in flight per warp / CTAs per SM, measured on 256 cfg5 images (fp32): 2/3 0.596 ms, 3/3 0.615, 4/3 0.648,
+// 2/4 0.582 (64 registers, spills), 4/2 0.774
+constexpr int kSupWarps = 8, kSupStripRows = 64, kSupAhead = 2;
 
 template <int DT>
 __device__ __forceinline__ float4 sup_load4(const void* base, long long row_off, int x, int W, bool row_ok, bool vec_ok) {
@@ -39,7 +41,7 @@ __device__ __forceinline__ float sup_score(float x, float h) {
 }
 
 template <int R, int DT>
-__global__ void __launch_bounds__(kSupWarps * 32) sdnet_suppress_kernel(View4 in, int C, int H, int W, int panels, int strips,
+__global__ void __launch_bounds__(kSupWarps * 32, 3) sdnet_suppress_kernel(View4 in, int C, int H, int W, int panels, int strips,
                                                                          long long units, float* __restrict__ out) {
   constexpr int kWin = 2 * R + 1;
   const int lane = threadIdx.x & 31;
@@ -81,16 +83,17 @@ __global__ void __launch_bounds__(kSupWarps * 32) sdnet_suppress_kernel(View4 in
       if (R == 2 && hx + 1 >= 0 && hx + 1 < W) h1 = ld_in<DT>(in.data, off + hx + 1);
     }
   };
-  // two rows in flight
-  float4 va, vb;
-  float a0, a1, b0, b1;
-  fetch(r_begin - R, va, a0, a1);
-  fetch(r_begin - R + 1, vb, b0, b1);
+  // kSupAhead rows in flight
+  float4 pv[kSupAhead];
+  float ph0[kSupAhead], ph1[kSupAhead];
+#pragma unroll
+  for (int k = 0; k < kSupAhead; ++k) fetch(r_begin - R + k, pv[k], ph0[k], ph1[k]);
   for (int y = r_begin - R; y < r_end + R; ++y) {
-    const float4 v = va;
-    const float e_h0 = a0, e_h1 = a1;
-    va = vb; a0 = b0; a1 = b1;
-    fetch(y + 2, vb, b0, b1);
+    const float4 v = pv[0];
+    const float e_h0 = ph0[0], e_h1 = ph1[0];
+#pragma unroll
+    for (int k = 0; k + 1 < kSupAhead; ++k) { pv[k] = pv[k + 1]; ph0[k] = ph0[k + 1]; ph1[k] = ph1[k + 1]; }
+    fetch(y + kSupAhead, pv[kSupAhead - 1], ph0[kSupAhead - 1], ph1[kSupAhead - 1]);
     // neighbours' columns: e = [l0 l1 | v.x v.y v.z v.w | r0 r1] (R = 2), [l1 | v | r0] (R = 1)
     float l0 = __shfl_up_sync(0xffffffffu, v.z, 1), l1 = __shfl_up_sync(0xffffffffu, v.w, 1);
     float r0 = __shfl_down_sync(0xffffffffu, v.x, 1), r1 = __shfl_down_sync(0xffffffffu, v.y, 1);
