@@ -155,7 +155,7 @@ __device__ __forceinline__ u32 ring_row_off(u32 rr) {
 // `row0` = ring row of the window's first row for group row 0 (the centre is R rows further).
 template <int R, int DT, int S>
 __device__ __forceinline__ void settle_entries(UnitState& st, const unsigned char* work, int nent, u32 ring_s, u32 row0,
-                                               float floorx, u32 idx0, int W, bool pre, u64* buf, u32* hist, int* minx,
+                                               u32 row_tab, float floorx, u32 idx0, int W, bool pre, u64* buf, u32* hist, int* minx,
                                                const SharedFloors& sf, int* count_ptr, u64* __restrict__ list, int cap,
                                                int K, int lane, float xscale, float satx) {
   constexpr float kNearTie = Num<DT>::kNear, kHiZone = Num<DT>::kHi, kLoZone = Num<DT>::kLo, kNearTie2 = Num<DT>::kNear2,
@@ -168,14 +168,22 @@ __device__ __forceinline__ void settle_entries(UnitState& st, const unsigned cha
     const u32 e = slot < nslots ? work[slot / kPx] : 0u;
     const u32 i = e >> 5, colp = kPx * (e & 31u) + (u32)(slot % kPx);
     const u32 col_addr = ring_s + (kPx + colp - R) * kEsz;  // first column of the window
-    const float x = TileMax<DT>::elem(col_addr + R * kEsz + ring_row_off<S>((row0 + i + R) & kRowMask));
+    // byte offsets of the window's rows.  Plain rows: a multiply.  Row pairs: the slot layout makes that
+    // eight instructions per row, so lane k keeps the offset of ring row k (row_tab) and a shuffle looks it up
+    u32 roff[2 * R + 1];
+#pragma unroll
+    for (int d = 0; d <= 2 * R; ++d) {
+      const u32 rr = (row0 + i + d) & kRowMask;
+      roff[d] = S == 1 ? rr * kTilePitchB : __shfl_sync(0xffffffffu, row_tab, (int)rr);
+    }
+    const float x = TileMax<DT>::elem(col_addr + R * kEsz + roff[R]);
     bool keep = slot < nslots && x > floorx;
     if (keep && !pre) {
       // window max in the storage format (no conversions for fp16/bf16), one accumulator per window row
       u32 hr[2 * R + 1];
 #pragma unroll
       for (int d = 0; d <= 2 * R; ++d) {
-        const u32 a = col_addr + ring_row_off<S>((row0 + i + d) & kRowMask);
+        const u32 a = col_addr + roff[d];
         u32 v[2 * R + 1];
 #pragma unroll
         for (int q = 0; q <= 2 * R; ++q) v[q] = TileMax<DT>::raw(a + kEsz * q);
@@ -270,6 +278,7 @@ sdnet_peaks_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_cons
   const int H = p.H, W = p.W;
   const u32 ring_own = ring_s + (u32)(16 + 16 * lane);  // this lane's word inside a ring row
   const u32 lt = (1u << lane) - 1u;
+  const u32 row_tab = ring_row_off<S>((u32)lane & kRowMask);  // lane k: byte offset of ring row k (see settle_entries)
 
   if (lane == 0) {
     for (int i = 0; i < NG; ++i) mbar_init(bars_s + 8 * i, 1);
@@ -398,7 +407,7 @@ sdnet_peaks_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_cons
           nent += __popc(bm);
         }
         __syncwarp();
-        settle_entries<R, DT, S>(st, work, nent, ring_s, row0, floorx, idx0, W, pre, buf, hist, minx, sf, count_ptr, list,
+        settle_entries<R, DT, S>(st, work, nent, ring_s, row0, row_tab, floorx, idx0, W, pre, buf, hist, minx, sf, count_ptr, list,
                                  p.cap, K, lane, xscale, satx);
         // while the plane has no floor yet, publish early and often; later only in batches
         if (st.nbuf >= 16 || (st.nbuf > 0 && gfloor_seen <= 0)) {
