@@ -124,3 +124,49 @@ def test_cuda_matching_against_oracle_on_dense_batch(cuda_device):
             assert (got.tp, got.npos, got.ndet) == (tp, npos, ndet), (key, label)
             np.testing.assert_allclose(got.acc, acc, rtol=1e-9, atol=0)
     assert ev.anchor_eval.reduce().tp > 50 and ev.part_eval.reduce().tp > 50
+
+
+def test_evaluation_classes_mirror_the_reference_formulas():
+    """Evaluation / Evaluations (evaluator.py:13-206): counters, derived metrics, +, |, reduce -- against
+    fixed expectations and, where the reference is importable, against its own classes."""
+    from structuredetector_b200.evaluator import Evaluation, Evaluations
+    a = Evaluation(tp=3, npos=5, ndet=4, acc=[0.01, 0.02, 0.03])
+    assert (a.fp, a.fn) == (1, 2) and a.precision == 0.75 and a.recall == 0.6
+    assert a.f1_score == pytest.approx(2 * 3 / 9) and a.csi == pytest.approx(3 / 6)
+    assert a.avg_acc == pytest.approx(0.02) and a.acc_err == pytest.approx(np.std([0.01, 0.02, 0.03]) / np.sqrt(3))
+    empty = Evaluation()
+    assert (empty.precision, empty.recall, empty.f1_score, empty.csi) == (1, 1, 1, 1) and np.isnan(empty.avg_acc)
+    assert Evaluation(tp=0, npos=0, ndet=2).precision == 0 and Evaluation(tp=0, npos=2, ndet=0).recall == 0
+    with pytest.raises(AssertionError):
+        Evaluation(tp=2, npos=1, ndet=2)
+    total = a + Evaluation(tp=1, npos=1, ndet=2, acc=[0.5])
+    assert (total.tp, total.npos, total.ndet, total.acc) == (4, 6, 6, [0.01, 0.02, 0.03, 0.5]) and a.tp == 3
+    x, y = Evaluations(["l0", "l1"]), Evaluations(["l0", "l1"])
+    x["l0"] += a
+    y["l1"] += Evaluation(tp=1, npos=2, ndet=1, acc=[0.1])
+    both = x + y
+    assert (both["l0"].tp, both["l1"].tp, both.reduce().npos) == (3, 1, 7) and len(both) == 2
+    parts = Evaluations(["p0"])
+    parts["p0"] += Evaluation(tp=2, npos=2, ndet=3, acc=[0.2, 0.3])
+    merged = both | parts
+    assert set(merged.labels) == {"l0", "l1", "p0"} and merged.reduce().tp == 6
+    ref_src = Path("/root/reference/src")
+    if ref_src.exists():
+        import sys
+        sys.dont_write_bytecode = True
+        sys.path.insert(0, str(ref_src))
+        try:
+            from sdnet.model.evaluator import Evaluation as RefEvaluation
+        finally:
+            sys.path.remove(str(ref_src))
+        rng = np.random.default_rng(3)
+        for _ in range(50):
+            npos, ndet = int(rng.integers(0, 20)), int(rng.integers(0, 20))
+            tp = int(rng.integers(0, min(npos, ndet) + 1))
+            acc = rng.random(tp).tolist()
+            ours, ref = Evaluation(tp, npos, ndet, list(acc)), RefEvaluation(tp, npos, ndet, list(acc))
+            for name in ("fp", "fn", "csi", "precision", "recall", "f1_score"):
+                assert getattr(ours, name) == getattr(ref, name), name
+            if tp:
+                assert ours.avg_acc == ref.avg_acc and ours.acc_err == ref.acc_err
+            assert ours.stats() == ref.stats() and repr(ours) == repr(ref)
