@@ -4,18 +4,19 @@
 namespace {
 
 // ---------------------------------------------------------------------------------------------
-// peaks kernel, TMA-tile form (the default fast path; needs 16 B-aligned rows)
+// peaks kernel, TMA-tile form (the default; needs a base and pitches TMA can describe, see
+// tile_rows_per_tma_row in sdnet_decode.cu)
 //
-// Every warp is an autonomous pipeline over one (plane, row strip, 128-column panel) unit.
-// An elected lane pulls 4-row x 136-column tiles (the panel plus four columns either side)
-// into the warp's private shared-memory ring with 2-D tensor-map bulk copies (TMA, SASS
-// UTMALDG), completion on one mbarrier per ring slot.  The tensor map is encoded with NaN
-// out-of-bounds fill: fmaxf ignores a NaN operand and every ordered comparison with NaN is
-// false, so out-of-image rows and columns behave exactly like max_pool2d's -inf padding with
-// no edge code at all.  Per group of four output rows the warp waits on one barrier, reads its
-// four centre rows (4 x LDS.128), takes the max of the 16 values and votes "does anything here
-// beat the pruning floor?"; only then does it look at single rows.  No warp ever waits for
-// another warp.
+// Every warp is an autonomous pipeline over one (plane, row strip, panel) unit; a lane owns one
+// 16-byte word per row (4 fp32 or 8 fp16/bf16 pixels), so a panel is 128 or 256 columns.  An elected
+// lane pulls 4-row tiles (the panel plus one word either side) into the warp's private shared-memory
+// ring with tensor-map bulk copies (TMA, SASS UTMALDG), completion on one mbarrier per ring slot.
+// The tensor map is encoded with NaN out-of-bounds fill: fmaxf / max.f16x2 ignore a NaN operand and
+// every ordered comparison with NaN is false, so out-of-image rows and columns behave exactly like
+// max_pool2d's -inf padding with no edge code at all.  Per group of four output rows the warp waits
+// on one barrier, reads its four centre rows (4 x LDS.128), takes the max of the 16 / 32 values and
+// votes "does anything here beat the pruning floor?"; only then does it list the words that do and
+// give every listed pixel a lane of its own (settle_entries).  No warp ever waits for another warp.
 // ---------------------------------------------------------------------------------------------
 constexpr int kGroupRows = 4;                                // output rows per TMA tile and per fast-path test
 constexpr int kTileCols = kPanelW + 8;

@@ -5,11 +5,12 @@
 namespace {
 
 // ---------------------------------------------------------------------------------------------
-// peaks kernel
+// peaks kernel, per-lane form (the fallback: any shape, stride and alignment)
 //
 // Work unit = (plane, row strip, 128-column panel), one warp per unit, units handed out by an
 // atomic counter.  Each warp streams its panel top to bottom through a private shared-memory
-// ring of kStages rows filled with cp.async (16 B per lane, straight from L2, no registers):
+// ring of kStages fp32 rows: fp32 maps are copied with per-lane cp.async (4 bytes each, no alignment
+// needed), fp16/bf16 maps are loaded and widened by the lanes (RowFeedCvt):
 //     row buffer (kPitch floats):  [pad pad hL hL | 128 panel columns | hR hR pad pad]
 // Per row the common case is: issue the copy of the row kStages-1 ahead, wait for the row two
 // below the centre, read the centre row (one LDS.128), and vote "does any pixel beat the
