@@ -170,3 +170,27 @@ def test_evaluation_classes_mirror_the_reference_formulas():
             if tp:
                 assert ours.avg_acc == ref.avg_acc and ours.acc_err == ref.acc_err
             assert ours.stats() == ref.stats() and repr(ours) == repr(ref)
+
+
+def test_ground_truth_packing_host_logic():
+    """Evaluator._pack_ground_truth: row layout, unknown labels (-1, never matched or counted), per-image
+    scale rows (evaluator.py:245-250), and the SDNET_MAX_GT limit.  Host only: loads the library, no launch."""
+    from structuredetector_b200 import ImageAnnotation, Keypoint, Object, _native
+    from structuredetector_b200.evaluator import Evaluator
+    args = SimpleNamespace(labels={"maize": 0, "bean": 1}, parts={"leaf": 0}, width=512, height=256, dist_threshold=0.05,
+                           conf_threshold=0.4, down_ratio=4.0)
+    ev = Evaluator(args)
+    anns = [
+        ImageAnnotation("a", [Object("bean", Keypoint("stem", 10.0, 20.0), [Keypoint("leaf", 1.0, 2.0), Keypoint("leaf", 3.0, 4.0)]),
+                              Object("weed", Keypoint("stem", 5.0, 6.0), [Keypoint("flower", 7.0, 8.0)])], img_size=(2048, 1024)),
+        ImageAnnotation("b", [], img_size=(1000, 3000)),
+    ]
+    (gt_a, n_a, wa), (gt_p, n_p, wp), scale = ev._pack_ground_truth(anns, torch.device("cpu"))
+    assert (wa, wp) == (2, 3) and n_a.tolist() == [2, 0] and n_p.tolist() == [3, 0]
+    assert gt_a[0].tolist() == [[10.0, 20.0, 1.0], [5.0, 6.0, -1.0]]
+    assert gt_p[0].tolist() == [[1.0, 2.0, 0.0], [3.0, 4.0, 0.0], [7.0, 8.0, -1.0]]
+    assert scale[0].tolist() == [2048 / 512, 1024 / 256, 1024 * 0.05, 1024.0]
+    assert scale[1].tolist() == [1000 / 512, 3000 / 256, 1000 * 0.05, 1000.0]
+    crowd = ImageAnnotation("c", [Object("bean", Keypoint("stem", 0.0, 0.0)) for _ in range(_native.MAX_GT + 1)], img_size=(10, 10))
+    with pytest.raises(ValueError):
+        ev._pack_ground_truth([crowd], torch.device("cpu"))
