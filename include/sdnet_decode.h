@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SDNET_ABI_VERSION 5
+#define SDNET_ABI_VERSION 6
 
 /* element types of the four input tensors */
 #define SDNET_DTYPE_F32 0
@@ -116,6 +116,27 @@ int sdnet_decode_launch(const SdnetDecodeParams* params, void* stream);
 #define SDNET_PATH_TILE_ROW_PAIRS 2 /* TMA tiles over row pairs: fp16/bf16 with an 8-byte-multiple row pitch (W = 612), H even */
 int sdnet_decode_peaks_path(const SdnetDecodeParams* params);
 
+/* How sdnet_decode_launch would cut these tensors into work for the peaks kernel on the current device
+ * (host-only; launches nothing).  The TMA tile kernel walks a line of columns (one panel of one plane,
+ * top to bottom; groups_per_column groups of four rows each): units [0, tier1_units) are whole columns,
+ * the rest of the line is cut into chunks of chunk_groups groups, one unit each.  The per-lane kernel
+ * cuts every plane into `strips` strips of rows_per_strip rows.  Parity tests use this to assert WHICH
+ * schedule branch a case exercised (whole columns, chunks, or both). */
+typedef struct SdnetSchedule {
+  uint32_t struct_size;  /* sizeof(SdnetSchedule), set by the caller */
+  int32_t path;          /* SDNET_PATH_* */
+  int32_t units;         /* work units handed out by the kernel's atomic counter */
+  int32_t tier1_units;   /* tile kernel: whole-column units */
+  int32_t chunk_units;   /* tile kernel: units - tier1_units */
+  int32_t chunk_groups;  /* tile kernel: groups of four rows per chunk unit */
+  int32_t groups_per_column;
+  int32_t panels;        /* panels per plane */
+  int32_t strips, rows_per_strip; /* per-lane kernel */
+  int32_t ctas, warps_per_cta, ctas_per_sm, sms;
+  int32_t list_capacity; /* records per plane before the exact select takes over */
+} SdnetSchedule;
+int sdnet_decode_schedule(const SdnetDecodeParams* params, SdnetSchedule* out);
+
 /* Profiling variant (bench.py's roofline leg): same work, but records CUDA events between the
  * three kernels on `stream`, WAITS for completion and returns the device time of each kernel in
  * milliseconds: kernel_ms[0] = peaks, [1] = exact-select, [2] = tail.  Synchronous by design. */
@@ -131,11 +152,15 @@ int sdnet_activate_launch(const SdnetTensor4* in, int dtype, int B, int C, int H
  * expects (decoders.py:211,226; SDNET_FLAG_PRE_ACTIVATED). */
 int sdnet_suppress_launch(const SdnetTensor4* in, int dtype, int B, int C, int H, int W, int radius, float* out, void* stream);
 
-/* Same as sdnet_decode_launch but the four input tensors live in (pinned) HOST memory:
- * the heat-map planes are staged to `staging` (device, >= B*(M+N)*H*W*4 bytes) in
- * chunks overlapped with the kernels, offsets/embeddings are only touched at the
- * selected peaks.  Outputs stay on the device.  Uses `stream` plus one internal
- * copy stream per call. */
+/* Same as sdnet_decode_launch but the four input tensors live in (pinned) HOST memory: the heat-map
+ * planes are copied to `staging` (device, >= B*(M+N)*H*W*elem bytes, 256-byte aligned) with one strided
+ * cudaMemcpy2DAsync per heat tensor on `stream`, then the three kernels run on `stream`;
+ * offsets/embeddings stay on the host and are only touched, through the unified address space, at the
+ * K + 2P selected peaks per image.  Outputs stay on the device.  Requirements: dense rows
+ * (stride_h == W) and dense channels (stride_c == H*W, free when the tensor has one channel); any
+ * batch stride.  Everything is enqueued on `stream`; no internal stream, no synchronisation.
+ * To overlap the copy of batch i+1 with the kernels of batch i, call it for consecutive batches on two
+ * streams with two staging buffers (what bench.py's e2e leg does). */
 int sdnet_decode_host_launch(const SdnetDecodeParams* params, void* staging, size_t staging_bytes, void* stream);
 
 /* ---- the step after the path: location matching of the reference evaluator, on the packed detections ----

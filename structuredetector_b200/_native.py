@@ -13,7 +13,7 @@ import os as _os
 
 # SDNET_DECODE_LIB: load another build of the same library (kernel experiments, tools/xbuild.sh)
 LIB_PATH = Path(_os.environ.get("SDNET_DECODE_LIB") or Path(__file__).resolve().parent / "csrc" / "libsdnet_decode.so").resolve()
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 FLAG_PRE_ACTIVATED = 1
 FLAG_NO_GROUPING = 2
@@ -34,6 +34,7 @@ EXPORTS = (
     "sdnet_decode_launch",
     "sdnet_decode_launch_timed",
     "sdnet_decode_peaks_path",
+    "sdnet_decode_schedule",
     "sdnet_match_launch",
     "sdnet_activate_launch",
     "sdnet_suppress_launch",
@@ -86,6 +87,12 @@ class SdnetDecodeParams(ctypes.Structure):
     ]
 
 
+class SdnetSchedule(ctypes.Structure):
+    _fields_ = [("struct_size", ctypes.c_uint32)] + [(name, ctypes.c_int32) for name in (
+        "path", "units", "tier1_units", "chunk_units", "chunk_groups", "groups_per_column", "panels", "strips",
+        "rows_per_strip", "ctas", "warps_per_cta", "ctas_per_sm", "sms", "list_capacity")]
+
+
 class SdnetMatchParams(ctypes.Structure):
     _fields_ = [
         ("struct_size", ctypes.c_uint32),
@@ -110,17 +117,24 @@ _lib = None
 def load() -> ctypes.CDLL:
     """Load the decode library once; raise ``NativeLibraryError`` if it cannot be used."""
     global _lib
-    if _lib is not None:
-        return _lib
-    if not LIB_PATH.exists():
+    if _lib is None:
+        _lib = load_from(LIB_PATH)
+    return _lib
+
+
+def load_from(path) -> ctypes.CDLL:
+    """dlopen one build of the library and declare its entry points (``load()`` for the product build;
+    kernel experiments load several builds side by side, tools/sweep.py)."""
+    path = Path(path)
+    if not path.exists():
         raise NativeLibraryError(
-            f"{LIB_PATH} is missing: build the CUDA extension first "
+            f"{path} is missing: build the CUDA extension first "
             "(python -m structuredetector_b200.build). There is no CPU fallback."
         )
-    lib = ctypes.CDLL(str(LIB_PATH))
+    lib = ctypes.CDLL(str(path))
     missing = [name for name in EXPORTS if not hasattr(lib, name)]
     if missing:
-        raise NativeLibraryError(f"{LIB_PATH} does not export {missing}")
+        raise NativeLibraryError(f"{path} does not export {missing}")
     lib.sdnet_abi_version.restype = ctypes.c_int
     lib.sdnet_error_string.restype = ctypes.c_char_p
     lib.sdnet_error_string.argtypes = [ctypes.c_int]
@@ -132,6 +146,8 @@ def load() -> ctypes.CDLL:
     lib.sdnet_match_launch.argtypes = [ctypes.POINTER(SdnetMatchParams), ctypes.c_void_p]
     lib.sdnet_decode_peaks_path.restype = ctypes.c_int
     lib.sdnet_decode_peaks_path.argtypes = [ctypes.POINTER(SdnetDecodeParams)]
+    lib.sdnet_decode_schedule.restype = ctypes.c_int
+    lib.sdnet_decode_schedule.argtypes = [ctypes.POINTER(SdnetDecodeParams), ctypes.POINTER(SdnetSchedule)]
     lib.sdnet_decode_launch_timed.restype = ctypes.c_int
     lib.sdnet_decode_launch_timed.argtypes = [ctypes.POINTER(SdnetDecodeParams), ctypes.c_void_p,
                                               ctypes.POINTER(ctypes.c_float)]
@@ -145,7 +161,6 @@ def load() -> ctypes.CDLL:
                                              ctypes.c_void_p]
     if lib.sdnet_abi_version() != ABI_VERSION:
         raise NativeLibraryError(f"ABI mismatch: library {lib.sdnet_abi_version()} != binding {ABI_VERSION}")
-    _lib = lib
     return lib
 
 
@@ -166,7 +181,7 @@ def check(code: int, what: str):
     raise RuntimeError(msg)
 
 
-def workspace_bytes(B, M, N, H, W, K, P, dtype=DTYPE_F32) -> int:
+def workspace_bytes(B, M, N, H, W, K, P, dtype=DTYPE_F32, lib=None) -> int:
     out = ctypes.c_size_t(0)
-    check(load().sdnet_decode_workspace_bytes(B, M, N, H, W, K, P, dtype, ctypes.byref(out)), "sdnet_decode_workspace_bytes")
+    check((lib or load()).sdnet_decode_workspace_bytes(B, M, N, H, W, K, P, dtype, ctypes.byref(out)), "sdnet_decode_workspace_bytes")
     return int(out.value)

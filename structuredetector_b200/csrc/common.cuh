@@ -50,10 +50,12 @@ struct PeaksParams {
   u32* sched;              // [0] dynamic unit counter
   u32* ghist;              // [planes][kFineBins] plane-wide logit histogram of recorded candidates
   int* gfloor;             // [planes] highest fine bin b with >= K recorded candidates in bins >= b (0 = none)
-  // tile kernel, two-tier schedule: units [0, tier1_units) are whole-height panels of planes
-  // [0, tier1_planes); the remaining planes are cut into `strips` strips so that the last wave of
-  // warps is filled with short units instead of idling behind a few long ones
-  int tier1_units, tier1_planes;
+  // tile kernel: the work is a line of columns (one panel of one plane, top to bottom), groups_per_col
+  // groups of four rows each.  Units [0, tier1_units) are whole columns; unit tier1_units + j is the
+  // j-th chunk of chunk_groups groups of the rest of the line and may run over a column's end into the
+  // next column (plan_peaks in sdnet_decode.cu)
+  int tier1_units, groups_per_col, chunk_groups;
+  u32 total_groups;
   int odd_x;               // tile kernel, row-pair maps: tensor-map x coordinate of an odd row's column 0
 };
 
@@ -164,13 +166,25 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(u32 bar, u32 bytes) {
 // try_wait with a suspend-time hint: the warp sleeps until the phase completes instead of spinning.
 // Measured: a spinning test_wait streams faster when nothing else runs (0.62 vs 0.94 ms with the
 // slow path disabled) but steals issue slots from the working warps in the real kernel (0.724 vs 0.718 ms).
+#ifndef SDNET_X_WAIT_NS
+#define SDNET_X_WAIT_NS 1000
+#endif
 __device__ __forceinline__ void mbar_wait(u32 bar, u32 parity) {
+#if SDNET_X_WAIT_NS > 0
   asm volatile(
       "{\n\t.reg .pred p;\n"
       "WAIT_LOOP:\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
       "@!p bra WAIT_LOOP;\n\t}"
-      ::"r"(bar), "r"(parity), "r"(1000u) : "memory");
+      ::"r"(bar), "r"(parity), "r"((u32)SDNET_X_WAIT_NS) : "memory");
+#else  // no suspend-time hint: the hardware's default time limit
+  asm volatile(
+      "{\n\t.reg .pred p;\n"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@!p bra WAIT_LOOP;\n\t}"
+      ::"r"(bar), "r"(parity) : "memory");
+#endif
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 

@@ -23,7 +23,19 @@ constexpr int kTileCols = kPanelW + 8;
 constexpr int kTilePitchB = kTileCols * 4;                   // 544 B per ring row
 constexpr int kTileBytes = kGroupRows * kTilePitchB;         // 2176 B per TMA tile (17 x 128 B)
 constexpr int kTileWarps = 4;
-constexpr int kTileNG = 4;   // ring slots (tiles) per warp: 16 rows, two or three tiles in flight, 5 CTAs/SM
+#ifndef SDNET_X_CTAS
+#define SDNET_X_CTAS 5
+#endif
+constexpr int kTileMinCtas = SDNET_X_CTAS;  // resident CTAs per SM the register allocation aims for
+constexpr int kMinChunkGroups = 8;  // shortest tier-2 unit (32 rows)
+#ifndef SDNET_X_NG
+#define SDNET_X_NG 4
+#endif
+constexpr int kTileNG = SDNET_X_NG;   // ring slots (tiles) per warp: a group reads two of them, the others are in flight
+#ifndef SDNET_X_FLUSH_AT
+#define SDNET_X_FLUSH_AT 16
+#endif
+constexpr int kFlushAt = SDNET_X_FLUSH_AT;  // buffered candidates that trigger a flush once the plane has a floor
 constexpr int kWork = 128;   // per-warp work list: one byte per (row of the group, lane) whose 16-byte word holds a pixel above the floor
 // S = rows per TMA row (see the kernel).  Under S = 2 a tile arrives as two 2-row boxes and a TMA
 // destination must be 128-byte aligned: the second box sits at +1152 and a slot takes 2304 bytes.
@@ -161,7 +173,7 @@ __device__ __forceinline__ void settle_entries(UnitState& st, const unsigned cha
                                                int K, int lane, float xscale, float satx) {
   constexpr float kNearTie = Num<DT>::kNear, kHiZone = Num<DT>::kHi, kLoZone = Num<DT>::kLo, kNearTie2 = Num<DT>::kNear2,
                   kHiZone2 = Num<DT>::kHi2;
-  constexpr u32 kRowMask = kTileNG * kGroupRows - 1;
+  constexpr u32 kRingRows = kTileNG * kGroupRows;
   constexpr int kPx = TileGeom<DT>::kPx, kEsz = TileGeom<DT>::kEsz;
   const int nslots = kPx * nent;
   for (int base = 0; base < nslots; base += 32) {  // warp-uniform
@@ -174,7 +186,8 @@ __device__ __forceinline__ void settle_entries(UnitState& st, const unsigned cha
     u32 roff[2 * R + 1];
 #pragma unroll
     for (int d = 0; d <= 2 * R; ++d) {
-      const u32 rr = (row0 + i + d) & kRowMask;
+      u32 rr = row0 + i + d;  // < 2 * kRingRows
+      if (rr >= kRingRows) rr -= kRingRows;
       roff[d] = S == 1 ? rr * kTilePitchB : __shfl_sync(0xffffffffu, row_tab, (int)rr);
     }
     const float x = TileMax<DT>::elem(col_addr + R * kEsz + roff[R]);
@@ -252,14 +265,14 @@ __device__ __forceinline__ void tile_fix_edges(u32 slot_s, int x0, int W, int la
 // instruction) -- and lands in its slot as rows 0, 2 | 1, 3 with the odd rows 8 bytes further right.
 // At the image edges such a box reads across the row boundary; tile_fix_edges repairs that after the wait.
 template <int R, int DT, int S>
-__global__ void __launch_bounds__(kTileWarps * 32, 5)
+__global__ void __launch_bounds__(kTileWarps * 32, kTileMinCtas)
 sdnet_peaks_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_constant__ CUtensorMap tm_anchor,
                         const __grid_constant__ CUtensorMap tm_part) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int NG = kTileNG;
-  constexpr u32 kRowMask = NG * kGroupRows - 1;
+  constexpr u32 kRingRows = NG * kGroupRows;
   constexpr int kPx = TileGeom<DT>::kPx, kPanel = TileGeom<DT>::kPanel;
-  static_assert((NG & (NG - 1)) == 0, "slot and parity of a tile come from its running number by mask and shift");
+  static_assert(NG >= 3 && kRingRows <= 32, "a group reads two slots; ring-row offsets are looked up by lane");
   static_assert(S == 1 || (R == 2 && DT != SDNET_DTYPE_F32), "row pairs: tiles must start on an even row");
   pdl_launch_dependents();
   const int lane = threadIdx.x & 31;
@@ -279,7 +292,7 @@ sdnet_peaks_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_cons
   const int H = p.H, W = p.W;
   const u32 ring_own = ring_s + (u32)(16 + 16 * lane);  // this lane's word inside a ring row
   const u32 lt = (1u << lane) - 1u;
-  const u32 row_tab = ring_row_off<S>((u32)lane & kRowMask);  // lane k: byte offset of ring row k (see settle_entries)
+  const u32 row_tab = ring_row_off<S>((u32)lane % kRingRows);  // lane k: byte offset of ring row k (see settle_entries)
 
   if (lane == 0) {
     for (int i = 0; i < NG; ++i) mbar_init(bars_s + 8 * i, 1);
@@ -290,26 +303,32 @@ sdnet_peaks_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_cons
   // Tiles are numbered in one running sequence over all units this warp processes: tile number n
   // lives in ring slot n % NG (ring rows 4 (n % NG) ..) and is the (n / NG)-th use of that slot, so
   // the slot's mbarrier is waited with parity (n / NG) & 1.  Every issued tile is waited exactly once.
-  u32 tile_n = 0;
+  // (slot, parity) of the current tile are carried in registers and stepped, so NG need not be a power of two.
+  u32 cur_slot = 0, cur_par = 0;
+  auto step_pos = [&](u32& slot, u32& par) {
+    if (++slot == (u32)NG) { slot = 0; par ^= 1u; }
+  };
   for (;;) {
     u32 unit = 0;
     if (lane == 0) unit = atomicAdd(p.sched, 1u);
     unit = __shfl_sync(0xffffffffu, unit, 0);
     if (unit >= (u32)p.units) break;
-    int panel, plane_id, r_begin, r_end;
+    // the unit's piece of the line of groups; it is walked one column segment at a time
+    u32 pos, pos_end;
     if (unit < (u32)p.tier1_units) {
-      panel = unit % p.panels;
-      plane_id = unit / p.panels;
-      r_begin = 0;
-      r_end = H;
+      pos = unit * (u32)p.groups_per_col;
+      pos_end = pos + (u32)p.groups_per_col;
     } else {
-      const u32 u2 = unit - (u32)p.tier1_units;
-      panel = u2 % p.panels;
-      const int t1 = u2 / p.panels;
-      plane_id = p.tier1_planes + t1 / p.strips;
-      r_begin = (t1 % p.strips) * p.rows_per_strip;
-      r_end = min(H, r_begin + p.rows_per_strip);
+      pos = (u32)p.tier1_units * (u32)p.groups_per_col + (unit - (u32)p.tier1_units) * (u32)p.chunk_groups;
+      pos_end = min(p.total_groups, pos + (u32)p.chunk_groups);
     }
+    while (pos < pos_end) {  // warp-uniform
+    const u32 column = pos / (u32)p.groups_per_col;
+    const int g_first = (int)(pos - column * (u32)p.groups_per_col);
+    const int g_last = min(p.groups_per_col, g_first + (int)(pos_end - pos));
+    pos += (u32)(g_last - g_first);
+    const int panel = (int)(column % (u32)p.panels), plane_id = (int)(column / (u32)p.panels);
+    const int r_begin = g_first * kGroupRows, r_end = min(H, g_last * kGroupRows);
     const int b = plane_id / C, c = plane_id % C;
     const bool is_anchor = c < p.M;
     const CUtensorMap* tmap = is_anchor ? &tm_anchor : &tm_part;
@@ -337,7 +356,7 @@ sdnet_peaks_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_cons
     *reinterpret_cast<int4*>(minx + 4 * lane) = make_int4(0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff);
     __syncwarp();
 
-    // tile k of the unit = image rows r_begin - R + 4k ..; running number tile_n + k
+    // tile k of the unit = image rows r_begin - R + 4k ..
     auto issue = [&](u32 s, int y) {  // lane 0: pull the tile whose first image row is y into slot s
       mbar_arrive_expect_tx(bars_s + 8 * s, kTileBytes);
       if (S == 1) {
@@ -347,26 +366,32 @@ sdnet_peaks_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_cons
         tma_tile_4d(ring_s + s * kSlotB + kOddBoxOff, tmap, xc + p.odd_x - kOddShiftB / 4, y >> 1, csel, b, bars_s + 8 * s);
       }
     };
-    auto wait_tile = [&](u32 n) {
-      mbar_wait(bars_s + 8 * (n & (NG - 1)), (n >> 2) & 1u);
+    auto wait_tile = [&](u32 slot, u32 par) {
+      mbar_wait(bars_s + 8 * slot, par);
       if (edge) {  // warp-uniform
-        tile_fix_edges<DT>(ring_s + (n & (NG - 1)) * kSlotB, x0, W, lane);
+        tile_fix_edges<DT>(ring_s + slot * kSlotB, x0, W, lane);
         __syncwarp();
       }
     };
     int y_next = r_begin - R;  // first image row of the next tile to issue
     if (lane == 0) {
       const int first = min(NG, groups);
-      for (int k = 0; k < first; ++k) issue((tile_n + (u32)k) & (NG - 1), y_next + kGroupRows * k);
+      u32 sl = cur_slot;
+      for (int k = 0; k < first; ++k) {
+        issue(sl, y_next + kGroupRows * k);
+        if (++sl == (u32)NG) sl = 0;
+      }
     }
     y_next += kGroupRows * NG;
     int gfloor_seen = 0;
     constexpr int poll_mask = 3;  // measured at 128-row strips: polling every group 0.179 ms, every 4th 0.136 ms, every 8th 0.146 ms
     u32 idx0 = (u32)(r_begin * W + panel * kPanel);  // flat index of the group's row 0, panel column 0
-    wait_tile(tile_n);
+    wait_tile(cur_slot, cur_par);
     for (int g = 0; g < groups_out; ++g, idx0 += (u32)(kGroupRows * W)) {
-      const u32 n = tile_n + (u32)g;  // tile holding the group's first window row
-      if (R == 2 || g + 1 < groups) wait_tile(n + 1);
+      // cur_* = the tile holding the group's first window row, nxt_* = the one after it
+      u32 nxt_slot = cur_slot, nxt_par = cur_par;
+      step_pos(nxt_slot, nxt_par);
+      if (R == 2 || g + 1 < groups) wait_tile(nxt_slot, nxt_par);
       if ((g & poll_mask) == 0) {
         // every 16 rows: apply the plane-wide floor fetched one period ago
         // and start the next fetch.  The load writes straight into the register it will be read
@@ -375,10 +400,10 @@ sdnet_peaks_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_cons
         asm volatile("ld.global.cg.s32 %0, [%1];" : "=r"(gfloor_seen) : "l"(gfloor_ptr) : "memory");
       }
       // window rows of group row i are ring rows row0 + i .. row0 + i + 2R; its centre row is row0 + i + R
-      const u32 row0 = (n * kGroupRows) & kRowMask;
+      const u32 row0 = cur_slot * kGroupRows;
       uint4 c0, c1, c2, c3;
       if (R == 2) {  // centres: rows 2, 3 of this tile's slot and rows 0, 1 of the next
-        const u32 a01 = ring_own + (n & (NG - 1)) * kSlotB, a23 = ring_own + ((n + 1) & (NG - 1)) * kSlotB;
+        const u32 a01 = ring_own + cur_slot * kSlotB, a23 = ring_own + nxt_slot * kSlotB;
         if (S == 1) {
           c0 = lds128u(a01 + 2 * kTilePitchB); c1 = lds128u(a01 + 3 * kTilePitchB);
           c2 = lds128u(a23); c3 = lds128u(a23 + kTilePitchB);
@@ -387,7 +412,7 @@ sdnet_peaks_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_cons
           c2 = lds128u(a23); c3 = lds64x2(a23 + kOddBoxOff + kOddShiftB);
         }
       } else {  // S == 1
-        const u32 a012 = ring_own + (row0 + 1) * kTilePitchB, a3 = ring_own + ((row0 + 4) & kRowMask) * kTilePitchB;
+        const u32 a012 = ring_own + (row0 + 1) * kTilePitchB, a3 = ring_own + nxt_slot * kGroupRows * kTilePitchB;
         c0 = lds128u(a012); c1 = lds128u(a012 + kTilePitchB); c2 = lds128u(a012 + 2 * kTilePitchB); c3 = lds128u(a3);
       }
       if (__any_sync(0xffffffffu, TileMax<DT>::group(c0, c1, c2, c3) > st.floorx)) {
@@ -411,7 +436,7 @@ sdnet_peaks_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_cons
         settle_entries<R, DT, S>(st, work, nent, ring_s, row0, row_tab, floorx, idx0, W, pre, buf, hist, minx, sf, count_ptr, list,
                                  p.cap, K, lane, xscale, satx);
         // while the plane has no floor yet, publish early and often; later only in batches
-        if (st.nbuf >= 16 || (st.nbuf > 0 && gfloor_seen <= 0)) {
+        if (st.nbuf >= kFlushAt || (st.nbuf > 0 && gfloor_seen <= 0)) {
           __syncwarp();
           flush_candidates<DT>(st, buf, hist, minx, sf, count_ptr, list, p.cap, K, lane, pre, xscale, satx);
         }
@@ -421,15 +446,18 @@ sdnet_peaks_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_cons
       __syncwarp();
       if (lane == 0 && g + NG < groups) {
         if (edge) fence_proxy_async();  // the slot was patched with ordinary stores
-        issue(n & (NG - 1), y_next);
+        issue(cur_slot, y_next);
       }
       y_next += kGroupRows;
+      cur_slot = nxt_slot;
+      cur_par = nxt_par;
     }
-    tile_n += (u32)groups;
+    for (int k = groups_out; k < groups; ++k) step_pos(cur_slot, cur_par);  // the halo tile below the last group
     if (st.nbuf) {
       __syncwarp();
       flush_candidates<DT>(st, buf, hist, minx, sf, count_ptr, list, p.cap, K, lane, pre, xscale, satx);
     }
+    }  // segments of the unit
   }
 }
 

@@ -29,6 +29,9 @@
 //   * ties: (score desc, class asc, flat index asc) -- what torch.topk does on CUDA for k > 32;
 //   * grouping arithmetic uses explicitly rounded mul/add/sqrt (no FMA contraction) and the
 //     first minimum wins.
+#include <atomic>
+#include <mutex>
+
 #include "common.cuh"
 #include "floors.cuh"
 #include "peaks_warp.cuh"
@@ -54,7 +57,14 @@ Workspace plan_workspace(int B, int M, int N, int H, int W, int K, int P) {
   Workspace ws;
   const size_t planes = (size_t)B * (M + N);
   const int kmax = K > P ? K : P;
-  ws.cap = (int)((size_t)H * W / 8 + 2 * (size_t)kmax + 1024);
+  // A tie-free plane of the benchmark configs records ~9-12 K candidates (K (1 + ln(maxima / K)) plus what the floors'
+  // lag lets through); a plane that overflows `cap` (huge exact plateaus) goes through the exact select, which
+  // keeps its 1-bit-per-pixel survivor bitmap behind the K output records of the same region.
+  const size_t by_k = 8 * (size_t)kmax + 8192, by_map = (size_t)H * W / 8 + 2 * (size_t)kmax + 1024;
+  const size_t exact_need = (size_t)kmax + 2 + ((size_t)H * W + 63) / 64 + 16;
+  size_t cap = by_k < by_map ? by_k : by_map;
+  if (cap < exact_need) cap = exact_need;
+  ws.cap = (int)cap;
   size_t off = 0;
   ws.off_counts = off; off = align_up(off + planes * sizeof(int), 256);
   ws.off_flags = off;  off = align_up(off + planes * sizeof(int), 256);
@@ -66,13 +76,19 @@ Workspace plan_workspace(int B, int M, int N, int H, int W, int K, int P) {
   return ws;
 }
 
+// SM count of the CURRENT device, cached per device ordinal (processes that drive several GPUs from
+// different threads see their own device's count); relaxed atomics: the value is idempotent.
 int device_sm_count() {
-  static int cached = 0;
-  if (cached) return cached;
+  constexpr int kMaxDev = 64;
+  static std::atomic<int> cached[kMaxDev];
   int dev = 0, sms = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev >= 0 && dev < kMaxDev) {
+    sms = cached[dev].load(std::memory_order_relaxed);
+    if (sms > 0) return sms;
+  }
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) return 148;
-  cached = sms;
+  if (dev >= 0 && dev < kMaxDev) cached[dev].store(sms, std::memory_order_relaxed);
   return sms;
 }
 
@@ -191,10 +207,12 @@ int select_peaks_path(const SdnetDecodeParams* p, CUtensorMap* tm_anchor, CUtens
 }
 
 template <typename Kern>
-void launch_peaks(Kern kern, dim3 grid, dim3 block, cudaStream_t stream, const PeaksParams& pp) {
+cudaError_t launch_peaks(Kern kern, dim3 grid, dim3 block, cudaStream_t stream, const PeaksParams& pp) {
   // > 48 KB of dynamic shared memory needs the opt-in (idempotent, cheap)
-  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kPeaksSmem);
+  const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kPeaksSmem);
+  if (e != cudaSuccess) return e;
   kern<<<grid, block, kPeaksSmem, stream>>>(pp);
+  return cudaSuccess;
 }
 
 // Launch with programmatic stream serialization (PDL): see pdl_wait() in the kernels.
@@ -213,14 +231,119 @@ void launch_pdl(Kern kern, dim3 grid, dim3 block, cudaStream_t stream, const Par
   cudaLaunchKernelEx(&cfg, kern, prm);
 }
 
+// Resident CTAs per SM of a tile-kernel instantiation, asked once per (device, instantiation); sets the
+// kernel's shared-memory attributes on the way.  0 = the attributes could not be set (`*err` says why).
+int tile_ctas_per_sm(TileKernel kern, int dtype, int tile_s, int radius, int smem, cudaError_t* err) {
+  constexpr int kMaxDev = 64;
+  static std::mutex mu;
+  static int cache[kMaxDev][3][3][3] = {};  // [device][dtype][rows per TMA row][radius]; 0 = not asked yet
+  int dev = 0;
+  *err = cudaGetDevice(&dev);
+  if (*err != cudaSuccess) return 0;
+  if (dev < 0 || dev >= kMaxDev) dev = kMaxDev - 1;
+  std::lock_guard<std::mutex> lock(mu);
+  int& per_sm = cache[dev][dtype][tile_s][radius];
+  if (per_sm > 0) return per_sm;
+  *err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (*err != cudaSuccess) return 0;
+  *err = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (*err != cudaSuccess) return 0;
+  int n = 0;
+  *err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, kTileWarps * 32, smem);
+  if (*err != cudaSuccess) return 0;
+  per_sm = n < 1 ? 1 : n;
+  return per_sm;
+}
+
+// Everything the peaks launch needs beyond the tensors: which kernel, how the planes are cut into
+// units, how many CTAs.  Host-only (sdnet_decode_schedule reports it without launching).
+struct PeaksPlan {
+  int path, tile_s;
+  TileKernel tile_kern;
+  int smem, ctas, ctas_per_sm, sms;
+  CUtensorMap tm_anchor, tm_part;
+};
+
+cudaError_t plan_peaks(const SdnetDecodeParams* p, PeaksParams& pp, PeaksPlan& pl) {
+  const int C = p->M + p->N;
+  const long long planes = (long long)p->B * C;
+  pl.sms = device_sm_count();
+  pl.tile_s = 0;
+  pl.path = select_peaks_path(p, &pl.tm_anchor, &pl.tm_part, &pl.tile_s);
+  const bool use_tile = pl.path == SDNET_PATH_TILE || pl.path == SDNET_PATH_TILE_ROW_PAIRS;
+  const bool is_f32 = p->dtype == SDNET_DTYPE_F32;
+  pp.odd_x = (int)(p->anchor_hm.stride_h / (is_f32 ? 1 : 2));  // in tensor-map elements
+  pp.tier1_units = 0;
+  pp.groups_per_col = 0;
+  pp.chunk_groups = 0;
+  pp.total_groups = 0;
+  pp.strips = 1;
+  pp.rows_per_strip = p->H;
+  if (use_tile) {
+    pl.tile_kern = tile_kernel_for(p->radius, p->dtype, pl.tile_s);
+    const int panel_cols = is_f32 ? TileGeom<SDNET_DTYPE_F32>::kPanel : TileGeom<SDNET_DTYPE_F16>::kPanel;
+    pl.smem = tile_smem(pl.tile_s);
+    cudaError_t err = cudaSuccess;
+    pl.ctas_per_sm = tile_ctas_per_sm(pl.tile_kern, p->dtype, pl.tile_s, p->radius, pl.smem, &err);
+    if (pl.ctas_per_sm <= 0) return err != cudaSuccess ? err : cudaErrorUnknown;
+    pp.panels = (p->W + panel_cols - 1) / panel_cols;
+    // The work is a line of `columns` x G groups of four rows (a column = one panel of one plane, top to
+    // bottom), cut into units handed out in order by an atomic counter.  Long units prune best (a unit
+    // warms its pruning floor once; measured at 128 images: whole columns 0.169 ms, 7 strips 0.221 ms), so:
+    //   tier 1: whole columns while they fill whole waves of the resident warps;
+    //   tier 2: what is left of the line cut into equal chunks, one per resident warp (a chunk may run
+    //           over the end of a column into the next one), so the last wave ends everywhere at once.
+    // With fewer columns than resident warps (small shards) everything is tier 2: one balanced wave.
+    const long long resident = (long long)pl.sms * pl.ctas_per_sm * kTileWarps;
+    const long long G = (p->H + kGroupRows - 1) / kGroupRows;
+    const long long columns = planes * pp.panels;
+    if (columns * G >= (1ll << 31)) return cudaErrorInvalidValue;
+    static const int chunk_override = [] {  // tuning knob, read once: SDNET_CHUNK_GROUPS = n
+      const char* e = getenv("SDNET_CHUNK_GROUPS");
+      return e ? atoi(e) : 0;
+    }();
+    const long long tier1 = (columns / resident) * resident;
+    const long long rest = (columns - tier1) * G;
+    long long chunk = (rest + resident - 1) / resident;
+    if (chunk < kMinChunkGroups) chunk = kMinChunkGroups;
+    if (chunk_override > 0) chunk = chunk_override;
+    if (chunk > G) chunk = G;
+    pp.tier1_units = (int)tier1;
+    pp.groups_per_col = (int)G;
+    pp.chunk_groups = (int)chunk;
+    pp.total_groups = (u32)(columns * G);
+    pp.units = (int)(tier1 + (rest + chunk - 1) / chunk);
+    long long ctas = ((long long)pp.units + kTileWarps - 1) / kTileWarps;
+    if (ctas > (long long)pl.sms * pl.ctas_per_sm) ctas = (long long)pl.sms * pl.ctas_per_sm;
+    pl.ctas = (int)ctas;
+  } else {
+    pl.tile_kern = nullptr;
+    pl.smem = kPeaksSmem;
+    pl.ctas_per_sm = kPeaksCtasPerSm;
+    pp.panels = (p->W + kPanelW - 1) / kPanelW;
+    const long long resident = (long long)pl.sms * kPeaksCtasPerSm * kWarps;
+    const long long units1 = planes * pp.panels;
+    int strips = (int)((4 * resident + units1 - 1) / units1);
+    const int max_strips = (p->H + 31) / 32;  // strips of at least 32 rows
+    if (strips > max_strips) strips = max_strips;
+    if (strips < 1) strips = 1;
+    pp.rows_per_strip = (p->H + strips - 1) / strips;
+    pp.strips = (p->H + pp.rows_per_strip - 1) / pp.rows_per_strip;
+    if (planes * pp.strips * pp.panels >= (1ll << 31)) return cudaErrorInvalidValue;
+    pp.units = (int)(planes * pp.strips * pp.panels);
+    long long ctas = ((long long)pp.units + kWarps - 1) / kWarps;
+    if (ctas > (long long)pl.sms * kPeaksCtasPerSm) ctas = (long long)pl.sms * kPeaksCtasPerSm;
+    pl.ctas = (int)ctas;
+  }
+  return cudaSuccess;
+}
+
 int launch_decode(const SdnetDecodeParams* p, cudaStream_t stream, cudaEvent_t* marks = nullptr) {
   const Workspace ws = plan_workspace(p->B, p->M, p->N, p->H, p->W, p->K, p->P);
   char* base = static_cast<char*>(p->workspace);
   const int C = p->M + p->N;
   const size_t planes = (size_t)p->B * C;
-  cudaError_t err = cudaMemsetAsync(base, 0, ws.off_lists, stream);
-  if (err != cudaSuccess) return (int)err;
-  if (marks) cudaEventRecord(marks[0], stream);
+  const int sms = device_sm_count();
 
   PeaksParams pp;
   pp.anchor = to_view(p->anchor_hm);
@@ -233,100 +356,29 @@ int launch_decode(const SdnetDecodeParams* p, cudaStream_t stream, cudaEvent_t* 
   pp.sched = reinterpret_cast<u32*>(base + ws.off_sched);
   pp.ghist = reinterpret_cast<u32*>(base + ws.off_ghist);
   pp.gfloor = reinterpret_cast<int*>(base + ws.off_gfloor);
-  pp.tier1_units = 0;
-  pp.tier1_planes = 0;
-  const int sms = device_sm_count();
-  CUtensorMap tm_anchor, tm_part;
-  int tile_s = 0;
-  const int path = select_peaks_path(p, &tm_anchor, &tm_part, &tile_s);
-  const bool use_tile = path == SDNET_PATH_TILE || path == SDNET_PATH_TILE_ROW_PAIRS;
-  const bool is_f32 = p->dtype == SDNET_DTYPE_F32;
-  pp.odd_x = (int)(p->anchor_hm.stride_h / (is_f32 ? 1 : 2));  // in tensor-map elements
-  static const int tier2_strips = [] {  // tuning knob, read once: SDNET_TIER2_STRIPS = n (default 2)
-    const char* e = getenv("SDNET_TIER2_STRIPS");
-    return e && atoi(e) > 0 ? atoi(e) : 2;
-  }();
-  static const int strips_override = [] {  // tuning knob, read once: SDNET_STRIPS = n
-    const char* e = getenv("SDNET_STRIPS");
-    return e ? atoi(e) : 0;
-  }();
-  auto pick_strips = [&](long long units_per_strip1, long long want_units) {
-    int strips = (int)((want_units + units_per_strip1 - 1) / units_per_strip1);
-    if (strips_override > 0) strips = strips_override;
-    const int max_strips = (p->H + 31) / 32;  // strips of at least 32 rows
-    if (strips > max_strips) strips = max_strips;
-    if (strips < 1) strips = 1;
-    pp.rows_per_strip = (p->H + strips - 1) / strips;
-    if (use_tile && tile_s == 2) pp.rows_per_strip = (pp.rows_per_strip + 1) & ~1;  // row pairs: strips start on even rows
-    pp.strips = (p->H + pp.rows_per_strip - 1) / pp.rows_per_strip;
-  };
-  if (use_tile) {
-    const TileKernel kern = tile_kernel_for(p->radius, p->dtype, tile_s);
-    const int kPanelCols = is_f32 ? TileGeom<SDNET_DTYPE_F32>::kPanel : TileGeom<SDNET_DTYPE_F16>::kPanel;
-    const int kTileSmem = tile_smem(tile_s);
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmem);
-    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    static int per_sm_cache[3][3][3] = {};  // [dtype][rows per TMA row][radius]; 0 = not asked yet
-    int& per_sm = per_sm_cache[p->dtype][tile_s][p->radius];
-    if (per_sm == 0 &&
-        (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTileWarps * 32, kTileSmem) != cudaSuccess || per_sm < 1))
-      per_sm = 1;
-    pp.panels = (p->W + kPanelCols - 1) / kPanelCols;
-    const long long resident_warps = (long long)sms * per_sm * kTileWarps;
-    // long units prune best (measured: 128 images, 1 strip 0.169 ms, 7 strips 0.221 ms): split planes
-    // into strips only while there are fewer units than resident warps
-    {
-      const long long units1 = (long long)planes * pp.panels;
-      pp.tier1_units = 0;
-      pp.tier1_planes = 0;
-      if (units1 <= resident_warps || strips_override > 0) {
-        // Fewer units than resident warps: every warp gets at most one unit per wave, so the kernel
-        // lasts ceil(units / warps) unit-times.  Cutting planes into S strips shortens the unit but
-        // costs ~15 % per extra strip (each strip re-warms its pruning floor); pick the S that
-        // minimises waves(S) * (1 + 0.15 (S - 1)) / S.  Measured at 128 images: S = 1, 2, 3, 4 ->
-        // 0.151, 0.163, 0.138, 0.183 ms.
-        int best_s = 1;
-        double best_cost = 1e30;
-        const int max_s = (p->H + 31) / 32 < 16 ? (p->H + 31) / 32 : 16;
-        for (int cand = 1; cand <= (max_s > 0 ? max_s : 1); ++cand) {
-          const long long waves = (units1 * cand + resident_warps - 1) / resident_warps;
-          const double cost = (double)waves * (1.0 + 0.15 * (cand - 1)) / cand;
-          if (cost < best_cost - 1e-9) { best_cost = cost; best_s = cand; }
-        }
-        pick_strips(units1, units1 * best_s);
-        pp.units = (int)(planes * pp.strips * pp.panels);
-      } else {
-        // whole waves of whole-height units first, then the leftover planes in short strips
-        const long long full_waves = units1 / resident_warps;
-        pp.tier1_planes = (int)((full_waves * resident_warps) / pp.panels);
-        pp.tier1_units = pp.tier1_planes * pp.panels;
-        const long long rest = (long long)planes - pp.tier1_planes;
-        pick_strips(rest > 0 ? rest * pp.panels : 1, rest > 0 ? rest * pp.panels * tier2_strips : 1);
-        pp.units = (int)(pp.tier1_units + rest * pp.strips * pp.panels);
-      }
-    }
-    long long ctas = ((long long)pp.units + kTileWarps - 1) / kTileWarps;
-    if (ctas > (long long)sms * per_sm) ctas = (long long)sms * per_sm;
-    kern<<<dim3((unsigned)ctas), dim3(kTileWarps * 32), kTileSmem, stream>>>(pp, tm_anchor, tm_part);
+  PeaksPlan pl;
+  cudaError_t err = plan_peaks(p, pp, pl);
+  if (err != cudaSuccess) return (int)err;
+  err = cudaMemsetAsync(base, 0, ws.off_lists, stream);
+  if (err != cudaSuccess) return (int)err;
+  if (marks) cudaEventRecord(marks[0], stream);
+
+  if (pl.tile_kern) {
+    pl.tile_kern<<<dim3((unsigned)pl.ctas), dim3(kTileWarps * 32), pl.smem, stream>>>(pp, pl.tm_anchor, pl.tm_part);
   } else {
-    pp.panels = (p->W + kPanelW - 1) / kPanelW;
-    const int resident_warps = sms * kPeaksCtasPerSm * kWarps;
-    pick_strips((long long)planes * pp.panels, 4ll * resident_warps);
-    pp.units = (int)(planes * pp.strips * pp.panels);
-    long long ctas = ((long long)pp.units + kWarps - 1) / kWarps;
-    if (ctas > (long long)sms * kPeaksCtasPerSm) ctas = (long long)sms * kPeaksCtasPerSm;
-    dim3 grid((unsigned)ctas), block(kThreads);
+    dim3 grid((unsigned)pl.ctas), block(kThreads);
     const bool r2 = p->radius == 2;
     if (p->dtype == SDNET_DTYPE_F16) {
-      if (r2) launch_peaks(sdnet_peaks_kernel<false, 2, SDNET_DTYPE_F16>, grid, block, stream, pp);
-      else launch_peaks(sdnet_peaks_kernel<false, 1, SDNET_DTYPE_F16>, grid, block, stream, pp);
+      err = r2 ? launch_peaks(sdnet_peaks_kernel<false, 2, SDNET_DTYPE_F16>, grid, block, stream, pp)
+               : launch_peaks(sdnet_peaks_kernel<false, 1, SDNET_DTYPE_F16>, grid, block, stream, pp);
     } else if (p->dtype == SDNET_DTYPE_BF16) {
-      if (r2) launch_peaks(sdnet_peaks_kernel<false, 2, SDNET_DTYPE_BF16>, grid, block, stream, pp);
-      else launch_peaks(sdnet_peaks_kernel<false, 1, SDNET_DTYPE_BF16>, grid, block, stream, pp);
+      err = r2 ? launch_peaks(sdnet_peaks_kernel<false, 2, SDNET_DTYPE_BF16>, grid, block, stream, pp)
+               : launch_peaks(sdnet_peaks_kernel<false, 1, SDNET_DTYPE_BF16>, grid, block, stream, pp);
     } else {
-      if (r2) launch_peaks(sdnet_peaks_kernel<false, 2, SDNET_DTYPE_F32>, grid, block, stream, pp);
-      else launch_peaks(sdnet_peaks_kernel<false, 1, SDNET_DTYPE_F32>, grid, block, stream, pp);
+      err = r2 ? launch_peaks(sdnet_peaks_kernel<false, 2, SDNET_DTYPE_F32>, grid, block, stream, pp)
+               : launch_peaks(sdnet_peaks_kernel<false, 1, SDNET_DTYPE_F32>, grid, block, stream, pp);
     }
+    if (err != cudaSuccess) return (int)err;
   }
   err = cudaGetLastError();
   if (err != cudaSuccess) return (int)err;
@@ -434,6 +486,32 @@ int sdnet_decode_peaks_path(const SdnetDecodeParams* params) {
   return select_peaks_path(params, &a, &b, &tile_s);
 }
 
+int sdnet_decode_schedule(const SdnetDecodeParams* params, SdnetSchedule* out) {
+  const int rc = validate(params);
+  if (rc != 0) return rc;
+  if (!out) return SDNET_E_NULL;
+  if (out->struct_size != sizeof(SdnetSchedule)) return SDNET_E_STRUCT;
+  PeaksParams pp;
+  PeaksPlan pl;
+  const cudaError_t err = plan_peaks(params, pp, pl);
+  if (err != cudaSuccess) return (int)err;
+  out->path = pl.path;
+  out->units = pp.units;
+  out->tier1_units = pp.tier1_units;
+  out->chunk_units = pl.tile_kern ? pp.units - pp.tier1_units : 0;
+  out->chunk_groups = pp.chunk_groups;
+  out->groups_per_column = pp.groups_per_col;
+  out->panels = pp.panels;
+  out->strips = pp.strips;
+  out->rows_per_strip = pp.rows_per_strip;
+  out->ctas = pl.ctas;
+  out->warps_per_cta = pl.tile_kern ? kTileWarps : kWarps;
+  out->ctas_per_sm = pl.ctas_per_sm;
+  out->sms = pl.sms;
+  out->list_capacity = plan_workspace(params->B, params->M, params->N, params->H, params->W, params->K, params->P).cap;
+  return 0;
+}
+
 int sdnet_decode_launch(const SdnetDecodeParams* params, void* stream) {
   const int rc = validate(params);
   if (rc) return rc;
@@ -504,31 +582,24 @@ int sdnet_decode_host_launch(const SdnetDecodeParams* params, void* staging, siz
   const int rc = validate(params);
   if (rc) return rc;
   if (!staging) return SDNET_E_NULL;
-  if (params->dtype != SDNET_DTYPE_F32) return SDNET_E_DTYPE;  // host-buffer entry point: fp32 only for now
   const SdnetDecodeParams& p = *params;
-  const size_t plane_bytes = (size_t)p.H * p.W * sizeof(float);
+  const size_t esz = p.dtype == SDNET_DTYPE_F32 ? 4 : 2;
+  const size_t plane_bytes = (size_t)p.H * p.W * esz;
   const size_t need = (size_t)p.B * (p.M + p.N) * plane_bytes;
   if (staging_bytes < need || ((uintptr_t)staging & 255)) return SDNET_E_WORKSPACE;
+  // dense rows; dense channels (a single channel has no channel stride to speak of)
   if (p.anchor_hm.stride_h != p.W || p.part_hm.stride_h != p.W) return SDNET_E_STRIDE;
+  if ((p.M > 1 && p.anchor_hm.stride_c != (long long)p.H * p.W) || (p.N > 1 && p.part_hm.stride_c != (long long)p.H * p.W))
+    return SDNET_E_STRIDE;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   // heat planes: host (strided per image) -> dense device staging [B][M+N][H][W]
   char* dst = static_cast<char*>(staging);
   const size_t img_bytes = (size_t)(p.M + p.N) * plane_bytes;
-  cudaError_t err;
-  if (p.anchor_hm.stride_c == (long long)p.H * p.W) {
-    err = cudaMemcpy2DAsync(dst, img_bytes, p.anchor_hm.data, (size_t)p.anchor_hm.stride_b * sizeof(float),
-                            (size_t)p.M * plane_bytes, p.B, cudaMemcpyHostToDevice, stream);
-  } else {
-    err = cudaErrorInvalidValue;
-  }
+  cudaError_t err = cudaMemcpy2DAsync(dst, img_bytes, p.anchor_hm.data, (size_t)p.anchor_hm.stride_b * esz,
+                                      (size_t)p.M * plane_bytes, p.B, cudaMemcpyHostToDevice, stream);
   if (err != cudaSuccess) return (int)err;
-  if (p.part_hm.stride_c == (long long)p.H * p.W || p.N == 1) {
-    err = cudaMemcpy2DAsync(dst + (size_t)p.M * plane_bytes, img_bytes, p.part_hm.data,
-                            (size_t)p.part_hm.stride_b * sizeof(float), (size_t)p.N * plane_bytes, p.B,
-                            cudaMemcpyHostToDevice, stream);
-  } else {
-    err = cudaErrorInvalidValue;
-  }
+  err = cudaMemcpy2DAsync(dst + (size_t)p.M * plane_bytes, img_bytes, p.part_hm.data, (size_t)p.part_hm.stride_b * esz,
+                          (size_t)p.N * plane_bytes, p.B, cudaMemcpyHostToDevice, stream);
   if (err != cudaSuccess) return (int)err;
   SdnetDecodeParams q = p;
   q.anchor_hm.data = dst;

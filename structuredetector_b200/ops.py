@@ -19,7 +19,7 @@ import torch
 from . import _native
 PEAKS_PATHS = ("warp", "tile", "tile_row_pairs")  # SDNET_PATH_* in include/sdnet_decode.h
 from ._native import (FLAG_EXACT_SELECT, FLAG_NO_GROUPING, FLAG_PRE_ACTIVATED, FLAG_WARP_KERNEL, SdnetDecodeParams,
-                      SdnetTensor4)
+                      SdnetSchedule, SdnetTensor4)
 
 __all__ = ["decode_packed", "activate_maps", "DecodePlan", "PackedDetections", "gpu_launches_per_decode"]
 
@@ -105,12 +105,14 @@ class DecodePlan:
     """Pre-sized workspace + output blob for one (device, shape, K, P): the low-overhead way
     to call the C ABI repeatedly (bench loop, CUDA-graph capture, sharded decode)."""
 
-    def __init__(self, device, B, M, N, H, W, K, P, dtype: torch.dtype = torch.float32):
+    def __init__(self, device, B, M, N, H, W, K, P, dtype: torch.dtype = torch.float32, lib=None):
         self.shape = (B, M, N, H, W, K, P)
         self.dtype = dtype
         self.device = torch.device(device)
-        self.lib = _native.load()
-        self.workspace_bytes = _native.workspace_bytes(B, M, N, H, W, K, P)
+        if self.device.type == "cuda" and self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.lib = lib if lib is not None else _native.load()
+        self.workspace_bytes = _native.workspace_bytes(B, M, N, H, W, K, P, _DTYPES[dtype], lib=self.lib)
         self.workspace = torch.empty(self.workspace_bytes, dtype=torch.uint8, device=self.device)
         self.out = _carve(torch.empty(packed_nbytes(B, K, P, M + N), dtype=torch.uint8, device=self.device),
                           B, K, P, M + N)
@@ -130,7 +132,27 @@ class DecodePlan:
         p.part_emb, p.assign = out.part_emb.data_ptr(), out.assign.data_ptr()
         p.counts, p.diag = out.counts.data_ptr(), out.diag.data_ptr()
 
-    def _bind_inputs(self, anchor_hm, part_hm, offsets, embeddings, conf_f32, dist_abs_f32, radius, flags):
+    def _check_inputs(self, anchor_hm, part_hm, offsets, embeddings, host_ok: bool = False):
+        """The kernels trust the plan's (B, M, N, H, W), dtype and device: a tensor that differs would be
+        reinterpreted or read out of bounds, so refuse it here."""
+        B, M, N, H, W, _, _ = self.shape
+        want = (("anchor_hm", anchor_hm, M), ("part_hm", part_hm, N), ("offsets", offsets, 2), ("embeddings", embeddings, 2))
+        for name, t, channels in want:
+            if t is None:
+                continue
+            if t.dtype != self.dtype:
+                raise TypeError(f"{name}: dtype {t.dtype} differs from the plan's {self.dtype}")
+            if tuple(t.shape) != (B, channels, H, W):
+                raise ValueError(f"{name}: shape {tuple(t.shape)} differs from the plan's {(B, channels, H, W)}")
+            if t.is_cuda:
+                if t.device != self.device:
+                    raise RuntimeError(f"{name} lives on {t.device}, the plan on {self.device}")
+            elif not (host_ok and t.is_pinned()):
+                raise RuntimeError(f"{name} lives on {t.device}: the B200 decode path has no CPU fallback")
+
+    def _bind_inputs(self, anchor_hm, part_hm, offsets, embeddings, conf_f32, dist_abs_f32, radius, flags,
+                     host_ok: bool = False):
+        self._check_inputs(anchor_hm, part_hm, offsets, embeddings, host_ok)
         p = self.params
         p.anchor_hm, p.part_hm, p.offsets = _view4(anchor_hm), _view4(part_hm), _view4(offsets)
         p.embeddings = _view4(embeddings) if embeddings is not None else SdnetTensor4(None, 0, 0, 0, 1)
@@ -156,6 +178,18 @@ class DecodePlan:
             _native.check(rc, "sdnet_decode_peaks_path")
         return PEAKS_PATHS[rc]
 
+    def schedule(self, anchor_hm, part_hm, offsets, embeddings, radius=2, flags=0) -> dict:
+        """How the peaks kernel cuts these tensors into units on this device (``sdnet_decode_schedule``)."""
+        self._bind_inputs(anchor_hm, part_hm, offsets, embeddings, 0.0, 0.0, radius, flags)
+        out = SdnetSchedule()
+        out.struct_size = ctypes.sizeof(SdnetSchedule)
+        with torch.cuda.device(self.device):
+            rc = self.lib.sdnet_decode_schedule(ctypes.byref(self.params), ctypes.byref(out))
+        _native.check(rc, "sdnet_decode_schedule")
+        d = {name: getattr(out, name) for name, _ in SdnetSchedule._fields_ if name != "struct_size"}
+        d["path"] = PEAKS_PATHS[d["path"]]
+        return d
+
     def run_timed(self, anchor_hm, part_hm, offsets, embeddings, conf_f32, dist_abs_f32, radius=2, flags=0):
         """Synchronous profiling run: returns (peaks_ms, exact_select_ms, tail_ms) device times."""
         self._bind_inputs(anchor_hm, part_hm, offsets, embeddings, conf_f32, dist_abs_f32, radius, flags)
@@ -166,11 +200,12 @@ class DecodePlan:
         return tuple(float(x) for x in ms)
 
     def run_host(self, anchor_hm, part_hm, offsets, embeddings, conf_f32, dist_abs_f32, staging: torch.Tensor,
-                 radius=2, flags=0, stream: int | None = None) -> PackedDetections:
+                 radius=2, flags=0, stream=None) -> PackedDetections:
         """Same, with the four inputs in pinned HOST memory (``sdnet_decode_host_launch``)."""
-        self._bind_inputs(anchor_hm, part_hm, offsets, embeddings, conf_f32, dist_abs_f32, radius, flags)
+        self._bind_inputs(anchor_hm, part_hm, offsets, embeddings, conf_f32, dist_abs_f32, radius, flags, host_ok=True)
         if stream is None:
-            stream = torch.cuda.current_stream(self.device).cuda_stream
+            stream = torch.cuda.current_stream(self.device)
+        stream = getattr(stream, "cuda_stream", stream)
         rc = self.lib.sdnet_decode_host_launch(ctypes.byref(self.params), ctypes.c_void_p(staging.data_ptr()),
                                                ctypes.c_size_t(staging.numel() * staging.element_size()),
                                                ctypes.c_void_p(stream))
@@ -184,6 +219,11 @@ class DecodePipeline:
     batch's peaks kernel already streams its heat maps, so a stream of batches runs at the peaks kernel's
     rate.  ``submit`` returns the slot's outputs and an event; a slot's outputs are overwritten
     ``depth`` submits later, so consume them (or wait on the event and copy) before that.
+
+    Stream safety: ``submit`` makes the slot's stream wait for everything already enqueued on the
+    caller's current stream (the producer of the inputs) and tells the caching allocator that the
+    inputs are in use on the slot's stream (``record_stream``), so the network may run ahead and
+    free/reuse its output buffers without the decode reading recycled memory.
 
     ``make_plan(i)`` builds slot i's plan: anything with ``.run(..., stream=)`` (``DecodePlan``,
     ``parallel.FusedGatherPlan``)."""
@@ -207,6 +247,10 @@ class DecodePipeline:
     def submit(self, anchor_hm, part_hm, offsets, embeddings, conf_f32, dist_abs_f32, radius=2, flags=0):
         k = self._next
         self._next = (k + 1) % len(self.plans)
+        self.streams[k].wait_stream(torch.cuda.current_stream(self.device))
+        for t in (anchor_hm, part_hm, offsets, embeddings):
+            if t is not None and t.is_cuda:
+                t.record_stream(self.streams[k])
         out = self.plans[k].run(anchor_hm, part_hm, offsets, embeddings, conf_f32, dist_abs_f32, radius, flags,
                                 stream=self.streams[k])
         self.events[k].record(self.streams[k])
@@ -226,6 +270,23 @@ def _f32(value: float, dtype: torch.dtype = torch.float32) -> float:
 
 
 # ------------------------------------------------------------------------------------ custom ops
+_OP_PLANS: dict = {}
+_OP_PLANS_MAX = 8
+
+
+def _op_plan(device, B, M, N, H, W, K, P, dtype) -> DecodePlan:
+    """Workspace cache of the custom op, keyed by (device, stream, shape, dtype): a decode needs its
+    scratch only while its three kernels run, and work on one stream is ordered, so consecutive calls
+    on a stream share one workspace instead of allocating ~0.1 MB per image per call."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream, B, M, N, H, W, K, P, dtype)
+    plan = _OP_PLANS.get(key)
+    if plan is None:
+        if len(_OP_PLANS) >= _OP_PLANS_MAX:
+            _OP_PLANS.pop(next(iter(_OP_PLANS)))
+        plan = _OP_PLANS[key] = DecodePlan(device, B, M, N, H, W, K, P, dtype)
+    return plan
+
+
 @torch.library.custom_op("sdnet_b200::decode", mutates_args=(), device_types="cuda")
 def _decode_op(anchor_hm: torch.Tensor, part_hm: torch.Tensor, offsets: torch.Tensor, embeddings: torch.Tensor,
                max_objects: int, max_parts: int, conf_f32: float, dist_abs_f32: float, radius: int,
@@ -233,9 +294,12 @@ def _decode_op(anchor_hm: torch.Tensor, part_hm: torch.Tensor, offsets: torch.Te
     B, M, H, W = anchor_hm.shape
     N = part_hm.shape[1]
     with torch.cuda.device(anchor_hm.device):
-        plan = DecodePlan(anchor_hm.device, B, M, N, H, W, max_objects, max_parts, anchor_hm.dtype)
+        plan = _op_plan(anchor_hm.device, B, M, N, H, W, max_objects, max_parts, anchor_hm.dtype)
+        # the op returns a fresh tensor (no aliasing between calls); the workspace is the cached part
+        blob = torch.empty(plan.out.blob.numel(), dtype=torch.uint8, device=anchor_hm.device)
+        plan._bind_outputs(_carve(blob, B, max_objects, max_parts, M + N))
         plan.run(anchor_hm, part_hm, offsets, embeddings, conf_f32, dist_abs_f32, radius, flags)
-    return plan.out.blob
+    return blob
 
 
 @_decode_op.register_fake
@@ -292,20 +356,43 @@ def decode_packed(outputs: dict, max_objects: int, max_parts: int, conf_thresh: 
     """Run the CUDA decode on the four network-output views and return packed device tensors."""
     a_hm, p_hm, off = outputs["anchor_hm"], outputs["part_hm"], outputs["offsets"]
     emb = outputs["embeddings"] if group or "embeddings" in outputs else None
+    on_host = not a_hm.is_cuda  # pinned host tensors take the host-buffer entry point (everything else on a CPU raises)
     for name, t in (("anchor_hm", a_hm), ("part_hm", p_hm), ("offsets", off)) + ((("embeddings", emb),) if emb is not None else ()):
-        _check_tensor(name, t, dtype=a_hm.dtype)
+        _check_tensor(name, t, allow_pinned_host=on_host, dtype=a_hm.dtype)
+        if t.is_cuda == on_host:
+            raise RuntimeError(f"{name} lives on {t.device} but anchor_hm on {a_hm.device}: keep the four outputs together")
     B, M, H, W = a_hm.shape
     N = p_hm.shape[1]
     if emb is None:
         emb = off  # never read under NO_GROUPING without part_emb consumers; keeps the op signature tensor-only
     flags = (FLAG_PRE_ACTIVATED if pre_activated else 0) | (0 if group else FLAG_NO_GROUPING) | (
         FLAG_EXACT_SELECT if exact_select else 0) | (FLAG_WARP_KERNEL if warp_kernel else 0)
+    if on_host:
+        return _decode_from_host(a_hm, p_hm, off, emb, int(max_objects), int(max_parts),
+                                 _f32(conf_thresh, a_hm.dtype), _f32(float(dist_thresh) * min(W, H)), int(radius), int(flags))
     a_hm, p_hm, off, emb = map(_unit_w_stride, (a_hm, p_hm, off, emb))
     # `scores > conf` compares in the scores' dtype (fp16 scores against fp16(conf)); the distance gate
     # always compares fp32 distances
     blob = _decode_op(a_hm, p_hm, off, emb, int(max_objects), int(max_parts), _f32(conf_thresh, a_hm.dtype),
                       _f32(float(dist_thresh) * min(W, H)), int(radius), int(flags))
     return _carve(blob, B, int(max_objects), int(max_parts), M + N)
+
+
+def _decode_from_host(a_hm, p_hm, off, emb, K, P, conf_f32, dist_abs_f32, radius, flags) -> PackedDetections:
+    """Pinned HOST tensors -> packed detections on the current CUDA device (``sdnet_decode_host_launch``:
+    the heat planes are uploaded into a cached staging buffer, offsets/embeddings are read in place)."""
+    B, M, H, W = a_hm.shape
+    N = p_hm.shape[1]
+    device = torch.device("cuda", torch.cuda.current_device())
+    plan = _op_plan(device, B, M, N, H, W, K, P, a_hm.dtype)
+    need = B * (M + N) * H * W * a_hm.element_size()
+    if getattr(plan, "staging", None) is None or plan.staging.numel() < need:
+        plan.staging = torch.empty(need, dtype=torch.uint8, device=device)
+    blob = torch.empty(plan.out.blob.numel(), dtype=torch.uint8, device=device)
+    out = _carve(blob, B, K, P, M + N)
+    plan._bind_outputs(out)
+    plan.run_host(a_hm, p_hm, off, emb, conf_f32, dist_abs_f32, plan.staging, radius, flags)
+    return out
 
 
 def peaks_path(outputs: dict, max_objects: int, max_parts: int, *, radius: int = 2, warp_kernel: bool = False) -> str:

@@ -83,9 +83,18 @@ class FusedGatherPlan:
     image rows ``shard_bounds(B, world, r)`` of every field.  ``dest_delta[j] = peer_base[j] -
     local_base`` (``SdnetDecodeParams.dest_delta``) is all the kernel needs, because symmetric buffers
     share one layout.  Requires equal per-field offsets on all ranks, i.e. the same (B, K, P, C).
+
+    Write-after-read safety across ranks: the plan owns TWO result buffers and alternates between them.
+    Run i stores into buffer i % 2 on every rank, then passes the barrier.  A rank can only start the
+    remote stores of run i + 2 (the next writer of the same buffer) after it has passed the barrier of
+    run i + 1, i.e. after every peer has reached that barrier on its own stream -- which that peer
+    enqueued after whatever it did with result i.  So: consume (or copy) a result ON THE RUN STREAM, or
+    make the run stream wait for your consumer, before calling ``run`` again; the tensors returned by run
+    i stay valid until run i + 2 is enqueued.  No extra barrier is needed.
     """
 
-    def __init__(self, device, global_batch: int, M: int, N: int, H: int, W: int, K: int, P: int, group=None):
+    def __init__(self, device, global_batch: int, M: int, N: int, H: int, W: int, K: int, P: int, group=None,
+                 dtype: torch.dtype = torch.float32):
         import torch.distributed._symmetric_memory as symm
 
         self.group = group if group is not None else dist.group.WORLD
@@ -93,20 +102,21 @@ class FusedGatherPlan:
         self.sizes = shard_sizes(global_batch, self.world)
         self.lo, self.hi = shard_bounds(global_batch, self.world, self.rank)
         C = M + N
-        nbytes = ops.packed_nbytes(global_batch, K, P, C)
-        self.blob = symm.empty(nbytes, dtype=torch.uint8, device=device)
+        nbytes = (ops.packed_nbytes(global_batch, K, P, C) + 255) // 256 * 256
+        self.blob = symm.empty(2 * nbytes, dtype=torch.uint8, device=device)
         self.handle = symm.rendezvous(self.blob, self.group)
-        self.result = ops._carve(self.blob, global_batch, K, P, C)  # the gathered detections, valid after run()
+        # the gathered detections of run i live in results[i % 2]
+        self.results = [ops._carve(self.blob[k * nbytes:(k + 1) * nbytes], global_batch, K, P, C) for k in range(2)]
+        self.result = self.results[0]  # what the most recent run() returned
+        self._runs = 0
         shard = self.hi - self.lo
-        self.plan = ops.DecodePlan(device, shard, M, N, H, W, K, P)
-        # point the plan's outputs at this rank's rows of the global blob ...
+        self.plan = ops.DecodePlan(device, shard, M, N, H, W, K, P, dtype)
+        # this rank's rows of each global buffer: where the plan's outputs point ...
         lo, hi = self.lo, self.hi
-        mine = ops.PackedDetections(
-            self.result.anchor_out[lo:hi], self.result.part_out[lo:hi], self.result.anchor_inds[lo:hi],
-            self.result.part_inds[lo:hi], self.result.part_emb[lo:hi], self.result.assign[lo:hi],
-            self.result.counts[lo:hi], self.result.diag[lo * C:hi * C], None)
-        self.plan._bind_outputs(mine)
-        # ... and have every store replicated into the peers' copies
+        self._mine = [ops.PackedDetections(
+            r.anchor_out[lo:hi], r.part_out[lo:hi], r.anchor_inds[lo:hi], r.part_inds[lo:hi], r.part_emb[lo:hi],
+            r.assign[lo:hi], r.counts[lo:hi], r.diag[lo * C:hi * C], None) for r in self.results]
+        # ... and every store is replicated into the peers' copies
         ptrs = list(self.handle.buffer_ptrs)
         prm = self.plan.params
         prm.n_dest = self.world
@@ -120,7 +130,11 @@ class FusedGatherPlan:
         the global result.  Every rank must call its plans in the same order."""
         if stream is None:
             stream = torch.cuda.current_stream(self.plan.device)
+        k = self._runs % 2
+        self._runs += 1
+        self.plan._bind_outputs(self._mine[k])
         self.plan.run(anchor_hm, part_hm, offsets, embeddings, conf_f32, dist_abs_f32, radius, flags, stream=stream)
         with torch.cuda.stream(stream):
             self.handle.barrier()
+        self.result = self.results[k]
         return self.result

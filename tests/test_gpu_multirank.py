@@ -12,6 +12,7 @@ from structuredetector_b200.synth import CONFIGS, make_raw, split_outputs
 
 pytestmark = pytest.mark.gpu
 BATCH = 10  # uneven over 4 ranks, even over 2
+FUSED_RUNS = 5
 
 
 def _worker(rank, world, port, out_dir):
@@ -33,12 +34,22 @@ def _worker(rank, world, port, out_dir):
 
         fp = parallel.FusedGatherPlan(f"cuda:{rank}", BATCH, cfg.labels, cfg.parts, cfg.height, cfg.width,
                                       cfg.max_objects, cfg.max_parts)
-        for _ in range(3):  # repeated runs reuse the symmetric blob
-            res = fp.run(outs["anchor_hm"], outs["part_hm"], outs["offsets"], outs["embeddings"],
+        # Repeated runs reuse the plan's two symmetric result buffers.  Every run decodes DIFFERENT inputs
+        # and its result is read (copied on the run stream) before the next run is enqueued, with no host
+        # synchronisation in between and rank 1 deliberately slowed down: a missing write-after-read guard
+        # would let the fast rank's next run overwrite rows the slow rank has not copied yet.
+        keys = ("anchor_out", "part_out", "anchor_inds", "part_inds", "assign")
+        copies = []
+        for it in range(FUSED_RUNS):
+            raw_it = make_raw(cfg, "noise", batch=BATCH, seed=500 + it)
+            o = split_outputs(raw_it[lo:hi].to(f"cuda:{rank}"), cfg.labels, cfg.parts)
+            res = fp.run(o["anchor_hm"], o["part_hm"], o["offsets"], o["embeddings"],
                          ops._f32(cfg.conf_threshold), ops._f32(cfg.dist_thresh * min(cfg.width, cfg.height)))
+            if rank == 1:
+                torch.cuda._sleep(20_000_000)  # ~10 ms of device time before this rank reads its copy
+            copies.append({k: getattr(res, k).clone() for k in keys})
         torch.cuda.synchronize()
-        torch.save({k: getattr(res, k).cpu() for k in ("anchor_out", "part_out", "anchor_inds", "part_inds", "assign")},
-                   os.path.join(out_dir, f"fused{rank}.pt"))
+        torch.save([{k: v.cpu() for k, v in c.items()} for c in copies], os.path.join(out_dir, f"fused{rank}.pt"))
     finally:
         dist.destroy_process_group()
 
@@ -57,8 +68,18 @@ def test_sharded_decode_equals_single_gpu(cuda_device, tmp_path, world):
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    want_runs = []
+    for it in range(FUSED_RUNS):
+        raw_it = make_raw(cfg, "noise", batch=BATCH, seed=500 + it)
+        w = ops.decode_packed(split_outputs(raw_it.to(cuda_device), cfg.labels, cfg.parts), cfg.max_objects,
+                              cfg.max_parts, cfg.conf_threshold, cfg.dist_thresh)
+        want_runs.append({k: getattr(w, k).cpu() for k in ("anchor_out", "part_out", "anchor_inds", "part_inds", "assign")})
     for rank in range(world):
-        for kind in ("rank", "fused"):
-            got = torch.load(os.path.join(tmp_path, f"{kind}{rank}.pt"))
-            for key, val in got.items():
-                assert torch.equal(val, getattr(want, key).cpu()), f"{kind} {rank}: {key}"
+        got = torch.load(os.path.join(tmp_path, f"rank{rank}.pt"))
+        for key, val in got.items():
+            assert torch.equal(val, getattr(want, key).cpu()), f"nccl gather, rank {rank}: {key}"
+        runs = torch.load(os.path.join(tmp_path, f"fused{rank}.pt"))
+        assert len(runs) == FUSED_RUNS
+        for it, (g, w) in enumerate(zip(runs, want_runs)):
+            for key, val in g.items():
+                assert torch.equal(val, w[key]), f"fused gather, rank {rank}, run {it}: {key}"

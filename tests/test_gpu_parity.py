@@ -98,7 +98,9 @@ def test_decode_matches_oracle(cuda_device, name, mode, batch, warp_kernel):
     raw = make_raw(cfg, mode, batch=batch)
     got, want = _decode_both(cfg, raw, cuda_device, warp_kernel=warp_kernel)
     assert_packed_equal(got, want, what=f"{name}/{mode}")
-    assert int(got["diag"][:, 1].sum()) == 0 or mode == "ties"
+    # the TMA kernel's lists must not overflow on tie-free inputs; the per-lane fallback cuts small batches into
+    # many short strips that all warm up at once and may hand a plane to the exact select (same result, checked above)
+    assert int(got["diag"][:, 1].sum()) == 0 or mode == "ties" or warp_kernel
     # every config's fp32 maps are 16-byte aligned: the default path is the TMA tile kernel
     outs = split_outputs(raw[:1].to(cuda_device), cfg.labels, cfg.parts)
     assert ops.peaks_path(outs, cfg.max_objects, cfg.max_parts, warp_kernel=warp_kernel) == ("warp" if warp_kernel else "tile")
