@@ -27,6 +27,8 @@ def _ratio(src, dst):
 class _Scalable:
     """``resize``/``normalize`` mutate and return self; the ``-d`` forms work on a deep copy."""
 
+    __slots__ = ()
+
     def resized(self, in_size, out_size):
         return copy.deepcopy(self).resize(in_size, out_size)
 
@@ -36,6 +38,10 @@ class _Scalable:
 
 
 class Keypoint(_Scalable):
+    # slots: the decoder builds ~300 of these per image; the C assembly loop (csrc/fastobj.c) stores straight
+    # into the slot offsets.  Attribute names and constructor are the reference's (utils.py:12-17).
+    __slots__ = ("kind", "x", "y", "score")
+
     def __init__(self, kind, x, y, score=None):
         self.kind, self.x, self.y, self.score = kind, x, y, score
 
@@ -120,6 +126,8 @@ class Box(_Scalable):
 
 class Object(_Scalable):
     """One detected structure: a named anchor keypoint plus the parts grouped onto it."""
+
+    __slots__ = ("name", "anchor", "parts", "box")
 
     def __init__(self, name, anchor, parts=None, box=None):
         self.name, self.anchor, self.box = name, anchor, box

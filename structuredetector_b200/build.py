@@ -41,7 +41,34 @@ def is_stale() -> bool:
     return any(src.stat().st_mtime > built for src in SOURCES + HEADERS)
 
 
+FASTOBJ_SRC = ROOT / "csrc" / "fastobj.c"
+
+
+def fastobj_output() -> Path:
+    import sysconfig
+
+    return ROOT / ("_fastobj" + (sysconfig.get_config_var("EXT_SUFFIX") or ".so"))
+
+
+def build_fastobj(force: bool = False, verbose: bool = False) -> Path:
+    """The host-side object-assembly extension (CPython C API, plain gcc)."""
+    import sysconfig
+
+    out = fastobj_output()
+    if not force and out.exists() and out.stat().st_mtime >= FASTOBJ_SRC.stat().st_mtime:
+        return out
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        raise RuntimeError("gcc not found; cannot build the object-assembly extension")
+    cmd = [cc, "-O2", "-fPIC", "-shared", "-Wall", f"-I{sysconfig.get_paths()['include']}", "-o", str(out), str(FASTOBJ_SRC)]
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.run(cmd, check=True)
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> Path:
+    build_fastobj(force, verbose)
     if not force and not is_stale():
         return OUTPUT
     cmd = [nvcc_path(), *NVCC_FLAGS, f"-I{REPO / 'include'}", f"-I{ROOT / 'csrc'}", "-o", str(OUTPUT), *map(str, SOURCES)]

@@ -71,10 +71,10 @@ __device__ __forceinline__ float local_floor(const u32* hist, const int* minx, i
 }
 
 __device__ __forceinline__ int fine_bin(float x) {
-  int bin = __float2int_rd((x - kBinLo) * kFineScale);
-  bin = max(0, min(kFineBins - 1, bin));
-  if (bin > 0 && x < kBinLo + (float)bin * (1.0f / kFineScale)) --bin;  // rounding guard, as in logit_bin
-  return bin;
+  // x * 16 is exact (a power of two), so floor(x * 16) - 16 * kBinLo is THE bin: an element is never
+  // counted in a bin whose lower edge is above it.  Large |x| saturates in the conversion, then in the clamp.
+  static_assert(kBinLo == -16.0f && kFineScale == 16.0f, "bin arithmetic below");
+  return max(0, min(kFineBins - 1, __float2int_rd(fminf(fmaxf(x * kFineScale, -4096.0f), 4096.0f)) + 256));
 }
 
 // Highest fine bin b with (count in bins >= b) >= K; lane l owns bins 32l..32l+31.  -1 if none.
@@ -156,7 +156,7 @@ struct UnitState {
   int nbuf;       // records waiting in the shared-memory buffer
 };
 
-template <int DT = SDNET_DTYPE_F32>
+template <int DT = SDNET_DTYPE_F32, bool kFlushCountsFine = true>
 __device__ __forceinline__ void flush_candidates(UnitState& st, const u64* buf, u32* hist, int* minx,
                                                  const SharedFloors& sf, int* count_ptr, u64* __restrict__ list,
                                                  int cap, int K, int lane, bool pre, float xscale, float satx) {
@@ -185,8 +185,7 @@ __device__ __forceinline__ void flush_candidates(UnitState& st, const u64* buf, 
         const int bin = logit_bin(xe);
         atomicAdd(&hist[bin], 1u);
         atomicMin(&minx[bin], ord_of(xe));
-        const int fb = fine_bin(xe);
-        if (sf.ghist) atomicAdd(&sf.ghist[fb], 1u);
+        if (kFlushCountsFine && sf.ghist) atomicAdd(&sf.ghist[fine_bin(xe)], 1u);
       }
     }
   }

@@ -36,12 +36,11 @@ constexpr int kTileNG = SDNET_X_NG;   // ring slots (tiles) per warp: a group re
 #define SDNET_X_FLUSH_AT 16
 #endif
 constexpr int kFlushAt = SDNET_X_FLUSH_AT;  // buffered candidates that trigger a flush once the plane has a floor
-constexpr int kWork = 128;   // per-warp work list: one byte per (row of the group, lane) whose 16-byte word holds a pixel above the floor
 // S = rows per TMA row (see the kernel).  Under S = 2 a tile arrives as two 2-row boxes and a TMA
 // destination must be 128-byte aligned: the second box sits at +1152 and a slot takes 2304 bytes.
 __host__ __device__ constexpr int tile_slot_bytes(int S) { return S == 1 ? kTileBytes : 2304; }
 __host__ __device__ constexpr int tile_smem_per_warp(int S) {
-  return ((kTileNG * tile_slot_bytes(S) + 32 + kBins * 8 + kBuf * 8 + kWork) + 127) / 128 * 128;
+  return ((kTileNG * tile_slot_bytes(S) + 32 + kBins * 8 + kBuf * 8) + 127) / 128 * 128;
 }
 __host__ __device__ constexpr int tile_smem(int S) { return kTileWarps * tile_smem_per_warp(S); }
 constexpr int kOddBoxOff = 1152;  // S = 2: offset of the odd rows' box inside a slot
@@ -63,6 +62,30 @@ __device__ __forceinline__ void tma_tile_4d(u32 dst, const CUtensorMap* map, int
   asm volatile(
       "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
       ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(c), "r"(b), "r"(bar) : "memory");
+}
+// Arm a slot's mbarrier with the tile's byte count and pull the tile, both predicated on `pred` inside one
+// convergent instruction sequence (no branch around it: the operands stay warp-uniform for the compiler).
+__device__ __forceinline__ void tma_tile_4d_if(bool pred, u32 dst, const CUtensorMap* map, int x, int y, int c, int b, u32 bar,
+                                               u32 tx_bytes) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %8, 0;\n\t"
+      "@p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%6], %7;\n\t"
+      "@p cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];\n\t"
+      "}"
+      ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(c), "r"(b), "r"(bar), "r"(tx_bytes), "r"((int)pred) : "memory");
+}
+__device__ __forceinline__ void tma_tile_4d_x2_if(bool pred, u32 dst0, u32 dst1, const CUtensorMap* map, int x0, int x1, int y, int c,
+                                                  int b, u32 bar, u32 tx_bytes) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %10, 0;\n\t"
+      "@p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%8], %9;\n\t"
+      "@p cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%2, {%3, %5, %6, %7}], [%8];\n\t"
+      "@p cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%1], [%2, {%4, %5, %6, %7}], [%8];\n\t"
+      "}"
+      ::"r"(dst0), "r"(dst1), "l"(map), "r"(x0), "r"(x1), "r"(y), "r"(c), "r"(b), "r"(bar), "r"(tx_bytes), "r"((int)pred)
+      : "memory");
 }
 __device__ __forceinline__ uint4 lds64x2(u32 addr) {  // 16 bytes from an 8-byte-aligned address
   uint4 v;
@@ -159,39 +182,55 @@ __device__ __forceinline__ u32 ring_row_off(u32 rr) {
   return (rr >> 2) * tile_slot_bytes(2) + (rr & 1u) * (kOddBoxOff + kOddShiftB) + ((rr >> 1) & 1u) * kTilePitchB;
 }
 
-// Settle the work list of one 4-row group.  Entry e = (row in group << 5) | lane names one 16-byte
-// word of centre pixels holding at least one pixel above the floor; kPx consecutive lanes take the
-// pixels of an entry, so records leave in (row, column) = index order.  A lane whose pixel beats the
-// floor reads the pixel's (2R+1)^2 window from the ring with scalar loads (columns and rows outside
-// the image hold NaN or -inf and never win a max), classifies it like classify_row and appends a
-// (logit, index) record to the warp's candidate buffer.
-// `row0` = ring row of the window's first row for group row 0 (the centre is R rows further).
+// Settle one 4-row group.  `hot` = the lanes whose block of centre pixels (4 rows x kPx columns, one 16-byte word
+// per row) holds at least one pixel above the floor.  Every pixel of a hot block gets a lane of its own: 16 lanes
+// per block for fp32 (two blocks per pass), 32 for fp16/bf16 (one block per pass).  A lane whose pixel beats the
+// floor reads the pixel's (2R+1)^2 window from the ring with scalar loads (columns and rows outside the image hold
+// NaN or -inf and never win a max), classifies it (x == window max: survivor; within the near-tie margin: exact
+// score compare), counts it in the plane-wide histogram right away -- so the other warps of the plane see it at
+// their next floor computation, not one flush later -- and appends a (logit, index) record to the warp's candidate
+// buffer.  Records leave in no particular order inside a group: every pixel of the group is tested against the same
+// floor snapshot, and the lists are unordered anyway.
+// `row0` = ring row of the window's first row for group row 0 (the centre is R rows further); `rows_here` = rows of
+// the group that belong to this unit (the rest are the next unit's).
+#ifndef SDNET_X_EARLYHIST
+#define SDNET_X_EARLYHIST 1
+#endif
 template <int R, int DT, int S>
-__device__ __forceinline__ void settle_entries(UnitState& st, const unsigned char* work, int nent, u32 ring_s, u32 row0,
-                                               u32 row_tab, float floorx, u32 idx0, int W, bool pre, u64* buf, u32* hist, int* minx,
-                                               const SharedFloors& sf, int* count_ptr, u64* __restrict__ list, int cap,
-                                               int K, int lane, float xscale, float satx) {
+__device__ __forceinline__ void settle_blocks(UnitState& st, u32 hot, int rows_here, u32 ring_s, u32 row0, u32 row_tab,
+                                              float floorx, u32 idx0, int W, bool pre, u64* buf, u32* hist, int* minx,
+                                              const SharedFloors& sf, int* count_ptr, u64* __restrict__ list, int cap,
+                                              int K, int lane, float xscale, float satx) {
   constexpr float kNearTie = Num<DT>::kNear, kHiZone = Num<DT>::kHi, kLoZone = Num<DT>::kLo, kNearTie2 = Num<DT>::kNear2,
                   kHiZone2 = Num<DT>::kHi2;
   constexpr u32 kRingRows = kTileNG * kGroupRows;
   constexpr int kPx = TileGeom<DT>::kPx, kEsz = TileGeom<DT>::kEsz;
-  const int nslots = kPx * nent;
-  for (int base = 0; base < nslots; base += 32) {  // warp-uniform
-    const int slot = base + lane;
-    const u32 e = slot < nslots ? work[slot / kPx] : 0u;
-    const u32 i = e >> 5, colp = kPx * (e & 31u) + (u32)(slot % kPx);
-    const u32 col_addr = ring_s + (kPx + colp - R) * kEsz;  // first column of the window
-    // byte offsets of the window's rows.  Plain rows: a multiply.  Row pairs: the slot layout makes that
-    // eight instructions per row, so lane k keeps the offset of ring row k (row_tab) and a shuffle looks it up
-    u32 roff[2 * R + 1];
+  constexpr int kBlk = kGroupRows * kPx;  // pixels of a block = lanes that settle it
+  const u32 sub = (u32)lane & (kBlk - 1);
+  const u32 i = sub / kPx, j = sub % kPx;  // this lane's pixel inside a block: group row, column
+  // byte offsets of the window's rows.  Plain rows: a multiply.  Row pairs: the slot layout makes that
+  // eight instructions per row, so lane k keeps the offset of ring row k (row_tab) and a shuffle looks it up
+  u32 roff[2 * R + 1];
 #pragma unroll
-    for (int d = 0; d <= 2 * R; ++d) {
-      u32 rr = row0 + i + d;  // < 2 * kRingRows
-      if (rr >= kRingRows) rr -= kRingRows;
-      roff[d] = S == 1 ? rr * kTilePitchB : __shfl_sync(0xffffffffu, row_tab, (int)rr);
+  for (int d = 0; d <= 2 * R; ++d) {
+    u32 rr = row0 + i + d;  // < 2 * kRingRows
+    if (rr >= kRingRows) rr -= kRingRows;
+    roff[d] = S == 1 ? rr * kTilePitchB : __shfl_sync(0xffffffffu, row_tab, (int)rr);
+  }
+  const bool row_ok = (int)i < rows_here;
+  while (hot) {  // warp-uniform
+    int hl = __ffs(hot) - 1;
+    hot &= hot - 1;
+    bool have = true;
+    if (kBlk == 16) {  // a second block for the upper half-warp
+      const int h1 = __ffs(hot) - 1;  // -1 when there is none
+      hot &= hot - 1;
+      if (lane >= 16) { hl = max(h1, 0); have = h1 >= 0; }
     }
+    const u32 colp = (u32)(kPx * hl) + j;
+    const u32 col_addr = ring_s + (kPx + colp - R) * kEsz;  // first column of the window
     const float x = TileMax<DT>::elem(col_addr + R * kEsz + roff[R]);
-    bool keep = slot < nslots && x > floorx;
+    bool keep = have && row_ok && x > floorx;
     if (keep && !pre) {
       // window max in the storage format (no conversions for fp16/bf16), one accumulator per window row
       u32 hr[2 * R + 1];
@@ -218,9 +257,14 @@ __device__ __forceinline__ void settle_entries(UnitState& st, const unsigned cha
     if (m) {  // warp-uniform
       if (st.nbuf + __popc(m) > kBuf) {
         __syncwarp();
-        flush_candidates<DT>(st, buf, hist, minx, sf, count_ptr, list, cap, K, lane, pre, xscale, satx);
+        flush_candidates<DT, !SDNET_X_EARLYHIST>(st, buf, hist, minx, sf, count_ptr, list, cap, K, lane, pre, xscale, satx);
       }
-      if (keep) buf[st.nbuf + __popc(m & ((1u << lane) - 1u))] = ((u64)__float_as_uint(x) << 32) | (idx0 + i * (u32)W + colp);
+      if (keep) {
+        buf[st.nbuf + __popc(m & ((1u << lane) - 1u))] = ((u64)__float_as_uint(x) << 32) | (idx0 + i * (u32)W + colp);
+#if SDNET_X_EARLYHIST
+        atomicAdd(&sf.ghist[fine_bin(fminf(fmaxf(x * xscale, -satx), satx))], 1u);
+#endif
+      }
       st.nbuf += __popc(m);
     }
   }
@@ -284,14 +328,12 @@ sdnet_peaks_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_cons
   u32* hist = reinterpret_cast<u32*>(wbase + NG * kSlotB + 32);
   int* minx = reinterpret_cast<int*>(hist + kBins);
   u64* buf = reinterpret_cast<u64*>(minx + kBins);
-  unsigned char* work = reinterpret_cast<unsigned char*>(buf + kBuf);
   const bool pre = p.pre_activated != 0;
   const float xscale = pre ? kPreScale : 1.0f;
   const float satx = pre ? CUDART_INF_F : kSatX;
   const int C = p.M + p.N;
   const int H = p.H, W = p.W;
   const u32 ring_own = ring_s + (u32)(16 + 16 * lane);  // this lane's word inside a ring row
-  const u32 lt = (1u << lane) - 1u;
   const u32 row_tab = ring_row_off<S>((u32)lane % kRingRows);  // lane k: byte offset of ring row k (see settle_entries)
 
   if (lane == 0) {
@@ -357,13 +399,12 @@ sdnet_peaks_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_cons
     __syncwarp();
 
     // tile k of the unit = image rows r_begin - R + 4k ..
-    auto issue = [&](u32 s, int y) {  // lane 0: pull the tile whose first image row is y into slot s
-      mbar_arrive_expect_tx(bars_s + 8 * s, kTileBytes);
+    auto issue = [&](bool pred, u32 s, int y) {  // the lanes with `pred` (one) pull the tile whose first image row is y into slot s
       if (S == 1) {
-        tma_tile_4d(ring_s + s * kSlotB, tmap, xc, y, csel, b, bars_s + 8 * s);
+        tma_tile_4d_if(pred, ring_s + s * kSlotB, tmap, xc, y, csel, b, bars_s + 8 * s, kTileBytes);
       } else {  // y is even (r_begin even, R = 2): rows y, y+2 then rows y+1, y+3
-        tma_tile_4d(ring_s + s * kSlotB, tmap, xc, y >> 1, csel, b, bars_s + 8 * s);
-        tma_tile_4d(ring_s + s * kSlotB + kOddBoxOff, tmap, xc + p.odd_x - kOddShiftB / 4, y >> 1, csel, b, bars_s + 8 * s);
+        tma_tile_4d_x2_if(pred, ring_s + s * kSlotB, ring_s + s * kSlotB + kOddBoxOff, tmap, xc, xc + p.odd_x - kOddShiftB / 4,
+                          y >> 1, csel, b, bars_s + 8 * s, kTileBytes);
       }
     };
     auto wait_tile = [&](u32 slot, u32 par) {
@@ -374,11 +415,11 @@ sdnet_peaks_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_cons
       }
     };
     int y_next = r_begin - R;  // first image row of the next tile to issue
-    if (lane == 0) {
-      const int first = min(NG, groups);
+    {
       u32 sl = cur_slot;
-      for (int k = 0; k < first; ++k) {
-        issue(sl, y_next + kGroupRows * k);
+#pragma unroll
+      for (int k = 0; k < NG; ++k) {
+        issue(lane == 0 && k < groups, sl, y_next + kGroupRows * k);
         if (++sl == (u32)NG) sl = 0;
       }
     }
@@ -415,39 +456,24 @@ sdnet_peaks_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_cons
         const u32 a012 = ring_own + (row0 + 1) * kTilePitchB, a3 = ring_own + nxt_slot * kGroupRows * kTilePitchB;
         c0 = lds128u(a012); c1 = lds128u(a012 + kTilePitchB); c2 = lds128u(a012 + 2 * kTilePitchB); c3 = lds128u(a3);
       }
-      if (__any_sync(0xffffffffu, TileMax<DT>::group(c0, c1, c2, c3) > st.floorx)) {
-        // Something in these four rows beats the floor.  Pixel-centric slow path: (1) every (row, lane)
-        // whose word of centre pixels holds one above the floor goes on the warp's work list, one
-        // ballot per row, row-major; (2) settle_entries gives each listed pixel a lane of its own.
-        // In the last, partial group of a strip the rows past its end belong to the next strip: they
-        // may raise this alarm for nothing but are never listed.
-        const float floorx = st.floorx;
-        const int rows_here = nrows - g * kGroupRows;
-        int nent = 0;
-#pragma unroll
-        for (int i = 0; i < kGroupRows; ++i) {
-          const uint4 ci = i == 0 ? c0 : (i == 1 ? c1 : (i == 2 ? c2 : c3));
-          const bool mine = TileMax<DT>::word(ci) > floorx && i < rows_here;
-          const u32 bm = __ballot_sync(0xffffffffu, mine);
-          if (mine) work[nent + __popc(bm & lt)] = (unsigned char)((i << 5) | lane);
-          nent += __popc(bm);
-        }
-        __syncwarp();
-        settle_entries<R, DT, S>(st, work, nent, ring_s, row0, row_tab, floorx, idx0, W, pre, buf, hist, minx, sf, count_ptr, list,
-                                 p.cap, K, lane, xscale, satx);
+      const u32 hot = __ballot_sync(0xffffffffu, TileMax<DT>::group(c0, c1, c2, c3) > st.floorx);
+      if (hot) {
+        // Something in these four rows beats the floor.  Pixel-centric slow path: every pixel of the blocks
+        // that hold such a pixel gets a lane of its own (settle_blocks).  In the last, partial group of a unit
+        // the rows past its end belong to the next unit: they may raise this alarm for nothing but are never recorded.
+        settle_blocks<R, DT, S>(st, hot, nrows - g * kGroupRows, ring_s, row0, row_tab, st.floorx, idx0, W, pre, buf, hist, minx,
+                                sf, count_ptr, list, p.cap, K, lane, xscale, satx);
         // while the plane has no floor yet, publish early and often; later only in batches
         if (st.nbuf >= kFlushAt || (st.nbuf > 0 && gfloor_seen <= 0)) {
           __syncwarp();
-          flush_candidates<DT>(st, buf, hist, minx, sf, count_ptr, list, p.cap, K, lane, pre, xscale, satx);
+          flush_candidates<DT, !SDNET_X_EARLYHIST>(st, buf, hist, minx, sf, count_ptr, list, p.cap, K, lane, pre, xscale, satx);
         }
       }
       // every lane's reads of the group's first tile are done (the votes above): refill its slot
       // with the tile NG ahead
       __syncwarp();
-      if (lane == 0 && g + NG < groups) {
-        if (edge) fence_proxy_async();  // the slot was patched with ordinary stores
-        issue(cur_slot, y_next);
-      }
+      if (edge) fence_proxy_async();  // the slot was patched with ordinary stores
+      issue(lane == 0 && g + NG < groups, cur_slot, y_next);
       y_next += kGroupRows;
       cur_slot = nxt_slot;
       cur_par = nxt_par;
@@ -455,7 +481,7 @@ sdnet_peaks_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_cons
     for (int k = groups_out; k < groups; ++k) step_pos(cur_slot, cur_par);  // the halo tile below the last group
     if (st.nbuf) {
       __syncwarp();
-      flush_candidates<DT>(st, buf, hist, minx, sf, count_ptr, list, p.cap, K, lane, pre, xscale, satx);
+      flush_candidates<DT, !SDNET_X_EARLYHIST>(st, buf, hist, minx, sf, count_ptr, list, p.cap, K, lane, pre, xscale, satx);
     }
     }  // segments of the unit
   }

@@ -424,6 +424,7 @@ int launch_decode(const SdnetDecodeParams* p, cudaStream_t stream, cudaEvent_t* 
   tp.out_counts = p->counts;
   tp.diag = p->diag;
   tp.exact_flags = reinterpret_cast<const int*>(base + ws.off_flags);
+  tp.ghist = pp.ghist;
   tp.n_dest = p->n_dest;
   for (int j = 0; j < SDNET_MAX_DEST; ++j) tp.dest_delta[j] = j < p->n_dest ? p->dest_delta[j] : 0;
   if (p->dtype == SDNET_DTYPE_F16) launch_pdl(sdnet_tail_kernel<SDNET_DTYPE_F16>, dim3((unsigned)p->B), dim3(2 * kTeamThreads), stream, tp);

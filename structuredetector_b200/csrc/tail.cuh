@@ -23,6 +23,7 @@ struct TailParams {
   int* out_counts;
   int* diag;
   const int* exact_flags;  // [planes] 1 if the exact select rewrote the list
+  const u32* ghist;        // [planes][kFineBins] logit histogram of the recorded candidates (peaks kernels)
   int n_dest;              // fused gather: every output is stored n_dest times, at ptr + dest_delta[j]
   long long dest_delta[SDNET_MAX_DEST];
 };
@@ -49,6 +50,8 @@ __device__ __forceinline__ u64 make_comp(u64 rec, int c_local) {
 // selects the anchors, team 1 the parts; each has its own sort buffer and syncs on its own named
 // barrier.  They meet once, before the grouping.
 constexpr int kTeamThreads = 256;
+constexpr float kNearField = 1e5f;   // see the grouping pass
+constexpr int kHistCollectMax = 512;  // a histogram cut-off that collects more than this falls back to the radix refinement
 
 struct Team {
   int tid;    // thread index inside the team
@@ -59,6 +62,30 @@ struct Team {
 };
 
 __device__ void bitonic_sort_desc(const Team& tm, u64* s, int n /* power of two */) {
+  if (n <= kTeamThreads) {
+    // one element per thread, in a register: partners less than a warp apart are exchanged by shuffle, only
+    // the j >= 32 steps (6 of the 36 at n = 256) go through shared memory and the team barrier
+    const int i = tm.tid;
+    u64 v = i < n ? s[i] : 0ull;
+    for (int k = 2; k <= n; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        u64 o;
+        if (j >= 32) {
+          if (i < n) s[i] = v;
+          tm.sync();
+          o = s[(i ^ j) & (n - 1)];
+          tm.sync();
+        } else {
+          o = __shfl_xor_sync(0xffffffffu, v, j);
+        }
+        const bool keep_max = ((i & k) == 0) == ((i & j) == 0);  // lower index of a descending pair, or upper of an ascending one
+        v = keep_max ? (v > o ? v : o) : (v < o ? v : o);
+      }
+    }
+    if (i < n) s[i] = v;
+    tm.sync();
+    return;
+  }
   for (int k = 2; k <= n; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
       for (int i = tm.tid; i < n; i += kTeamThreads) {
@@ -74,91 +101,140 @@ __device__ void bitonic_sort_desc(const Team& tm, u64* s, int n /* power of two 
   }
 }
 
+// Composite key of the lowest score a candidate counted in fine bin `bin` (or a higher one) can have.
+template <int DT>
+__device__ __forceinline__ u32 bin_floor_key(int bin, bool pre) {
+  if (bin <= 0) return 0u;  // bin 0 is open below
+  const float edge = kBinLo + (float)bin * (1.0f / kFineScale);
+  if (pre) {  // the histogram ran on kPreScale * value; keys are the order-preserving bits of the value
+    const u32 bits = __float_as_uint(edge / kPreScale);
+    return (bits & 0x80000000u) ? ~bits : (bits | 0x80000000u);
+  }
+  return __float_as_uint(Num<DT>::act(edge));  // the score is monotone in the logit (saturation included)
+}
+
 // Select the `want` largest composites of planes [c0, c0+nc) of image b into s_sel (sorted
 // descending).  Returns the number selected (< want only when fewer candidates exist).
+//
+// Cut-off: the peaks kernel left, per plane, a histogram of its recorded candidates over 1/16-logit bins.
+// Summed over the group's planes it names the highest bin B with >= want candidates in bins >= B: everything
+// whose score reaches the score of B's lower edge is collected (a superset of those bins, normally want plus
+// a few dozen) and sorted.  When that cannot be used -- a plane went through the exact select, which rewrites
+// its list, or the superset is too large (heavily tied scores) -- an 8-bit radix refinement over the
+// composites finds the cut-off instead.
+template <int DT>
 __device__ int select_group(const Team& tm, const TailParams& p, int b, int c0, int nc, int want, u64* s_sel,
                             u32* s_hist, int* s_misc) {
   const int C = p.M + p.N;
   const int tid = tm.tid;
+  const bool pre = p.pre_activated != 0;
   // total candidates
   if (tid == 0) {
-    int tot = 0;
-    for (int c = 0; c < nc; ++c) tot += min(p.counts[(size_t)b * C + c0 + c], p.cap);
+    int tot = 0, rewritten = 0;
+    for (int c = 0; c < nc; ++c) {
+      tot += min(p.counts[(size_t)b * C + c0 + c], p.cap);
+      rewritten |= p.exact_flags[(size_t)b * C + c0 + c];
+    }
     s_misc[0] = tot;
     s_misc[1] = 0;  // collected
+    s_misc[5] = rewritten;
   }
   tm.sync();
   const int total = s_misc[0];
   u64 prefix = 0;   // value of the top `bits` bits that boundary elements share
   int bits = 0;
-  // radix-refine until what is left (everything certainly selected + the boundary bucket) is a
-  // small sort: the bitonic network below costs O(n log^2 n) and dominated this kernel when it
-  // was handed the full 2048-element buffer
+  u32 floor_key = 0;  // histogram cut-off: collect every composite whose 32-bit key is >= floor_key
+  // what is collected (everything certainly selected + the boundary bucket) should be a small sort: the bitonic
+  // network costs O(n log^2 n)
   const int target = min(kSortN, max(want + 64, 128));
-  if (total > target) {
-    int need = want;      // how many still have to come from the boundary bucket
-    int certain = 0;      // elements strictly above the boundary bucket
-    for (int level = 0; level < 8; ++level) {
-      const int shift = 56 - 8 * level;
-      for (int i = tid; i < 256; i += kTeamThreads) s_hist[i] = 0;
-      tm.sync();
-      for (int c = 0; c < nc; ++c) {
-        const int n = min(p.counts[(size_t)b * C + c0 + c], p.cap);
-        const u64* list = p.lists + ((size_t)b * C + c0 + c) * p.cap;
-        for (int i = tid; i < n; i += kTeamThreads) {
-          const u64 v = make_comp(list[i], c);
-          if (bits == 0 || (v >> (64 - bits)) == prefix) atomicAdd(&s_hist[(u32)(v >> shift) & 0xffu], 1u);
-        }
+  bool by_hist = total > target && p.ghist != nullptr && s_misc[5] == 0;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    if (by_hist) {
+      for (int bin = tid; bin < kFineBins; bin += kTeamThreads) {
+        u32 sum = 0;
+        for (int c = 0; c < nc; ++c) sum += __ldcg(p.ghist + ((size_t)b * C + c0 + c) * kFineBins + bin);
+        s_hist[bin] = sum;
       }
       tm.sync();
       if (tid < 32) {
-        // lane l owns digits 8l..8l+7; suffix-scan from the top
-        u32 loc[8], sum = 0;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) { loc[q] = s_hist[8 * tid + q]; sum += loc[q]; }
-        u32 suf = sum;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          u32 t = __shfl_down_sync(0xffffffffu, suf, d);
-          if (tid + d < 32) suf += t;
-        }
-        const u32 mask = __ballot_sync(0xffffffffu, suf >= (u32)need);
-        const int L = 31 - __clz(mask);  // mask != 0 because the bucket holds >= need elements
-        if (tid == L) {
-          u32 above = suf - sum;
-          int dsel = 8 * L;
-          for (int q = 7; q >= 0; --q) {
-            if (above + loc[q] >= (u32)need) { dsel = 8 * L + q; break; }
-            above += loc[q];
+        const int fb = floor_bin_fine<true>(s_hist, tid, want);  // highest bin with >= want candidates at or above it; -1: none
+        if (tid == 0) s_misc[2] = fb;
+      }
+      tm.sync();
+      floor_key = s_misc[2] > 0 ? bin_floor_key<DT>(s_misc[2], pre) : 0u;
+      tm.sync();
+    } else if (total > target) {
+      int need = want;      // how many still have to come from the boundary bucket
+      int certain = 0;      // elements strictly above the boundary bucket
+      for (int level = 0; level < 8; ++level) {
+        const int shift = 56 - 8 * level;
+        for (int i = tid; i < 256; i += kTeamThreads) s_hist[i] = 0;
+        tm.sync();
+        for (int c = 0; c < nc; ++c) {
+          const int n = min(p.counts[(size_t)b * C + c0 + c], p.cap);
+          const u64* list = p.lists + ((size_t)b * C + c0 + c) * p.cap;
+          for (int i = tid; i < n; i += kTeamThreads) {
+            const u64 v = make_comp(list[i], c);
+            if (bits == 0 || (v >> (64 - bits)) == prefix) atomicAdd(&s_hist[(u32)(v >> shift) & 0xffu], 1u);
           }
-          s_misc[2] = dsel;
-          s_misc[3] = (int)above;                 // elements in this bucket with a larger digit
-          s_misc[4] = (int)s_hist[dsel];          // size of the new boundary bucket
+        }
+        tm.sync();
+        if (tid < 32) {
+          // lane l owns digits 8l..8l+7; suffix-scan from the top
+          u32 loc[8], sum = 0;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) { loc[q] = s_hist[8 * tid + q]; sum += loc[q]; }
+          u32 suf = sum;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            u32 t = __shfl_down_sync(0xffffffffu, suf, d);
+            if (tid + d < 32) suf += t;
+          }
+          const u32 mask = __ballot_sync(0xffffffffu, suf >= (u32)need);
+          const int L = 31 - __clz(mask);  // mask != 0 because the bucket holds >= need elements
+          if (tid == L) {
+            u32 above = suf - sum;
+            int dsel = 8 * L;
+            for (int q = 7; q >= 0; --q) {
+              if (above + loc[q] >= (u32)need) { dsel = 8 * L + q; break; }
+              above += loc[q];
+            }
+            s_misc[2] = dsel;
+            s_misc[3] = (int)above;                 // elements in this bucket with a larger digit
+            s_misc[4] = (int)s_hist[dsel];          // size of the new boundary bucket
+          }
+        }
+        tm.sync();
+        const int dsel = s_misc[2], above = s_misc[3], binc = s_misc[4];
+        certain += above;
+        need -= above;
+        prefix = (prefix << 8) | (u64)dsel;
+        bits += 8;
+        tm.sync();
+        if (certain + binc <= target) break;  // everything at or above the boundary bucket is a small sort
+      }
+    }
+    // collect: the composites at or above the cut-off
+    for (int c = 0; c < nc; ++c) {
+      const int n = min(p.counts[(size_t)b * C + c0 + c], p.cap);
+      const u64* list = p.lists + ((size_t)b * C + c0 + c) * p.cap;
+      for (int i = tid; i < n; i += kTeamThreads) {
+        const u64 v = make_comp(list[i], c);
+        if ((u32)(v >> 32) >= floor_key && (bits == 0 || (v >> (64 - bits)) >= prefix)) {
+          const int slot = atomicAdd(&s_misc[1], 1);
+          if (slot < kSortN) s_sel[slot] = v;
         }
       }
-      tm.sync();
-      const int dsel = s_misc[2], above = s_misc[3], binc = s_misc[4];
-      certain += above;
-      need -= above;
-      prefix = (prefix << 8) | (u64)dsel;
-      bits += 8;
-      tm.sync();
-      if (certain + binc <= target) break;  // everything at or above the boundary bucket is a small sort
     }
+    tm.sync();
+    if (!by_hist || s_misc[1] <= kHistCollectMax) break;
+    // the histogram's superset is too large to sort cheaply (heavily tied scores): refine by radix instead
+    tm.sync();
+    if (tid == 0) s_misc[1] = 0;
+    by_hist = false;
+    floor_key = 0;
+    tm.sync();
   }
-  // collect: all elements whose top `bits` bits are >= prefix
-  for (int c = 0; c < nc; ++c) {
-    const int n = min(p.counts[(size_t)b * C + c0 + c], p.cap);
-    const u64* list = p.lists + ((size_t)b * C + c0 + c) * p.cap;
-    for (int i = tid; i < n; i += kTeamThreads) {
-      const u64 v = make_comp(list[i], c);
-      if (bits == 0 || (v >> (64 - bits)) >= prefix) {
-        const int slot = atomicAdd(&s_misc[1], 1);
-        if (slot < kSortN) s_sel[slot] = v;
-      }
-    }
-  }
-  tm.sync();
   const int got = min(s_misc[1], kSortN);
   int n2 = 32;
   while (n2 < got) n2 <<= 1;
@@ -209,12 +285,13 @@ __device__ __forceinline__ float key_to_score(u32 key, bool pre) {
 }
 
 template <int DT>
-__global__ void __launch_bounds__(2 * kTeamThreads) sdnet_tail_kernel(const __grid_constant__ TailParams p) {
+__global__ void __launch_bounds__(2 * kTeamThreads, 3) sdnet_tail_kernel(const __grid_constant__ TailParams p) {
   __shared__ u64 s_sel[2][kSortN];
-  __shared__ u32 s_hist[2][256];
+  __shared__ __align__(16) u32 s_hist[2][kFineBins];
   __shared__ int s_misc[2][8];
   __shared__ float s_ax[SDNET_MAX_TOPK], s_ay[SDNET_MAX_TOPK];
   __shared__ int s_cnt[2];
+  __shared__ int s_far;  // a valid anchor or part origin lies outside +-kNearField: grouping must look at the masked slots too
   const int b = blockIdx.x;
   Team tm;
   tm.id = threadIdx.x / kTeamThreads;
@@ -222,6 +299,7 @@ __global__ void __launch_bounds__(2 * kTeamThreads) sdnet_tail_kernel(const __gr
   const int W = p.W;
   const bool pre = p.pre_activated != 0;
   if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
+  if (threadIdx.x == 2) s_far = 0;
   pdl_wait();  // candidate lists (peaks kernel, possibly rewritten by the exact select) are final
   __syncthreads();
   typedef typename Num<DT>::In In;
@@ -232,7 +310,7 @@ __global__ void __launch_bounds__(2 * kTeamThreads) sdnet_tail_kernel(const __gr
 
   if (tm.id == 0) {
     // ---- anchors
-    const int have = select_group(tm, p, b, 0, p.M, p.K, sel, s_hist[0], s_misc[0]);
+    const int have = select_group<DT>(tm, p, b, 0, p.M, p.K, sel, s_hist[0], s_misc[0]);
     if (have < p.K) zero_fill(tm, p, b, 0, have, p.K, sel, s_hist[0]);
     int n_valid = 0;
     for (int s = tm.tid; s < p.K; s += kTeamThreads) {
@@ -250,11 +328,12 @@ __global__ void __launch_bounds__(2 * kTeamThreads) sdnet_tail_kernel(const __gr
       s_ax[s] = valid ? x : kFar;
       s_ay[s] = valid ? y : kFar;
       n_valid += valid ? 1 : 0;
+      if (valid && !(fabsf(x) < kNearField && fabsf(y) < kNearField)) s_far = 1;
     }
     if (n_valid) atomicAdd(&s_cnt[0], n_valid);
   } else {
     // ---- parts
-    const int have = select_group(tm, p, b, p.M, p.N, p.P, sel, s_hist[1], s_misc[1]);
+    const int have = select_group<DT>(tm, p, b, p.M, p.N, p.P, sel, s_hist[1], s_misc[1]);
     if (have < p.P) zero_fill(tm, p, b, p.M, have, p.P, sel, s_hist[1]);
     const In* embx = p.embeddings.data ? static_cast<const In*>(p.embeddings.data) + (long long)b * p.embeddings.sb : nullptr;
     const In* emby = embx ? embx + p.embeddings.sc : nullptr;
@@ -282,6 +361,7 @@ __global__ void __launch_bounds__(2 * kTeamThreads) sdnet_tail_kernel(const __gr
       if (p.part_emb) store_out(p, reinterpret_cast<float2*>(p.part_emb) + (size_t)b * p.P + s, make_float2(ex, ey));
       const bool valid = score > p.conf;
       n_valid += valid ? 1 : 0;
+      if (valid && !(fabsf(ox) < kNearField && fabsf(oy) < kNearField)) s_far = 1;
       // masked parts sit at (-1e6, -1e6): decoders.py:80-81.  The slot's composite is no longer
       // needed: keep the part's origin there for the grouping pass.
       reinterpret_cast<float2*>(sel)[s] = make_float2(valid ? ox : -kFar, valid ? oy : -kFar);
@@ -297,31 +377,38 @@ __global__ void __launch_bounds__(2 * kTeamThreads) sdnet_tail_kernel(const __gr
   // the same root and the reference's min() then keeps the FIRST anchor.  Hence two sweeps without a
   // root in the loop: m2, then the first anchor whose square lies within 1e-6 of m2 (a root can only
   // tie if its square is within 2^-22 relative) AND whose root equals root(m2).
+  // Slots are in score order, so the valid anchors / parts are the first s_cnt[0] / s_cnt[1] slots.  Masked slots sit
+  // 1e6 away (decoders.py:80-86); as long as every valid coordinate is within kNearField = 1e5 and the gate is below
+  // 1e5, no pair with a masked member can pass the gate or tie with one that does, so only valid x valid pairs are
+  // searched (13 x 36 instead of 100 x 100 on the realistic maps).  Otherwise: the full P x K search.
   const float2* origin = reinterpret_cast<const float2*>(s_sel[1]);
+  const bool full = s_far != 0 || !(p.dist_abs < kNearField);
+  const int Ka = full ? p.K : s_cnt[0], Pp = full ? p.P : s_cnt[1];
   int g = 32;
-  while (g > 1 && p.P * g > (int)blockDim.x) g >>= 1;
+  while (g > 1 && Pp * g > (int)blockDim.x) g >>= 1;
   const int sub = threadIdx.x & (g - 1), per_pass = blockDim.x / g;
   for (int s0 = 0; s0 < p.P; s0 += per_pass) {  // block-uniform
     const int s = s0 + (int)threadIdx.x / g;
     const bool live = s < p.P;
     int slot = -1;
-    if (!p.no_grouping) {  // kernel-uniform
-      const float qx = live ? origin[s].x : 0.f, qy = live ? origin[s].y : 0.f;
+    if (!p.no_grouping && s0 < Pp) {  // block-uniform
+      const bool search = s < Pp;
+      const float qx = search ? origin[s].x : 0.f, qy = search ? origin[s].y : 0.f;
       float m2 = CUDART_INF_F;
-      for (int a = sub; a < p.K; a += g) {
+      for (int a = sub; a < Ka; a += g) {
         const float dx = __fsub_rn(qx, s_ax[a]), dy = __fsub_rn(qy, s_ay[a]);
         m2 = fminf(m2, __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
       }
       for (int w = g >> 1; w > 0; w >>= 1) m2 = fminf(m2, __shfl_xor_sync(0xffffffffu, m2, w));
       const float best = __fsqrt_rn(m2), near = m2 * 1.000001f;
       int arg = 0x7fffffff;
-      for (int a = sub; a < p.K; a += g) {
+      for (int a = sub; a < Ka; a += g) {
         const float dx = __fsub_rn(qx, s_ax[a]), dy = __fsub_rn(qy, s_ay[a]);
         const float sq = __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
         if (sq <= near && __fsqrt_rn(sq) == best) { arg = a; break; }
       }
       for (int w = g >> 1; w > 0; w >>= 1) arg = min(arg, __shfl_xor_sync(0xffffffffu, arg, w));
-      slot = (best < p.dist_abs) ? arg : -1;
+      slot = (search && best < p.dist_abs) ? arg : -1;
     }
     if (live && sub == 0) store_out(p, p.assign + (size_t)b * p.P + s, slot);
   }

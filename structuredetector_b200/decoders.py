@@ -18,6 +18,12 @@ import torch
 from . import ops
 from .annotations import ImageAnnotation, Keypoint, Object
 
+try:
+    from . import _fastobj  # C object assembly (csrc/fastobj.c), built by structuredetector_b200.build
+except ImportError as exc:  # no silent slow path: say how to get it
+    raise ImportError("structuredetector_b200._fastobj is missing: run `python -m structuredetector_b200.build` "
+                      "(gcc, CPython headers) to build the object-assembly extension") from exc
+
 __all__ = ["Decoder", "CoreMLDecoder", "KeypointDecoder", "RawDecoder"]
 
 
@@ -99,40 +105,15 @@ class Decoder(_DecoderBase):
 
     # reference: decoders.py:103-139
     def _assemble(self, host: ops.PackedDetections, conf_thresh, out_size, in_size):
-        """Python objects from the packed rows.  All arithmetic is done once per batch in numpy float64
-        (the reference multiplies ``.item()`` doubles by ``in/out``; float64 numpy products are the same
-        IEEE operations), the per-object Python work is one constructor call."""
+        """Python objects from the packed rows, built by the C loop in ``csrc/fastobj.c``: float32 coordinates
+        widened to double and multiplied by ``in/out`` in double (the reference multiplies ``.item()`` doubles),
+        ``score > conf`` in double, parts bucketed by anchor slot in part-slot order."""
         sx, sy = in_size[0] / out_size[0], in_size[1] / out_size[1]
-        a = host.anchor_out.numpy().astype(np.float64)
-        p = host.part_out.numpy()[:, :, :4].astype(np.float64)
-        assign = host.assign.numpy()
-        anchor_name = self.anchor_name
-        labels, kinds = self._names(self.label_map), self._names(self.part_map)
-        ax, ay, a_score = (a[:, :, 0] * sx).tolist(), (a[:, :, 1] * sy).tolist(), a[:, :, 2].tolist()
-        a_cls = a[:, :, 3].astype(np.int64).tolist()
-        px, py, p_score = (p[:, :, 0] * sx).tolist(), (p[:, :, 1] * sy).tolist(), p[:, :, 2].tolist()
-        p_cls = p[:, :, 3].astype(np.int64).tolist()
-        keep = (a[:, :, 2] > conf_thresh)  # double compare, like .item() in the reference
-        annotations = []
-        for b in range(a.shape[0]):
-            # parts of each anchor slot, in part-slot (score) order
-            slots = assign[b]
-            grouped = np.flatnonzero(slots >= 0)
-            buckets = {}
-            if grouped.size:
-                kx, ky, ks, kc = px[b], py[b], p_score[b], p_cls[b]
-                for i, slot in zip(grouped.tolist(), slots[grouped].tolist()):
-                    kp = Keypoint(kinds[kc[i]], kx[i], ky[i], ks[i])
-                    if slot in buckets:
-                        buckets[slot].append(kp)
-                    else:
-                        buckets[slot] = [kp]
-            xs, ys, ss, cs = ax[b], ay[b], a_score[b], a_cls[b]
-            get = buckets.get
-            objects = [Object(labels[cs[i]], Keypoint(anchor_name, xs[i], ys[i], ss[i]), get(i))
-                       for i in np.flatnonzero(keep[b]).tolist()]
-            annotations.append(ImageAnnotation(f"batch_{b}", objects))
-        return annotations
+        a, p, assign = host.anchor_out, host.part_out, host.assign
+        B, K = a.shape[:2]
+        return _fastobj.assemble(a.contiguous().numpy(), p.contiguous().numpy(), assign.contiguous().numpy(), B, K,
+                                 p.shape[1], float(conf_thresh), sx, sy, self._names(self.label_map),
+                                 self._names(self.part_map), self.anchor_name, Keypoint, Object, ImageAnnotation)
 
     @staticmethod
     def _names(mapping):
@@ -147,16 +128,9 @@ class Decoder(_DecoderBase):
     # reference: decoders.py:142-159
     def _raw_parts(self, host: ops.PackedDetections, conf_thresh, out_size, in_size):
         sx, sy = in_size[0] / out_size[0], in_size[1] / out_size[1]
-        p = host.part_out.numpy()[:, :, :4].astype(np.float64)
-        kinds = self._names(self.part_map)
-        px, py, ps = (p[:, :, 0] * sx).tolist(), (p[:, :, 1] * sy).tolist(), p[:, :, 2].tolist()
-        pc = p[:, :, 3].astype(np.int64).tolist()
-        keep = ~(p[:, :, 2] < conf_thresh)
-        result = []
-        for b in range(p.shape[0]):
-            xs, ys, ss, cs = px[b], py[b], ps[b], pc[b]
-            result.append([Keypoint(kinds[cs[i]], xs[i], ys[i], ss[i]) for i in np.flatnonzero(keep[b]).tolist()])
-        return result
+        p = host.part_out
+        return _fastobj.keypoints(p.contiguous().numpy(), p.shape[0], p.shape[1], p.shape[2], float(conf_thresh), sx, sy,
+                                  self._names(self.part_map), Keypoint)
 
 
 class CoreMLDecoder(Decoder):

@@ -8,6 +8,14 @@ if str(ROOT) not in sys.path:
     sys.path.insert(0, str(ROOT))
 
 
+def pytest_sessionstart(session):
+    """The host-side C extension is a build artefact (git-ignored): make sure it exists before the
+    package is imported.  gcc only, a no-op when it is up to date."""
+    from structuredetector_b200 import build
+
+    build.build_fastobj()
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 

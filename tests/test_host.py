@@ -7,6 +7,7 @@ import json
 import re
 from pathlib import Path
 
+import numpy as np
 import pytest
 import torch
 
@@ -123,3 +124,57 @@ def test_annotation_types_follow_the_reference_api(tmp_path):
     assert again.objects[0].parts[0].score == 0.9 and again.img_size == [100, 100]
     assert json.loads((tmp_path / "batch_0.json").read_text())["objects"][0]["label"] == "bean"
     assert "Keypoint(kind: leaf" in repr(kp) and ImageAnnotation("x").is_empty
+
+
+def _random_packed(rng, B, K, P, M, N, conf):
+    """Packed rows the way the tail kernel leaves them: scores sorted descending, some exactly at float32(conf)
+    (emitted by the double compare only when float32(conf) > conf), parts pointing at any slot or -1."""
+    blob = torch.zeros(ops.packed_nbytes(B, K, P, M + N), dtype=torch.uint8)
+    host = ops._carve(blob, B, K, P, M + N)
+    a, p = host.anchor_out.numpy(), host.part_out.numpy()
+    a[..., 0], a[..., 1] = rng.uniform(0, 600, (B, K)), rng.uniform(0, 500, (B, K))
+    a[..., 2] = -np.sort(-rng.uniform(0.2, 1.0, (B, K)).astype(np.float32), axis=1)
+    a[:, K // 2, 2] = np.float32(conf)
+    a[..., 3] = rng.integers(0, M, (B, K))
+    p[..., 0], p[..., 1] = rng.uniform(0, 600, (B, P)), rng.uniform(0, 500, (B, P))
+    p[..., 2] = -np.sort(-rng.uniform(0.2, 1.0, (B, P)).astype(np.float32), axis=1)
+    p[:, P // 3, 2] = np.float32(conf)
+    p[..., 3] = rng.integers(0, N, (B, P))
+    host.assign.numpy()[:] = rng.integers(-1, K, (B, P))
+    return host
+
+
+@pytest.mark.parametrize("conf", [0.4, 0.5, 0.25])
+def test_c_object_assembly_matches_the_oracle(conf):
+    """csrc/fastobj.c (what Decoder._assemble / _raw_parts run) against the numpy restatement of
+    decoders.py:103-159: same objects, same order, same doubles -- including parts grouped onto an anchor
+    that the double compare does not emit and the >= / > asymmetry between raw parts and objects."""
+    from types import SimpleNamespace
+
+    from oracle import sdnet_oracle as O
+    from structuredetector_b200 import Decoder
+
+    rng = np.random.default_rng(7)
+    B, K, P, M, N = 5, 23, 31, 3, 2
+    host = _random_packed(rng, B, K, P, M, N, conf)
+    labels, kinds = {i: f"label{i}" for i in range(M)}, {i: f"part{i}" for i in range(N)}
+    dec = Decoder(SimpleNamespace(_r_labels=labels, _r_parts=kinds, anchor_name="stem", down_ratio=4.0, max_objects=K,
+                                  max_parts=P, conf_threshold=conf, decoder_dist_thresh=0.1))
+    out_size, in_size = (612, 512), (2448, 2051)  # unequal, inexact ratios
+    packed = {"anchor_out": host.anchor_out.numpy(), "part_out": host.part_out.numpy(), "assign": host.assign.numpy()}
+    anns = dec._assemble(host, conf, out_size, in_size)
+    want = O.assemble(packed, labels, kinds, "stem", conf, out_size, in_size)
+    got = [[(o.name, (o.anchor.kind, o.anchor.x, o.anchor.y, o.anchor.score), [(k.kind, k.x, k.y, k.score) for k in o.parts])
+            for o in ann.objects] for ann in anns]
+    assert got == want
+    assert [str(a.image_path) for a in anns] == [f"batch_{b}" for b in range(B)]
+    assert all(o.box is None and isinstance(o.parts, list) for a in anns for o in a.objects)
+    raw = dec._raw_parts(host, conf, out_size, in_size)
+    assert [[(k.kind, k.x, k.y, k.score) for k in img] for img in raw] == O.raw_parts(packed, kinds, conf, out_size, in_size)
+    # the instances behave like the reference's: mutable, deep-copyable, resizable
+    first = anns[0].objects[0]
+    x0 = first.anchor.x
+    clone = anns[0].resized((2, 2), (1, 1))
+    assert clone.objects[0].anchor.x == x0 / 2 and first.anchor.x == x0
+    first.parts.append(Keypoint("part0", 1.0, 2.0, 0.5))
+    assert first.nb_parts >= 1

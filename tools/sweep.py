@@ -42,10 +42,30 @@ def main():
     M, N, H, W, K, P = cfg.labels, cfg.parts, cfg.height, cfg.width, cfg.max_objects, cfg.max_parts
     conf = float(torch.tensor(cfg.conf_threshold, dtype=tdtype))
     dist = float(torch.tensor(cfg.dist_thresh * min(W, H), dtype=torch.float32))
+    import os
+    import shutil
+    import tempfile
+
     libs = {}
-    for name in args.names:
+    tmpdir = tempfile.mkdtemp()
+    for spec in args.names:  # name[@ENV=VAL[,ENV=VAL...]]: the library's read-once tuning knobs come from the environment
+        name, _, envs = spec.partition("@")
         path = _native.LIB_PATH if name == "base" else ROOT / "structuredetector_b200" / "csrc" / "exp" / f"lib_{name}.so"
-        libs[name] = _native.load_from(path)
+        env = dict(kv.split("=") for kv in envs.split(",")) if envs else {}
+        if env:  # a private copy, so that dlopen gives this spec its own statics
+            copy = Path(tmpdir) / f"lib_{spec.replace('@', '_').replace('=', '_').replace(',', '_')}.so"
+            shutil.copy(path, copy)
+            path = copy
+        os.environ.update(env)
+        lib = _native.load_from(path)
+        # one tiny decode now: the knobs are read at the library's first launch
+        tiny = torch.zeros(1, 7, 32, 32, device=dev)
+        to = split_outputs(tiny, 2, 1)
+        ops.DecodePlan(dev, 1, 2, 1, 32, 32, 10, 10, lib=lib).run(to["anchor_hm"], to["part_hm"], to["offsets"], to["embeddings"], 0.4, 3.2)
+        torch.cuda.synchronize()
+        for k in env:
+            del os.environ[k]
+        libs[spec] = lib
     results = []
     for mode in args.modes.split(","):
         uniq = make_raw(cfg, mode, batch=32).to(dev)
@@ -89,7 +109,7 @@ def main():
                 except Exception as exc:  # noqa: BLE001
                     r["sched"] = repr(exc)
                 results.append(r)
-                print(f"{name:14s} {mode:6s} {images:5d}  peaks {pm:.4f} (min {pmin:.4f}) frac {r['frac']:.3f}  tail {r['tail_ms']:.4f}  "
+                print(f"{name:32s} {mode:6s} {images:5d}  peaks {pm:.4f} (min {pmin:.4f}) frac {r['frac']:.3f}  tail {r['tail_ms']:.4f}  "
                       f"serial {serial_ms:.4f}  cand {r['cand_per_plane']:.0f}  same {same}", flush=True)
                 del plan
     Path(args.out).parent.mkdir(exist_ok=True)
