@@ -24,23 +24,24 @@ constexpr int kTilePitchB = kTileCols * 4;                   // 544 B per ring r
 constexpr int kTileBytes = kGroupRows * kTilePitchB;         // 2176 B per TMA tile (17 x 128 B)
 constexpr int kTileWarps = 4;
 #ifndef SDNET_X_CTAS
-#define SDNET_X_CTAS 5
+#define SDNET_X_CTAS 6
 #endif
 constexpr int kTileMinCtas = SDNET_X_CTAS;  // resident CTAs per SM the register allocation aims for
 constexpr int kMinChunkGroups = 8;  // shortest tier-2 unit (32 rows)
 #ifndef SDNET_X_NG
-#define SDNET_X_NG 4
+#define SDNET_X_NG 3
 #endif
 constexpr int kTileNG = SDNET_X_NG;   // ring slots (tiles) per warp: a group reads two of them, the others are in flight
 #ifndef SDNET_X_FLUSH_AT
 #define SDNET_X_FLUSH_AT 16
 #endif
+constexpr int kWork = 128;   // per-warp work list: one byte per (row of the group, lane) whose 16-byte word holds a pixel above the floor
 constexpr int kFlushAt = SDNET_X_FLUSH_AT;  // buffered candidates that trigger a flush once the plane has a floor
 // S = rows per TMA row (see the kernel).  Under S = 2 a tile arrives as two 2-row boxes and a TMA
 // destination must be 128-byte aligned: the second box sits at +1152 and a slot takes 2304 bytes.
 __host__ __device__ constexpr int tile_slot_bytes(int S) { return S == 1 ? kTileBytes : 2304; }
 __host__ __device__ constexpr int tile_smem_per_warp(int S) {
-  return ((kTileNG * tile_slot_bytes(S) + 32 + kBins * 8 + kBuf * 8) + 127) / 128 * 128;
+  return ((kTileNG * tile_slot_bytes(S) + 32 + kBins * 8 + kBuf * 8 + kWork) + 127) / 128 * 128;
 }
 __host__ __device__ constexpr int tile_smem(int S) { return kTileWarps * tile_smem_per_warp(S); }
 constexpr int kOddBoxOff = 1152;  // S = 2: offset of the odd rows' box inside a slot
@@ -62,30 +63,6 @@ __device__ __forceinline__ void tma_tile_4d(u32 dst, const CUtensorMap* map, int
   asm volatile(
       "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
       ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(c), "r"(b), "r"(bar) : "memory");
-}
-// Arm a slot's mbarrier with the tile's byte count and pull the tile, both predicated on `pred` inside one
-// convergent instruction sequence (no branch around it: the operands stay warp-uniform for the compiler).
-__device__ __forceinline__ void tma_tile_4d_if(bool pred, u32 dst, const CUtensorMap* map, int x, int y, int c, int b, u32 bar,
-                                               u32 tx_bytes) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %8, 0;\n\t"
-      "@p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%6], %7;\n\t"
-      "@p cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];\n\t"
-      "}"
-      ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(c), "r"(b), "r"(bar), "r"(tx_bytes), "r"((int)pred) : "memory");
-}
-__device__ __forceinline__ void tma_tile_4d_x2_if(bool pred, u32 dst0, u32 dst1, const CUtensorMap* map, int x0, int x1, int y, int c,
-                                                  int b, u32 bar, u32 tx_bytes) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %10, 0;\n\t"
-      "@p mbarrier.arrive.expect_tx.shared::cta.b64 _, [%8], %9;\n\t"
-      "@p cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%2, {%3, %5, %6, %7}], [%8];\n\t"
-      "@p cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%1], [%2, {%4, %5, %6, %7}], [%8];\n\t"
-      "}"
-      ::"r"(dst0), "r"(dst1), "l"(map), "r"(x0), "r"(x1), "r"(y), "r"(c), "r"(b), "r"(bar), "r"(tx_bytes), "r"((int)pred)
-      : "memory");
 }
 __device__ __forceinline__ uint4 lds64x2(u32 addr) {  // 16 bytes from an 8-byte-aligned address
   uint4 v;
@@ -182,55 +159,57 @@ __device__ __forceinline__ u32 ring_row_off(u32 rr) {
   return (rr >> 2) * tile_slot_bytes(2) + (rr & 1u) * (kOddBoxOff + kOddShiftB) + ((rr >> 1) & 1u) * kTilePitchB;
 }
 
-// Settle one 4-row group.  `hot` = the lanes whose block of centre pixels (4 rows x kPx columns, one 16-byte word
-// per row) holds at least one pixel above the floor.  Every pixel of a hot block gets a lane of its own: 16 lanes
-// per block for fp32 (two blocks per pass), 32 for fp16/bf16 (one block per pass).  A lane whose pixel beats the
-// floor reads the pixel's (2R+1)^2 window from the ring with scalar loads (columns and rows outside the image hold
-// NaN or -inf and never win a max), classifies it (x == window max: survivor; within the near-tie margin: exact
-// score compare), counts it in the plane-wide histogram right away -- so the other warps of the plane see it at
-// their next floor computation, not one flush later -- and appends a (logit, index) record to the warp's candidate
-// buffer.  Records leave in no particular order inside a group: every pixel of the group is tested against the same
-// floor snapshot, and the lists are unordered anyway.
-// `row0` = ring row of the window's first row for group row 0 (the centre is R rows further); `rows_here` = rows of
-// the group that belong to this unit (the rest are the next unit's).
-#ifndef SDNET_X_EARLYHIST
-#define SDNET_X_EARLYHIST 1
+#ifndef SDNET_X_QUICK
+#define SDNET_X_QUICK 1  // settle_entries: reject flank pixels on their four direct neighbours before the full window
 #endif
+#ifndef SDNET_X_EARLYHIST
+#define SDNET_X_EARLYHIST 1  // count a candidate in the plane-wide histogram when it is found, not when it is flushed
+#endif
+// Settle the work list of one 4-row group.  Entry e = (row in group << 5) | lane names one 16-byte
+// word of centre pixels holding at least one pixel above the floor; kPx consecutive lanes take the
+// pixels of an entry, so records leave in (row, column) = index order.  A lane whose pixel beats the
+// floor reads the pixel's (2R+1)^2 window from the ring with scalar loads (columns and rows outside
+// the image hold NaN or -inf and never win a max), classifies it like classify_row and appends a
+// (logit, index) record to the warp's candidate buffer.
+// `row0` = ring row of the window's first row for group row 0 (the centre is R rows further).
 template <int R, int DT, int S>
-__device__ __forceinline__ void settle_blocks(UnitState& st, u32 hot, int rows_here, u32 ring_s, u32 row0, u32 row_tab,
-                                              float floorx, u32 idx0, int W, bool pre, u64* buf, u32* hist, int* minx,
-                                              const SharedFloors& sf, int* count_ptr, u64* __restrict__ list, int cap,
-                                              int K, int lane, float xscale, float satx) {
+__device__ __forceinline__ void settle_entries(UnitState& st, const unsigned char* work, int nent, u32 ring_s, u32 row0,
+                                               u32 row_tab, float floorx, u32 idx0, int W, bool pre, u64* buf, u32* hist, int* minx,
+                                               const SharedFloors& sf, int* count_ptr, u64* __restrict__ list, int cap,
+                                               int K, int lane, float xscale, float satx) {
   constexpr float kNearTie = Num<DT>::kNear, kHiZone = Num<DT>::kHi, kLoZone = Num<DT>::kLo, kNearTie2 = Num<DT>::kNear2,
                   kHiZone2 = Num<DT>::kHi2;
   constexpr u32 kRingRows = kTileNG * kGroupRows;
   constexpr int kPx = TileGeom<DT>::kPx, kEsz = TileGeom<DT>::kEsz;
-  constexpr int kBlk = kGroupRows * kPx;  // pixels of a block = lanes that settle it
-  const u32 sub = (u32)lane & (kBlk - 1);
-  const u32 i = sub / kPx, j = sub % kPx;  // this lane's pixel inside a block: group row, column
-  // byte offsets of the window's rows.  Plain rows: a multiply.  Row pairs: the slot layout makes that
-  // eight instructions per row, so lane k keeps the offset of ring row k (row_tab) and a shuffle looks it up
-  u32 roff[2 * R + 1];
-#pragma unroll
-  for (int d = 0; d <= 2 * R; ++d) {
-    u32 rr = row0 + i + d;  // < 2 * kRingRows
-    if (rr >= kRingRows) rr -= kRingRows;
-    roff[d] = S == 1 ? rr * kTilePitchB : __shfl_sync(0xffffffffu, row_tab, (int)rr);
-  }
-  const bool row_ok = (int)i < rows_here;
-  while (hot) {  // warp-uniform
-    int hl = __ffs(hot) - 1;
-    hot &= hot - 1;
-    bool have = true;
-    if (kBlk == 16) {  // a second block for the upper half-warp
-      const int h1 = __ffs(hot) - 1;  // -1 when there is none
-      hot &= hot - 1;
-      if (lane >= 16) { hl = max(h1, 0); have = h1 >= 0; }
-    }
-    const u32 colp = (u32)(kPx * hl) + j;
+  const int nslots = kPx * nent;
+  for (int base = 0; base < nslots; base += 32) {  // warp-uniform
+    const int slot = base + lane;
+    const u32 e = slot < nslots ? work[slot / kPx] : 0u;
+    const u32 i = e >> 5, colp = kPx * (e & 31u) + (u32)(slot % kPx);
     const u32 col_addr = ring_s + (kPx + colp - R) * kEsz;  // first column of the window
+    // byte offsets of the window's rows.  Plain rows: a multiply.  Row pairs: the slot layout makes that
+    // eight instructions per row, so lane k keeps the offset of ring row k (row_tab) and a shuffle looks it up
+    u32 roff[2 * R + 1];
+#pragma unroll
+    for (int d = 0; d <= 2 * R; ++d) {
+      u32 rr = row0 + i + d;  // < 2 * kRingRows
+      if (rr >= kRingRows) rr -= kRingRows;
+      roff[d] = S == 1 ? rr * kTilePitchB : __shfl_sync(0xffffffffu, row_tab, (int)rr);
+    }
     const float x = TileMax<DT>::elem(col_addr + R * kEsz + roff[R]);
-    bool keep = have && row_ok && x > floorx;
+    bool keep = slot < nslots && x > floorx;
+#if SDNET_X_QUICK
+    if (!pre) {
+      // Most pixels above the floor are not peaks but the flanks of one (a blob holds ~200 of them): four loads
+      // settle those.  With m4 = the largest of the four direct neighbours (<= the window maximum h), x cannot
+      // share h's score when x < m4 - kNear2, x <= kHi2 - 1 and x >= kLo (the four near-tie zones all need the
+      // opposite); NaN neighbours (outside the image) are ignored by fmaxf.
+      const u32 ctr = col_addr + R * kEsz;
+      const float m4 = fmaxf(fmaxf(TileMax<DT>::elem(ctr + roff[R - 1]), TileMax<DT>::elem(ctr + roff[R + 1])),
+                             fmaxf(TileMax<DT>::elem(ctr - kEsz + roff[R]), TileMax<DT>::elem(ctr + kEsz + roff[R])));
+      if (x < m4 - kNearTie2 && x <= kHiZone2 - 1.0f && x >= kLoZone) keep = false;
+    }
+#endif
     if (keep && !pre) {
       // window max in the storage format (no conversions for fp16/bf16), one accumulator per window row
       u32 hr[2 * R + 1];
@@ -262,12 +241,132 @@ __device__ __forceinline__ void settle_blocks(UnitState& st, u32 hot, int rows_h
       if (keep) {
         buf[st.nbuf + __popc(m & ((1u << lane) - 1u))] = ((u64)__float_as_uint(x) << 32) | (idx0 + i * (u32)W + colp);
 #if SDNET_X_EARLYHIST
-        atomicAdd(&sf.ghist[fine_bin(fminf(fmaxf(x * xscale, -satx), satx))], 1u);
+        atomicAdd(&sf.ghist[fine_bin(fminf(fmaxf(x * xscale, -satx), satx))], 1u);  // the plane's other warps see it at once
 #endif
       }
       st.nbuf += __popc(m);
     }
   }
+}
+
+// Dense settle of one 4-row group (fp32, plain rows): when many blocks are hot -- the first groups of a unit, before
+// the plane has a floor worth the name -- giving every pixel a lane of its own costs a pass of ~100 instructions per
+// two blocks.  Here the whole (2R+1)^2 maximum filter of the group is formed once in registers instead: each lane
+// loads its word of the 4 + 2R window rows (lanes 0 / 31 also the panel's halo words), takes the vertical maxima of
+// its four columns for each of the four centre rows (one row at a time: few registers), fetches the two neighbouring columns either side from the
+// adjacent lanes by shuffle, and classifies its 16 pixels exactly like the pixel-centric path.  ~300 instructions for
+// the group, whatever the number of hot pixels.  Returns false (nothing recorded) when the group holds more
+// survivors than the candidate buffer: the caller then takes the pixel-centric path, which flushes as it goes.
+#ifndef SDNET_X_DENSE
+#define SDNET_X_DENSE 16
+#endif
+constexpr int kDenseLanes = SDNET_X_DENSE;  // hot lanes from which the dense path is taken (0 = never)
+
+
+// The dense maximum filter of one 4-row group (fp32, plain rows): bit 4 i + c of the result says that pixel
+// (group row i, column c of this lane's word) is above `floorx` and survives the reference's NMS.
+template <int R>
+__device__ __forceinline__ u32 dense_keep_mask_f32(int rows_here, u32 ring_s, u32 ring_own, u32 row0, float floorx, bool pre, int lane) {
+  constexpr int DT = SDNET_DTYPE_F32;
+  constexpr float kNearTie = Num<DT>::kNear, kHiZone = Num<DT>::kHi, kLoZone = Num<DT>::kLo;
+  constexpr u32 kRingRows = kTileNG * kGroupRows;
+  // own word and, for the panel's edge lanes, the halo word next to it (the other lanes read word 0 for nothing)
+  const u32 halo_a = ring_s + (lane == 31 ? 33u * 16u : 0u);
+  u32 km = 0;  // bit 4 i + c: pixel (group row i, column c of this lane's word) is a candidate
+#pragma unroll
+  for (int i = 0; i < kGroupRows; ++i) {
+    if (i < rows_here) {  // warp-uniform
+      // vertical maxima over the window rows of centre row i, re-read from the ring row by row: shared-memory loads are
+      // cheap, registers are what limits the kernel's occupancy (fmaxf ignores the NaN of out-of-image rows)
+      float4 v, xc;
+      float2 ev;
+#pragma unroll
+      for (int d = 0; d <= 2 * R; ++d) {
+        u32 rr = row0 + i + d;
+        if (rr >= kRingRows) rr -= kRingRows;
+        const float4 a = lds128(ring_own + rr * kTilePitchB);
+        const float4 w = lds128(halo_a + rr * kTilePitchB);
+        const float2 e = lane == 31 ? make_float2(w.x, w.y) : make_float2(w.z, w.w);
+        if (d == 0) {
+          v = a;
+          ev = e;
+        } else {
+          v.x = fmaxf(v.x, a.x); v.y = fmaxf(v.y, a.y); v.z = fmaxf(v.z, a.z); v.w = fmaxf(v.w, a.w);
+          ev.x = fmaxf(ev.x, e.x); ev.y = fmaxf(ev.y, e.y);
+        }
+        if (d == R) xc = a;
+      }
+      // the two columns either side, from the neighbouring lanes (panel edges: from the halo words)
+      float l2 = __shfl_up_sync(0xffffffffu, v.z, 1), l3 = __shfl_up_sync(0xffffffffu, v.w, 1);
+      float r0 = __shfl_down_sync(0xffffffffu, v.x, 1), r1 = __shfl_down_sync(0xffffffffu, v.y, 1);
+      if (lane == 0) { l2 = ev.x; l3 = ev.y; }
+      if (lane == 31) { r0 = ev.x; r1 = ev.y; }
+      float4 h;
+      if (R == 2) {
+        h.x = max3(max3(l2, l3, v.x), v.y, v.z);
+        h.y = max3(max3(l3, v.x, v.y), v.z, v.w);
+        h.z = max3(max3(v.x, v.y, v.z), v.w, r0);
+        h.w = max3(max3(v.y, v.z, v.w), r0, r1);
+      } else {
+        h.x = max3(l3, v.x, v.y);
+        h.y = max3(v.x, v.y, v.z);
+        h.z = max3(v.y, v.z, v.w);
+        h.w = max3(v.z, v.w, r0);
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float x = comp(xc, c), hh = comp(h, c);
+        bool keep = x > floorx;
+        if (keep && !pre && x != hh) {
+          const bool amb = (x >= hh - kNearTie) || (hh > kHiZone && x > kHiZone - 1.0f) || (hh < kLoZone);
+          keep = amb && Num<DT>::act(x) == Num<DT>::act(hh);  // rare
+        }
+        km |= (keep ? 1u : 0u) << (4 * i + c);
+      }
+    }
+  }
+  return km;
+}
+
+template <int R>
+__device__ __forceinline__ bool settle_dense_f32(UnitState& st, int rows_here, u32 ring_s, u32 ring_own, u32 row0, float floorx,
+                                                 u32 idx0, int W, bool pre, u64* buf, u32* hist, int* minx, const SharedFloors& sf,
+                                                 int* count_ptr, u64* __restrict__ list, int cap, int K, int lane, float xscale,
+                                                 float satx) {
+  constexpr int DT = SDNET_DTYPE_F32;
+  constexpr u32 kRingRows = kTileNG * kGroupRows;
+  u32 km = dense_keep_mask_f32<R>(rows_here, ring_s, ring_own, row0, floorx, pre, lane);
+  // where this lane's records go: exclusive prefix of the per-lane counts
+  const int cnt = __popc(km);
+  int incl = cnt;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += t;
+  }
+  const int total = __shfl_sync(0xffffffffu, incl, 31);
+  if (total == 0) return true;
+  if (total > kBuf) return false;
+  if (st.nbuf + total > kBuf) {
+    __syncwarp();
+    flush_candidates<DT, !SDNET_X_EARLYHIST>(st, buf, hist, minx, sf, count_ptr, list, cap, K, lane, pre, xscale, satx);
+  }
+  int pos = st.nbuf + incl - cnt;
+  const u32 centre0 = row0 + R;
+  while (km) {
+    const int bit = __ffs(km) - 1;
+    km &= km - 1;
+    const u32 i = (u32)bit >> 2, c = (u32)bit & 3u;
+    u32 rr = centre0 + i;
+    if (rr >= kRingRows) rr -= kRingRows;
+    const float x = TileMax<DT>::elem(ring_own + rr * kTilePitchB + 4 * c);
+    buf[pos++] = ((u64)__float_as_uint(x) << 32) | (idx0 + i * (u32)W + 4u * (u32)lane + c);
+#if SDNET_X_EARLYHIST
+    atomicAdd(&sf.ghist[fine_bin(fminf(fmaxf(x * xscale, -satx), satx))], 1u);
+#endif
+  }
+  st.nbuf += total;
+  return true;
 }
 
 // S = 2 only: a tile that touches the left or right image edge has read across a row boundary (see
@@ -328,6 +427,8 @@ sdnet_peaks_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_cons
   u32* hist = reinterpret_cast<u32*>(wbase + NG * kSlotB + 32);
   int* minx = reinterpret_cast<int*>(hist + kBins);
   u64* buf = reinterpret_cast<u64*>(minx + kBins);
+  unsigned char* work = reinterpret_cast<unsigned char*>(buf + kBuf);
+  const u32 lt = (1u << lane) - 1u;
   const bool pre = p.pre_activated != 0;
   const float xscale = pre ? kPreScale : 1.0f;
   const float satx = pre ? CUDART_INF_F : kSatX;
@@ -399,12 +500,13 @@ sdnet_peaks_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_cons
     __syncwarp();
 
     // tile k of the unit = image rows r_begin - R + 4k ..
-    auto issue = [&](bool pred, u32 s, int y) {  // the lanes with `pred` (one) pull the tile whose first image row is y into slot s
+    auto issue = [&](u32 s, int y) {  // lane 0: pull the tile whose first image row is y into slot s
+      mbar_arrive_expect_tx(bars_s + 8 * s, kTileBytes);
       if (S == 1) {
-        tma_tile_4d_if(pred, ring_s + s * kSlotB, tmap, xc, y, csel, b, bars_s + 8 * s, kTileBytes);
+        tma_tile_4d(ring_s + s * kSlotB, tmap, xc, y, csel, b, bars_s + 8 * s);
       } else {  // y is even (r_begin even, R = 2): rows y, y+2 then rows y+1, y+3
-        tma_tile_4d_x2_if(pred, ring_s + s * kSlotB, ring_s + s * kSlotB + kOddBoxOff, tmap, xc, xc + p.odd_x - kOddShiftB / 4,
-                          y >> 1, csel, b, bars_s + 8 * s, kTileBytes);
+        tma_tile_4d(ring_s + s * kSlotB, tmap, xc, y >> 1, csel, b, bars_s + 8 * s);
+        tma_tile_4d(ring_s + s * kSlotB + kOddBoxOff, tmap, xc + p.odd_x - kOddShiftB / 4, y >> 1, csel, b, bars_s + 8 * s);
       }
     };
     auto wait_tile = [&](u32 slot, u32 par) {
@@ -415,11 +517,11 @@ sdnet_peaks_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_cons
       }
     };
     int y_next = r_begin - R;  // first image row of the next tile to issue
-    {
+    if (lane == 0) {
+      const int first = min(NG, groups);
       u32 sl = cur_slot;
-#pragma unroll
-      for (int k = 0; k < NG; ++k) {
-        issue(lane == 0 && k < groups, sl, y_next + kGroupRows * k);
+      for (int k = 0; k < first; ++k) {
+        issue(sl, y_next + kGroupRows * k);
         if (++sl == (u32)NG) sl = 0;
       }
     }
@@ -458,11 +560,35 @@ sdnet_peaks_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_cons
       }
       const u32 hot = __ballot_sync(0xffffffffu, TileMax<DT>::group(c0, c1, c2, c3) > st.floorx);
       if (hot) {
-        // Something in these four rows beats the floor.  Pixel-centric slow path: every pixel of the blocks
-        // that hold such a pixel gets a lane of its own (settle_blocks).  In the last, partial group of a unit
-        // the rows past its end belong to the next unit: they may raise this alarm for nothing but are never recorded.
-        settle_blocks<R, DT, S>(st, hot, nrows - g * kGroupRows, ring_s, row0, row_tab, st.floorx, idx0, W, pre, buf, hist, minx,
-                                sf, count_ptr, list, p.cap, K, lane, xscale, satx);
+        // Something in these four rows beats the floor (`hot` = the lanes whose 4 x kPx block holds such a pixel).  In
+        // the last, partial group of a unit the rows past its end belong to the next unit: they may raise this alarm
+        // for nothing but are never recorded.
+        // Two ways to settle the group, by how many lanes are hot:
+        //   many (the first groups of a unit, before the plane has a floor worth the name): the whole maximum filter
+        //   of the group once, in registers (settle_dense_f32);
+        //   otherwise: list the hot 16-byte words, one ballot per row, and give every pixel of a listed word a
+        //   lane (settle_entries).  (Measured and dropped: giving every pixel of a hot lane's 4-row block a lane
+        //   without building the list -- more, emptier passes: 0.72 / 0.78 ms against 0.69 / 0.75 ms.)
+        const int nhot = __popc(hot), rows_here = nrows - g * kGroupRows;
+        const float floorx = st.floorx;
+        bool settled = false;
+        if (DT == SDNET_DTYPE_F32 && S == 1 && kDenseLanes > 0 && nhot >= kDenseLanes)
+          settled = settle_dense_f32<R>(st, rows_here, ring_s, ring_own, row0, floorx, idx0, W, pre, buf, hist, minx, sf, count_ptr,
+                                        list, p.cap, K, lane, xscale, satx);
+        if (!settled) {
+          int nent = 0;
+#pragma unroll
+          for (int i = 0; i < kGroupRows; ++i) {
+            const uint4 ci = i == 0 ? c0 : (i == 1 ? c1 : (i == 2 ? c2 : c3));
+            const bool mine = TileMax<DT>::word(ci) > floorx && i < rows_here;
+            const u32 bm = __ballot_sync(0xffffffffu, mine);
+            if (mine) work[nent + __popc(bm & lt)] = (unsigned char)((i << 5) | lane);
+            nent += __popc(bm);
+          }
+          __syncwarp();
+          settle_entries<R, DT, S>(st, work, nent, ring_s, row0, row_tab, floorx, idx0, W, pre, buf, hist, minx, sf, count_ptr, list,
+                                   p.cap, K, lane, xscale, satx);
+        }
         // while the plane has no floor yet, publish early and often; later only in batches
         if (st.nbuf >= kFlushAt || (st.nbuf > 0 && gfloor_seen <= 0)) {
           __syncwarp();
@@ -472,8 +598,10 @@ sdnet_peaks_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_cons
       // every lane's reads of the group's first tile are done (the votes above): refill its slot
       // with the tile NG ahead
       __syncwarp();
-      if (edge) fence_proxy_async();  // the slot was patched with ordinary stores
-      issue(lane == 0 && g + NG < groups, cur_slot, y_next);
+      if (lane == 0 && g + NG < groups) {
+        if (edge) fence_proxy_async();  // the slot was patched with ordinary stores
+        issue(cur_slot, y_next);
+      }
       y_next += kGroupRows;
       cur_slot = nxt_slot;
       cur_par = nxt_par;

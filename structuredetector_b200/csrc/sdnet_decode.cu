@@ -264,6 +264,28 @@ struct PeaksPlan {
   CUtensorMap tm_anchor, tm_part;
 };
 
+// Cut the line of columns x groups (pp.panels, pp.H set) into units for `resident` warps: see plan_peaks.
+bool plan_tile_line(PeaksParams& pp, long long planes, long long resident, int chunk_override, int* ctas, long long max_ctas) {
+  const long long G = (pp.H + kGroupRows - 1) / kGroupRows;
+  const long long columns = planes * pp.panels;
+  if (columns * G >= (1ll << 31)) return false;
+  const long long tier1 = (columns / resident) * resident;
+  const long long rest = (columns - tier1) * G;
+  long long chunk = (rest + resident - 1) / resident;
+  if (chunk < kMinChunkGroups) chunk = kMinChunkGroups;
+  if (chunk_override > 0) chunk = chunk_override;
+  if (chunk > G) chunk = G;
+  pp.tier1_units = (int)tier1;
+  pp.groups_per_col = (int)G;
+  pp.chunk_groups = (int)chunk;
+  pp.total_groups = (u32)(columns * G);
+  pp.units = (int)(tier1 + (rest + chunk - 1) / chunk);
+  long long n = ((long long)pp.units + kTileWarps - 1) / kTileWarps;
+  if (n > max_ctas) n = max_ctas;
+  *ctas = (int)n;
+  return true;
+}
+
 cudaError_t plan_peaks(const SdnetDecodeParams* p, PeaksParams& pp, PeaksPlan& pl) {
   const int C = p->M + p->N;
   const long long planes = (long long)p->B * C;
@@ -294,28 +316,14 @@ cudaError_t plan_peaks(const SdnetDecodeParams* p, PeaksParams& pp, PeaksPlan& p
     //   tier 2: what is left of the line cut into equal chunks, one per resident warp (a chunk may run
     //           over the end of a column into the next one), so the last wave ends everywhere at once.
     // With fewer columns than resident warps (small shards) everything is tier 2: one balanced wave.
-    const long long resident = (long long)pl.sms * pl.ctas_per_sm * kTileWarps;
-    const long long G = (p->H + kGroupRows - 1) / kGroupRows;
-    const long long columns = planes * pp.panels;
-    if (columns * G >= (1ll << 31)) return cudaErrorInvalidValue;
     static const int chunk_override = [] {  // tuning knob, read once: SDNET_CHUNK_GROUPS = n
       const char* e = getenv("SDNET_CHUNK_GROUPS");
       return e ? atoi(e) : 0;
     }();
-    const long long tier1 = (columns / resident) * resident;
-    const long long rest = (columns - tier1) * G;
-    long long chunk = (rest + resident - 1) / resident;
-    if (chunk < kMinChunkGroups) chunk = kMinChunkGroups;
-    if (chunk_override > 0) chunk = chunk_override;
-    if (chunk > G) chunk = G;
-    pp.tier1_units = (int)tier1;
-    pp.groups_per_col = (int)G;
-    pp.chunk_groups = (int)chunk;
-    pp.total_groups = (u32)(columns * G);
-    pp.units = (int)(tier1 + (rest + chunk - 1) / chunk);
-    long long ctas = ((long long)pp.units + kTileWarps - 1) / kTileWarps;
-    if (ctas > (long long)pl.sms * pl.ctas_per_sm) ctas = (long long)pl.sms * pl.ctas_per_sm;
-    pl.ctas = (int)ctas;
+    pp.H = p->H;
+    if (!plan_tile_line(pp, planes, (long long)pl.sms * pl.ctas_per_sm * kTileWarps, chunk_override, &pl.ctas,
+                        (long long)pl.sms * pl.ctas_per_sm))
+      return cudaErrorInvalidValue;
   } else {
     pl.tile_kern = nullptr;
     pl.smem = kPeaksSmem;
@@ -564,6 +572,29 @@ int sdnet_suppress_launch(const SdnetTensor4* in, int dtype, int B, int C, int H
   if (in->stride_w != 1) return SDNET_E_STRIDE;
   if (dtype != SDNET_DTYPE_F32 && dtype != SDNET_DTYPE_F16 && dtype != SDNET_DTYPE_BF16) return SDNET_E_DTYPE;
   if (radius != 1 && radius != 2) return SDNET_E_RADIUS;
+  static const bool no_tile = [] { const char* e = getenv("SDNET_SUPPRESS_PATH"); return e && e[0] == 'w'; }();  // tuning knob
+  // fp32 maps that TMA can describe (and a 16-byte-aligned output): the tile kernel
+  CUtensorMap tm;
+  if (!no_tile && dtype == SDNET_DTYPE_F32 && ((uintptr_t)out & 15) == 0 && (long long)B * C * ((W + kPanelW - 1) / kPanelW) * ((H + 3) / 4) < (1ll << 31) &&
+      tile_rows_per_tma_row(*in, dtype, H, W, radius) == 1 && make_tile_map(&tm, *in, dtype, B, C, H, W, 1)) {
+    PeaksParams pp = {};
+    pp.B = B; pp.M = C; pp.N = 0; pp.H = H; pp.W = W;
+    pp.panels = (W + kPanelW - 1) / kPanelW;
+    const auto kern = radius == 2 ? sdnet_suppress_tile_kernel<2> : sdnet_suppress_tile_kernel<1>;
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSupTileSmem);
+    if (err != cudaSuccess) return (int)err;
+    err = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (err != cudaSuccess) return (int)err;
+    int per_sm = 0;
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTileWarps * 32, kSupTileSmem);
+    if (err != cudaSuccess) return (int)err;
+    if (per_sm < 1) per_sm = 1;
+    const int sms = device_sm_count();
+    int ctas = 0;
+    plan_tile_line(pp, (long long)B * C, (long long)sms * per_sm * kTileWarps, 0, &ctas, sms * per_sm);
+    kern<<<dim3((unsigned)ctas), dim3(kTileWarps * 32), kSupTileSmem, static_cast<cudaStream_t>(stream)>>>(pp, tm, out);
+    return (int)cudaGetLastError();
+  }
   const int panels = (W + kPanelW - 1) / kPanelW, strips = (H + kSupStripRows - 1) / kSupStripRows;
   const long long units = (long long)panels * strips * C * B;
   const long long blocks = (units + kSupWarps - 1) / kSupWarps;

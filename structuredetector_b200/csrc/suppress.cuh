@@ -134,4 +134,112 @@ __global__ void __launch_bounds__(kSupWarps * 32, 3) sdnet_suppress_kernel(View4
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// TMA-tile form (fp32 maps whose base and pitches TMA can describe): the peaks kernel's feed -- autonomous warps,
+// private ring of 4-row tiles pulled by tensor-map bulk copies, NaN out-of-bounds fill standing in for max_pool2d's
+// -inf padding -- with the dense maximum filter of peaks_tile.cuh run on EVERY group.  Two to three tiles per warp
+// are in flight (the register-window kernel above keeps two ROWS), which is what an HBM-bound pass needs.
+// Output: each lane zero-fills its 16-byte word of the group's four rows with full-width vector stores, then
+// overwrites the few pixels that survive with their score (same thread, same address: program order).
+// Units are the peaks kernel's (whole columns, then balanced chunks), dealt round-robin: every group costs the same
+// here, so no atomic counter -- and no workspace -- is needed.
+// ---------------------------------------------------------------------------------------------
+constexpr int kSupTileSmemPerWarp = (kTileNG * kTileBytes + 32 + 127) / 128 * 128;
+constexpr int kSupTileSmem = kTileWarps * kSupTileSmemPerWarp;
+
+template <int R>
+__global__ void __launch_bounds__(kTileWarps * 32, 6)
+sdnet_suppress_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_constant__ CUtensorMap tm, float* __restrict__ out) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int NG = kTileNG;
+  constexpr u32 kRingRows = NG * kGroupRows;
+  constexpr int DT = SDNET_DTYPE_F32;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  unsigned char* wbase = smem_raw + (size_t)warp * kSupTileSmemPerWarp;
+  const u32 ring_s = smem_u32(wbase);
+  const u32 bars_s = ring_s + NG * kTileBytes;
+  const int C = p.M + p.N;
+  const int H = p.H, W = p.W;
+  const u32 ring_own = ring_s + (u32)(16 + 16 * lane);
+  if (lane == 0) {
+    for (int i = 0; i < NG; ++i) mbar_init(bars_s + 8 * i, 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
+  u32 cur_slot = 0, cur_par = 0;
+  auto step_pos = [&](u32& slot, u32& par) {
+    if (++slot == (u32)NG) { slot = 0; par ^= 1u; }
+  };
+  for (u32 unit = blockIdx.x * kTileWarps + warp; unit < (u32)p.units; unit += gridDim.x * kTileWarps) {
+    u32 pos, pos_end;
+    if (unit < (u32)p.tier1_units) {
+      pos = unit * (u32)p.groups_per_col;
+      pos_end = pos + (u32)p.groups_per_col;
+    } else {
+      pos = (u32)p.tier1_units * (u32)p.groups_per_col + (unit - (u32)p.tier1_units) * (u32)p.chunk_groups;
+      pos_end = min(p.total_groups, pos + (u32)p.chunk_groups);
+    }
+    while (pos < pos_end) {  // warp-uniform: one column segment at a time
+      const u32 column = pos / (u32)p.groups_per_col;
+      const int g_first = (int)(pos - column * (u32)p.groups_per_col);
+      const int g_last = min(p.groups_per_col, g_first + (int)(pos_end - pos));
+      pos += (u32)(g_last - g_first);
+      const int panel = (int)(column % (u32)p.panels), plane_id = (int)(column / (u32)p.panels);
+      const int r_begin = g_first * kGroupRows, r_end = min(H, g_last * kGroupRows);
+      const int b = plane_id / C, c = plane_id % C;
+      const int x0 = panel * kPanelW - 4;
+      const int nrows = r_end - r_begin;
+      const int groups = (nrows + 2 * R + kGroupRows - 1) / kGroupRows;
+      const int groups_out = (nrows + kGroupRows - 1) / kGroupRows;
+      const int col0 = panel * kPanelW + 4 * lane;
+      float* out_row = out + ((size_t)plane_id * H + r_begin) * W + col0;
+      __syncwarp();  // everyone is done with the previous segment's ring
+      auto issue = [&](u32 s, int y) {
+        mbar_arrive_expect_tx(bars_s + 8 * s, kTileBytes);
+        tma_tile_4d(ring_s + s * kTileBytes, &tm, x0, y, c, b, bars_s + 8 * s);
+      };
+      int y_next = r_begin - R;
+      if (lane == 0) {
+        const int first = min(NG, groups);
+        u32 sl = cur_slot;
+        for (int k = 0; k < first; ++k) {
+          issue(sl, y_next + kGroupRows * k);
+          if (++sl == (u32)NG) sl = 0;
+        }
+      }
+      y_next += kGroupRows * NG;
+      mbar_wait(bars_s + 8 * cur_slot, cur_par);
+      for (int g = 0; g < groups_out; ++g, out_row += (size_t)kGroupRows * W) {
+        u32 nxt_slot = cur_slot, nxt_par = cur_par;
+        step_pos(nxt_slot, nxt_par);
+        if (R == 2 || g + 1 < groups) mbar_wait(bars_s + 8 * nxt_slot, nxt_par);
+        const u32 row0 = cur_slot * kGroupRows;
+        const int rows_here = nrows - g * kGroupRows;
+        u32 km = dense_keep_mask_f32<R>(rows_here, ring_s, ring_own, row0, -CUDART_INF_F, false, lane);
+        if (col0 < W) {  // W is a multiple of 4: the whole word is inside the image
+#pragma unroll
+          for (int i = 0; i < kGroupRows; ++i)
+            if (i < rows_here) *reinterpret_cast<float4*>(out_row + (size_t)i * W) = make_float4(0.f, 0.f, 0.f, 0.f);
+          while (km) {
+            const int bit = __ffs(km) - 1;
+            km &= km - 1;
+            const u32 i = (u32)bit >> 2, cc = (u32)bit & 3u;
+            u32 rr = row0 + R + i;
+            if (rr >= kRingRows) rr -= kRingRows;
+            const float x = TileMax<DT>::elem(ring_own + rr * kTilePitchB + 4 * cc);
+            out_row[(size_t)i * W + cc] = Num<DT>::act(x);
+          }
+        }
+        __syncwarp();
+        if (lane == 0 && g + NG < groups) issue(cur_slot, y_next);
+        y_next += kGroupRows;
+        cur_slot = nxt_slot;
+        cur_par = nxt_par;
+      }
+      for (int k = groups_out; k < groups; ++k) step_pos(cur_slot, cur_par);
+    }
+  }
+}
+
 }  // namespace
