@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SDNET_ABI_VERSION 6
+#define SDNET_ABI_VERSION 7
 
 /* element types of the four input tensors */
 #define SDNET_DTYPE_F32 0
@@ -152,6 +152,12 @@ int sdnet_activate_launch(const SdnetTensor4* in, int dtype, int B, int C, int H
  * expects (decoders.py:211,226; SDNET_FLAG_PRE_ACTIVATED). */
 int sdnet_suppress_launch(const SdnetTensor4* in, int dtype, int B, int C, int H, int W, int radius, float* out, void* stream);
 
+/* Same, written into a strided fp32 (B, C, H, W) view (`out->stride_w` == 1, `out->stride_h` >= W): the first
+ * channels of a pre-allocated (B, C + 4, H, W) tensor, so that "network output with its heat maps baked" -- the
+ * reference's RawDecoder / CoreMLModel (src/sdnet/cli/convert_coreml.py:12-29) -- needs no torch.cat pass. */
+int sdnet_suppress_into_launch(const SdnetTensor4* in, int dtype, int B, int C, int H, int W, int radius, const SdnetTensor4* out,
+                               void* stream);
+
 /* Same as sdnet_decode_launch but the four input tensors live in (pinned) HOST memory: the heat-map
  * planes are copied to `staging` (device, >= B*(M+N)*H*W*elem bytes, 256-byte aligned) with one strided
  * cudaMemcpy2DAsync per heat tensor on `stream`, then the three kernels run on `stream`;
@@ -191,6 +197,39 @@ typedef struct SdnetMatchParams {
 } SdnetMatchParams;
 
 int sdnet_match_launch(const SdnetMatchParams* params, void* stream);
+
+/* Object-level matching of the reference evaluator on the packed detections: Evaluator.eval_csi with
+ * Evaluator.compute_csi (src/sdnet/model/evaluator.py:380-420, 539-581) and Evaluator.eval_classif (:429-474),
+ * what `evaluate` accumulates with eval_csi=True, eval_classif=True (src/sdnet/cli/evaluate.py:43-45).
+ * A predicted object is an anchor slot with score > conf plus the part slots `assign` groups onto it
+ * (decoders.py:108-137); ground truth = the annotation's objects and, in object order, their parts. */
+typedef struct SdnetObjectMatchParams {
+  uint32_t struct_size; /* sizeof(SdnetObjectMatchParams) */
+  int32_t B, M, N, K, P;
+  int32_t max_gt_objects, max_gt_parts; /* row lengths of the ground-truth arrays, <= SDNET_MAX_GT */
+  double conf;          /* objects: score > conf (decoders.py:116) */
+  double sx, sy;        /* heat-map -> network-input scale, in/out (decoders.py:139) */
+  double csi_threshold; /* args.csi_threshold (evaluator.py:414) */
+  const float* anchor_out;     /* (B, K, 4) as written by sdnet_decode_launch */
+  const float* part_out;       /* (B, P, 6) */
+  const int32_t* assign;       /* (B, P) */
+  const double* image_scale;   /* (B, 4): as in SdnetMatchParams */
+  const double* gt_objects;    /* (B, max_gt_objects, 3): anchor x, y, class index; annotation order */
+  const int32_t* n_gt_objects; /* (B) */
+  const double* gt_parts;      /* (B, max_gt_parts, 3): x, y, kind index; grouped by object, object order */
+  const int32_t* gt_part_owner;/* (B, max_gt_parts): index of the object each part belongs to (non-decreasing);
+                                  at most 64 parts per object */
+  const int32_t* n_gt_parts;   /* (B) */
+  const int32_t* cls_group;    /* (M): 0 / 1 for the classes named "bean" / "maize" (the reference's hard-coded
+                                  classification labels, evaluator.py:422-427), -1 for every other class */
+  int32_t* csi_stats;          /* (B, M, 3): ndet, npos, tp per class */
+  double* csi_acc;             /* (B, K): the CSI of the true positives, NaN elsewhere (slot = score order) */
+  int32_t* classif_stats;      /* (B, 20, 3): ndet, npos, tp for "bean_0".."bean_9", "maize_0".."maize_9" */
+  double* classif_acc;         /* (B, K): distance / min(img_size) of the true positives, NaN elsewhere */
+  int32_t* pred_parts;         /* (B, K): number of parts of each emitted object, -1 for slots not emitted */
+} SdnetObjectMatchParams;
+
+int sdnet_match_objects_launch(const SdnetObjectMatchParams* params, void* stream);
 
 #ifdef __cplusplus
 }

@@ -9,7 +9,7 @@ The tensor half runs in hand-written sm_100a kernels (``csrc/``) behind a C ABI
 (``include/sdnet_decode.h``); there is no CPU fallback.
 """
 from .annotations import Box, ImageAnnotation, Keypoint, Object
-from .decoders import CoreMLDecoder, Decoder, KeypointDecoder, RawDecoder
+from .decoders import CoreMLDecoder, CoreMLModel, Decoder, KeypointDecoder, RawDecoder
 
-__all__ = ["Decoder", "CoreMLDecoder", "KeypointDecoder", "RawDecoder", "Keypoint", "Box", "Object", "ImageAnnotation"]
+__all__ = ["Decoder", "CoreMLDecoder", "KeypointDecoder", "RawDecoder", "CoreMLModel", "Keypoint", "Box", "Object", "ImageAnnotation"]
 __version__ = "0.1.0"

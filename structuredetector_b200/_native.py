@@ -13,7 +13,7 @@ import os as _os
 
 # SDNET_DECODE_LIB: load another build of the same library (kernel experiments, tools/xbuild.sh)
 LIB_PATH = Path(_os.environ.get("SDNET_DECODE_LIB") or Path(__file__).resolve().parent / "csrc" / "libsdnet_decode.so").resolve()
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 FLAG_PRE_ACTIVATED = 1
 FLAG_NO_GROUPING = 2
@@ -36,8 +36,10 @@ EXPORTS = (
     "sdnet_decode_peaks_path",
     "sdnet_decode_schedule",
     "sdnet_match_launch",
+    "sdnet_match_objects_launch",
     "sdnet_activate_launch",
     "sdnet_suppress_launch",
+    "sdnet_suppress_into_launch",
     "sdnet_decode_host_launch",
 )
 
@@ -107,6 +109,22 @@ class SdnetMatchParams(ctypes.Structure):
     ]
 
 
+class SdnetObjectMatchParams(ctypes.Structure):
+    _fields_ = [
+        ("struct_size", ctypes.c_uint32),
+        ("B", ctypes.c_int32), ("M", ctypes.c_int32), ("N", ctypes.c_int32), ("K", ctypes.c_int32), ("P", ctypes.c_int32),
+        ("max_gt_objects", ctypes.c_int32), ("max_gt_parts", ctypes.c_int32),
+        ("conf", ctypes.c_double), ("sx", ctypes.c_double), ("sy", ctypes.c_double), ("csi_threshold", ctypes.c_double),
+        ("anchor_out", ctypes.c_void_p), ("part_out", ctypes.c_void_p), ("assign", ctypes.c_void_p),
+        ("image_scale", ctypes.c_void_p),
+        ("gt_objects", ctypes.c_void_p), ("n_gt_objects", ctypes.c_void_p),
+        ("gt_parts", ctypes.c_void_p), ("gt_part_owner", ctypes.c_void_p), ("n_gt_parts", ctypes.c_void_p),
+        ("cls_group", ctypes.c_void_p),
+        ("csi_stats", ctypes.c_void_p), ("csi_acc", ctypes.c_void_p),
+        ("classif_stats", ctypes.c_void_p), ("classif_acc", ctypes.c_void_p), ("pred_parts", ctypes.c_void_p),
+    ]
+
+
 class NativeLibraryError(RuntimeError):
     pass
 
@@ -144,6 +162,8 @@ def load_from(path) -> ctypes.CDLL:
     lib.sdnet_decode_launch.argtypes = [ctypes.POINTER(SdnetDecodeParams), ctypes.c_void_p]
     lib.sdnet_match_launch.restype = ctypes.c_int
     lib.sdnet_match_launch.argtypes = [ctypes.POINTER(SdnetMatchParams), ctypes.c_void_p]
+    lib.sdnet_match_objects_launch.restype = ctypes.c_int
+    lib.sdnet_match_objects_launch.argtypes = [ctypes.POINTER(SdnetObjectMatchParams), ctypes.c_void_p]
     lib.sdnet_decode_peaks_path.restype = ctypes.c_int
     lib.sdnet_decode_peaks_path.argtypes = [ctypes.POINTER(SdnetDecodeParams)]
     lib.sdnet_decode_schedule.restype = ctypes.c_int
@@ -153,6 +173,8 @@ def load_from(path) -> ctypes.CDLL:
                                               ctypes.POINTER(ctypes.c_float)]
     lib.sdnet_suppress_launch.restype = ctypes.c_int
     lib.sdnet_suppress_launch.argtypes = [ctypes.POINTER(SdnetTensor4)] + [ctypes.c_int] * 6 + [ctypes.c_void_p, ctypes.c_void_p]
+    lib.sdnet_suppress_into_launch.restype = ctypes.c_int
+    lib.sdnet_suppress_into_launch.argtypes = [ctypes.POINTER(SdnetTensor4)] + [ctypes.c_int] * 6 + [ctypes.POINTER(SdnetTensor4), ctypes.c_void_p]
     lib.sdnet_activate_launch.restype = ctypes.c_int
     lib.sdnet_activate_launch.argtypes = [ctypes.POINTER(SdnetTensor4), ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                           ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]

@@ -18,6 +18,7 @@
 #include <Python.h>
 #include <descrobject.h>
 #include <stdint.h>
+#include <string.h>
 #include <structmember.h>
 
 typedef struct {
@@ -231,9 +232,138 @@ done:
   return result;
 }
 
+/* ---- packed detections -> JSON text, without building a single annotation object ---------------------------
+ * json_text(anchor_out, part_out, assign, B, K, P, conf, sx, sy, resize, labels_json, kinds_json, anchor_json,
+ *           paths_json, sizes_json) -> list[str]
+ * One string per image, byte-identical to json.dumps(annotation.json_repr(), indent=2) of the annotation the decoder
+ * would have returned (utils.py:275-286; Keypoint / Object json_repr :52-57, 205-212), optionally after
+ * annotation.resize(net_size, img_size) as `detect` does (cli/detect.py:42-53): resize[b] = (rx, ry) or None.
+ * Names, paths and image sizes arrive already JSON-encoded (json.dumps on the Python side); floats are written with
+ * float.__repr__'s shortest round-trip form, which is what json.dumps uses. */
+typedef struct {
+  char* data;
+  size_t len, cap;
+} Buf;
+
+static int buf_reserve(Buf* b, size_t extra) {
+  if (b->len + extra <= b->cap) return 0;
+  size_t cap = b->cap ? b->cap : 4096;
+  while (cap < b->len + extra) cap *= 2;
+  char* d = (char*)PyMem_Realloc(b->data, cap);
+  if (!d) { PyErr_NoMemory(); return -1; }
+  b->data = d;
+  b->cap = cap;
+  return 0;
+}
+static int buf_put(Buf* b, const char* s, size_t n) {
+  if (buf_reserve(b, n) < 0) return -1;
+  memcpy(b->data + b->len, s, n);
+  b->len += n;
+  return 0;
+}
+#define PUT(b, lit) buf_put((b), (lit), sizeof(lit) - 1)
+static int buf_put_obj(Buf* b, PyObject* str) {
+  Py_ssize_t n;
+  const char* s = PyUnicode_AsUTF8AndSize(str, &n);
+  return s ? buf_put(b, s, (size_t)n) : -1;
+}
+static int buf_put_double(Buf* b, double v) {
+  if (v != v) return PUT(b, "NaN");
+  if (v > 1.7976931348623157e308) return PUT(b, "Infinity");
+  if (v < -1.7976931348623157e308) return PUT(b, "-Infinity");
+  char* s = PyOS_double_to_string(v, 'r', 0, Py_DTSF_ADD_DOT_0, NULL);
+  if (!s) return -1;
+  const int rc = buf_put(b, s, strlen(s));
+  PyMem_Free(s);
+  return rc;
+}
+/* one keypoint of an object's "parts" list (8 spaces deep) */
+static int put_keypoint(Buf* b, PyObject* kind_json, double x, double y, double score) {
+  if (PUT(b, "        {\n          \"kind\": ") < 0 || buf_put_obj(b, kind_json) < 0 ||
+      PUT(b, ",\n          \"location\": {\n            \"x\": ") < 0 || buf_put_double(b, x) < 0 ||
+      PUT(b, ",\n            \"y\": ") < 0 || buf_put_double(b, y) < 0 || PUT(b, "\n          },\n          \"score\": ") < 0 ||
+      buf_put_double(b, score) < 0 || PUT(b, "\n        }") < 0)
+    return -1;
+  return 0;
+}
+
+static PyObject* json_text(PyObject* self, PyObject* args) {
+  PyObject *a_obj, *p_obj, *s_obj, *resize, *labels, *kinds, *anchor_json, *paths, *sizes;
+  Py_ssize_t B, K, P;
+  double conf, sx, sy;
+  if (!PyArg_ParseTuple(args, "OOOnnndddO!O!O!UO!O!", &a_obj, &p_obj, &s_obj, &B, &K, &P, &conf, &sx, &sy, &PyList_Type, &resize,
+                        &PyList_Type, &labels, &PyList_Type, &kinds, &anchor_json, &PyList_Type, &paths, &PyList_Type, &sizes))
+    return NULL;
+  if (PyList_GET_SIZE(resize) != B || PyList_GET_SIZE(paths) != B || PyList_GET_SIZE(sizes) != B) {
+    PyErr_SetString(PyExc_ValueError, "resize, paths and sizes need one entry per image");
+    return NULL;
+  }
+  Views v = {{0}, {0}, {0}};
+  PyObject* result = NULL;
+  Buf buf = {NULL, 0, 0};
+  if (PyObject_GetBuffer(a_obj, &v.anchor, PyBUF_SIMPLE) < 0 || PyObject_GetBuffer(p_obj, &v.part, PyBUF_SIMPLE) < 0 ||
+      PyObject_GetBuffer(s_obj, &v.assign, PyBUF_SIMPLE) < 0)
+    goto done;
+  if (B < 0 || K <= 0 || P <= 0 || v.anchor.len < B * K * 16 || v.part.len < B * P * 24 || v.assign.len < B * P * 4) {
+    PyErr_SetString(PyExc_ValueError, "packed buffers are smaller than (B, K, 4) / (B, P, 6) / (B, P)");
+    goto done;
+  }
+  result = PyList_New(B);
+  if (!result) goto done;
+  const float* A = (const float*)v.anchor.buf;
+  const float* Pt = (const float*)v.part.buf;
+  const int32_t* S = (const int32_t*)v.assign.buf;
+  for (Py_ssize_t b = 0; b < B; ++b) {
+    const float* a = A + b * K * 4;
+    const float* p = Pt + b * P * 6;
+    const int32_t* s = S + b * P;
+    double rx = 1.0, ry = 1.0;
+    int resized = 0;
+    PyObject* r = PyList_GET_ITEM(resize, b);
+    if (r != Py_None) {
+      if (!PyArg_ParseTuple(r, "dd", &rx, &ry)) { Py_CLEAR(result); goto done; }
+      resized = 1;
+    }
+    buf.len = 0;
+    int bad = PUT(&buf, "{\n  \"image_path\": ") < 0 || buf_put_obj(&buf, PyList_GET_ITEM(paths, b)) < 0 ||
+              PUT(&buf, ",\n  \"img_size\": ") < 0 || buf_put_obj(&buf, PyList_GET_ITEM(sizes, b)) < 0 ||
+              PUT(&buf, ",\n  \"objects\": [") < 0;
+    Py_ssize_t n_out = 0;
+    for (Py_ssize_t k = 0; k < K && !bad; ++k) {
+      if (!((double)a[k * 4 + 2] > conf)) continue;
+      PyObject* label = name_at(labels, (long)a[k * 4 + 3]);
+      if (!label) { bad = 1; break; }
+      bad = (n_out && PUT(&buf, ",") < 0) || PUT(&buf, "\n    {\n      \"label\": ") < 0 || buf_put_obj(&buf, label) < 0 ||
+            PUT(&buf, ",\n      \"box\": null,\n      \"parts\": [\n") < 0;
+      double x = (double)a[k * 4] * sx, y = (double)a[k * 4 + 1] * sy;
+      if (resized) { x *= rx; y *= ry; }
+      bad = bad || put_keypoint(&buf, anchor_json, x, y, (double)a[k * 4 + 2]) < 0;
+      for (Py_ssize_t i = 0; i < P && !bad; ++i) {
+        if (s[i] != k) continue;
+        PyObject* kind = name_at(kinds, (long)p[i * 6 + 3]);
+        if (!kind) { bad = 1; break; }
+        double px = (double)p[i * 6] * sx, py = (double)p[i * 6 + 1] * sy;
+        if (resized) { px *= rx; py *= ry; }
+        bad = PUT(&buf, ",\n") < 0 || put_keypoint(&buf, kind, px, py, (double)p[i * 6 + 2]) < 0;
+      }
+      bad = bad || PUT(&buf, "\n      ]\n    }") < 0;
+      ++n_out;
+    }
+    bad = bad || (n_out && PUT(&buf, "\n  ") < 0) || PUT(&buf, "]\n}") < 0;
+    PyObject* text = bad ? NULL : PyUnicode_DecodeUTF8(buf.data, (Py_ssize_t)buf.len, "strict");
+    if (!text) { Py_CLEAR(result); goto done; }
+    PyList_SET_ITEM(result, b, text);
+  }
+done:
+  if (buf.data) PyMem_Free(buf.data);
+  views_release(&v);
+  return result;
+}
+
 static PyMethodDef methods[] = {
     {"assemble", assemble, METH_VARARGS, "packed detections -> list[ImageAnnotation] (decoders.py:103-139)"},
     {"keypoints", keypoints, METH_VARARGS, "packed part rows -> list[list[Keypoint]] (decoders.py:142-159)"},
+    {"json_text", json_text, METH_VARARGS, "packed detections -> list[str], one JSON document per image (utils.py:275-286)"},
     {NULL, NULL, 0, NULL}};
 
 static struct PyModuleDef module = {PyModuleDef_HEAD_INIT, "_fastobj", "C object assembly of the SDNet decoding path", -1, methods};

@@ -487,6 +487,26 @@ int sdnet_match_launch(const SdnetMatchParams* p, void* stream) {
   return (int)cudaGetLastError();
 }
 
+int sdnet_match_objects_launch(const SdnetObjectMatchParams* p, void* stream) {
+  if (!p) return SDNET_E_NULL;
+  if (p->struct_size != sizeof(SdnetObjectMatchParams)) return SDNET_E_STRUCT;
+  if (!p->anchor_out || !p->part_out || !p->assign || !p->image_scale || !p->n_gt_objects || !p->n_gt_parts || !p->cls_group ||
+      !p->csi_stats || !p->csi_acc || !p->classif_stats || !p->classif_acc || !p->pred_parts ||
+      (p->max_gt_objects > 0 && !p->gt_objects) || (p->max_gt_parts > 0 && (!p->gt_parts || !p->gt_part_owner)))
+    return SDNET_E_NULL;
+  if (p->B <= 0 || p->M <= 0 || p->N <= 0 || p->K <= 0 || p->P <= 0 || p->K > SDNET_MAX_TOPK || p->P > SDNET_MAX_TOPK ||
+      p->M + p->N > SDNET_MAX_CHANNELS || p->max_gt_objects < 0 || p->max_gt_parts < 0 || p->max_gt_objects > SDNET_MAX_GT ||
+      p->max_gt_parts > SDNET_MAX_GT)
+    return SDNET_E_SHAPE;
+  const size_t Go = (size_t)p->max_gt_objects, Gp = (size_t)p->max_gt_parts, K = (size_t)p->K, P = (size_t)p->P;
+  const size_t n_stats = 3 * (size_t)(p->M > 20 ? p->M : 20);
+  const size_t smem = 8 * (2 * Go + 3 * K + 2 * P + 2 * Gp) + 4 * (3 * Go + 1 + 3 * K + 1 + 2 * P + Gp + n_stats) + 16;
+  cudaError_t err = cudaFuncSetAttribute(sdnet_match_objects_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (err != cudaSuccess) return (int)err;
+  sdnet_match_objects_kernel<<<dim3((unsigned)p->B), dim3(kMatchThreads), smem, static_cast<cudaStream_t>(stream)>>>(*p);
+  return (int)cudaGetLastError();
+}
+
 int sdnet_decode_peaks_path(const SdnetDecodeParams* params) {
   const int rc = validate(params);
   if (rc != 0) return rc;
@@ -566,8 +586,11 @@ int sdnet_activate_launch(const SdnetTensor4* in, int dtype, int B, int C, int H
   return (int)cudaGetLastError();
 }
 
-int sdnet_suppress_launch(const SdnetTensor4* in, int dtype, int B, int C, int H, int W, int radius, float* out, void* stream) {
-  if (!in || !in->data || !out) return SDNET_E_NULL;
+int sdnet_suppress_into_launch(const SdnetTensor4* in, int dtype, int B, int C, int H, int W, int radius, const SdnetTensor4* out_t,
+                               void* stream) {
+  if (!in || !in->data || !out_t || !out_t->data) return SDNET_E_NULL;
+  if (out_t->stride_w != 1 || out_t->stride_h < W) return SDNET_E_STRIDE;
+  const View4 outv = to_view(*out_t);
   if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return SDNET_E_SHAPE;
   if (in->stride_w != 1) return SDNET_E_STRIDE;
   if (dtype != SDNET_DTYPE_F32 && dtype != SDNET_DTYPE_F16 && dtype != SDNET_DTYPE_BF16) return SDNET_E_DTYPE;
@@ -575,7 +598,8 @@ int sdnet_suppress_launch(const SdnetTensor4* in, int dtype, int B, int C, int H
   static const bool no_tile = [] { const char* e = getenv("SDNET_SUPPRESS_PATH"); return e && e[0] == 'w'; }();  // tuning knob
   // fp32 maps that TMA can describe (and a 16-byte-aligned output): the tile kernel
   CUtensorMap tm;
-  if (!no_tile && dtype == SDNET_DTYPE_F32 && ((uintptr_t)out & 15) == 0 && (long long)B * C * ((W + kPanelW - 1) / kPanelW) * ((H + 3) / 4) < (1ll << 31) &&
+  if (!no_tile && dtype == SDNET_DTYPE_F32 &&
+      (((uintptr_t)out_t->data | (uintptr_t)(out_t->stride_b * 4) | (uintptr_t)(out_t->stride_c * 4) | (uintptr_t)(out_t->stride_h * 4)) & 15) == 0 && (long long)B * C * ((W + kPanelW - 1) / kPanelW) * ((H + 3) / 4) < (1ll << 31) &&
       tile_rows_per_tma_row(*in, dtype, H, W, radius) == 1 && make_tile_map(&tm, *in, dtype, B, C, H, W, 1)) {
     PeaksParams pp = {};
     pp.B = B; pp.M = C; pp.N = 0; pp.H = H; pp.W = W;
@@ -592,7 +616,7 @@ int sdnet_suppress_launch(const SdnetTensor4* in, int dtype, int B, int C, int H
     const int sms = device_sm_count();
     int ctas = 0;
     plan_tile_line(pp, (long long)B * C, (long long)sms * per_sm * kTileWarps, 0, &ctas, sms * per_sm);
-    kern<<<dim3((unsigned)ctas), dim3(kTileWarps * 32), kSupTileSmem, static_cast<cudaStream_t>(stream)>>>(pp, tm, out);
+    kern<<<dim3((unsigned)ctas), dim3(kTileWarps * 32), kSupTileSmem, static_cast<cudaStream_t>(stream)>>>(pp, tm, outv);
     return (int)cudaGetLastError();
   }
   const int panels = (W + kPanelW - 1) / kPanelW, strips = (H + kSupStripRows - 1) / kSupStripRows;
@@ -602,12 +626,23 @@ int sdnet_suppress_launch(const SdnetTensor4* in, int dtype, int B, int C, int H
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const dim3 grid((unsigned)blocks), block(kSupWarps * 32);
   const View4 v = to_view(*in);
-#define SDNET_SUPPRESS(R, DT) sdnet_suppress_kernel<R, DT><<<grid, block, 0, st>>>(v, C, H, W, panels, strips, units, out)
+#define SDNET_SUPPRESS(R, DT) sdnet_suppress_kernel<R, DT><<<grid, block, 0, st>>>(v, C, H, W, panels, strips, units, outv)
   if (dtype == SDNET_DTYPE_F16) { if (radius == 2) SDNET_SUPPRESS(2, SDNET_DTYPE_F16); else SDNET_SUPPRESS(1, SDNET_DTYPE_F16); }
   else if (dtype == SDNET_DTYPE_BF16) { if (radius == 2) SDNET_SUPPRESS(2, SDNET_DTYPE_BF16); else SDNET_SUPPRESS(1, SDNET_DTYPE_BF16); }
   else { if (radius == 2) SDNET_SUPPRESS(2, SDNET_DTYPE_F32); else SDNET_SUPPRESS(1, SDNET_DTYPE_F32); }
 #undef SDNET_SUPPRESS
   return (int)cudaGetLastError();
+}
+
+int sdnet_suppress_launch(const SdnetTensor4* in, int dtype, int B, int C, int H, int W, int radius, float* out, void* stream) {
+  if (!out) return SDNET_E_NULL;
+  SdnetTensor4 dense;
+  dense.data = out;
+  dense.stride_w = 1;
+  dense.stride_h = W;
+  dense.stride_c = (int64_t)H * W;
+  dense.stride_b = (int64_t)C * H * W;
+  return sdnet_suppress_into_launch(in, dtype, B, C, H, W, radius, &dense, stream);
 }
 
 int sdnet_decode_host_launch(const SdnetDecodeParams* params, void* staging, size_t staging_bytes, void* stream_v) {

@@ -42,7 +42,7 @@ __device__ __forceinline__ float sup_score(float x, float h) {
 
 template <int R, int DT>
 __global__ void __launch_bounds__(kSupWarps * 32, 3) sdnet_suppress_kernel(View4 in, int C, int H, int W, int panels, int strips,
-                                                                         long long units, float* __restrict__ out) {
+                                                                         long long units, View4 outv) {
   constexpr int kWin = 2 * R + 1;
   const int lane = threadIdx.x & 31;
   const long long unit = (long long)blockIdx.x * kSupWarps + (threadIdx.x >> 5);
@@ -60,8 +60,9 @@ __global__ void __launch_bounds__(kSupWarps * 32, 3) sdnet_suppress_kernel(View4
   // fp16/bf16 elements measured slower than four 2-byte loads here: 0.89 vs 0.76 ms)
   const bool vec_ok = DT == SDNET_DTYPE_F32 && ((reinterpret_cast<uintptr_t>(in.data) | (uintptr_t)(in.sb * 4) | (uintptr_t)(in.sc * 4) |
                                                   (uintptr_t)(in.sh * 4)) & 15) == 0;
-  const bool out_vec = (W & 3) == 0;
-  float* out_plane = out + (b * C + c) * (long long)H * W;
+  float* out_plane = static_cast<float*>(const_cast<void*>(outv.data)) + b * outv.sb + (long long)c * outv.sc;
+  const bool out_vec = (W & 3) == 0 && ((reinterpret_cast<uintptr_t>(outv.data) | (uintptr_t)(outv.sb * 4) | (uintptr_t)(outv.sc * 4) |
+                                        (uintptr_t)(outv.sh * 4)) & 15) == 0;
   // halo columns of the panel: lane 0 fetches the R columns left of it, lane 31 the R columns right
   const int hx = lane == 0 ? x - R : x + 4;
   const bool halo_lane = lane == 0 || lane == 31;
@@ -121,7 +122,7 @@ __global__ void __launch_bounds__(kSupWarps * 32, 3) sdnet_suppress_kernel(View4
       }
       const float4 ctr = cwin[0];
       const float4 s = make_float4(sup_score<DT>(ctr.x, h.x), sup_score<DT>(ctr.y, h.y), sup_score<DT>(ctr.z, h.z), sup_score<DT>(ctr.w, h.w));
-      float* dst = out_plane + (long long)yo * W + x;
+      float* dst = out_plane + (long long)yo * outv.sh + x;
       if (out_vec) {
         *reinterpret_cast<float4*>(dst) = s;
       } else {
@@ -149,7 +150,7 @@ constexpr int kSupTileSmem = kTileWarps * kSupTileSmemPerWarp;
 
 template <int R>
 __global__ void __launch_bounds__(kTileWarps * 32, 6)
-sdnet_suppress_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_constant__ CUtensorMap tm, float* __restrict__ out) {
+sdnet_suppress_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_constant__ CUtensorMap tm, const View4 outv) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int NG = kTileNG;
   constexpr u32 kRingRows = NG * kGroupRows;
@@ -193,7 +194,9 @@ sdnet_suppress_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_c
       const int groups = (nrows + 2 * R + kGroupRows - 1) / kGroupRows;
       const int groups_out = (nrows + kGroupRows - 1) / kGroupRows;
       const int col0 = panel * kPanelW + 4 * lane;
-      float* out_row = out + ((size_t)plane_id * H + r_begin) * W + col0;
+      const size_t orow = (size_t)outv.sh;  // output row pitch in elements (a multiple of 4: checked on the host)
+      float* out_row = static_cast<float*>(const_cast<void*>(outv.data)) + (size_t)b * outv.sb + (size_t)c * outv.sc +
+                       (size_t)r_begin * orow + col0;
       __syncwarp();  // everyone is done with the previous segment's ring
       auto issue = [&](u32 s, int y) {
         mbar_arrive_expect_tx(bars_s + 8 * s, kTileBytes);
@@ -210,7 +213,7 @@ sdnet_suppress_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_c
       }
       y_next += kGroupRows * NG;
       mbar_wait(bars_s + 8 * cur_slot, cur_par);
-      for (int g = 0; g < groups_out; ++g, out_row += (size_t)kGroupRows * W) {
+      for (int g = 0; g < groups_out; ++g, out_row += (size_t)kGroupRows * orow) {
         u32 nxt_slot = cur_slot, nxt_par = cur_par;
         step_pos(nxt_slot, nxt_par);
         if (R == 2 || g + 1 < groups) mbar_wait(bars_s + 8 * nxt_slot, nxt_par);
@@ -220,7 +223,7 @@ sdnet_suppress_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_c
         if (col0 < W) {  // W is a multiple of 4: the whole word is inside the image
 #pragma unroll
           for (int i = 0; i < kGroupRows; ++i)
-            if (i < rows_here) *reinterpret_cast<float4*>(out_row + (size_t)i * W) = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < rows_here) *reinterpret_cast<float4*>(out_row + (size_t)i * orow) = make_float4(0.f, 0.f, 0.f, 0.f);
           while (km) {
             const int bit = __ffs(km) - 1;
             km &= km - 1;
@@ -228,7 +231,7 @@ sdnet_suppress_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_c
             u32 rr = row0 + R + i;
             if (rr >= kRingRows) rr -= kRingRows;
             const float x = TileMax<DT>::elem(ring_own + rr * kTilePitchB + 4 * cc);
-            out_row[(size_t)i * W + cc] = Num<DT>::act(x);
+            out_row[(size_t)i * orow + cc] = Num<DT>::act(x);
           }
         }
         __syncwarp();

@@ -51,6 +51,7 @@ __device__ __forceinline__ u64 make_comp(u64 rec, int c_local) {
 // barrier.  They meet once, before the grouping.
 constexpr int kTeamThreads = 256;
 constexpr float kNearField = 1e5f;   // see the grouping pass
+constexpr int kRankSortMax = 192;     // up to this many collected composites are sorted by counting ranks (<= kTeamThreads)
 constexpr int kHistCollectMax = 512;  // a histogram cut-off that collects more than this falls back to the radix refinement
 
 struct Team {
@@ -236,6 +237,19 @@ __device__ int select_group(const Team& tm, const TailParams& p, int b, int c0, 
     tm.sync();
   }
   const int got = min(s_misc[1], kSortN);
+  if (got <= kRankSortMax) {
+    // The usual case (want plus a few dozen): every thread ranks its own composite by counting the larger ones --
+    // got broadcast reads per thread, no barrier in the loop; composites are pairwise distinct (they end in the
+    // pixel index and the class), so the ranks are a permutation.
+    const u64 mine = tid < got ? s_sel[tid] : 0ull;
+    int rank = 0;
+    if (tid < got)
+      for (int j = 0; j < got; ++j) rank += s_sel[j] > mine ? 1 : 0;
+    tm.sync();
+    if (tid < got) s_sel[rank] = mine;
+    tm.sync();
+    return min(got, want);
+  }
   int n2 = 32;
   while (n2 < got) n2 <<= 1;
   for (int i = got + tid; i < n2; i += kTeamThreads) s_sel[i] = 0;

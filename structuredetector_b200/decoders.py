@@ -11,6 +11,8 @@ from __future__ import annotations
 
 import contextlib
 import gc
+import json
+from pathlib import Path
 
 import numpy as np
 import torch
@@ -24,7 +26,7 @@ except ImportError as exc:  # no silent slow path: say how to get it
     raise ImportError("structuredetector_b200._fastobj is missing: run `python -m structuredetector_b200.build` "
                       "(gcc, CPython headers) to build the object-assembly extension") from exc
 
-__all__ = ["Decoder", "CoreMLDecoder", "KeypointDecoder", "RawDecoder"]
+__all__ = ["Decoder", "CoreMLDecoder", "KeypointDecoder", "RawDecoder", "CoreMLModel"]
 
 
 @contextlib.contextmanager
@@ -103,6 +105,51 @@ class Decoder(_DecoderBase):
         meta["raw_offsets"] = outputs["offsets"]
         return meta
 
+    # reference: utils.py:275-286 (json_repr / save_json) on what decoders.py:103-139 would have built
+    def detections_json(self, outputs, conf_thresh=None, dist_thresh=None, *, image_paths=None, img_sizes=None, net_size=None):
+        """One JSON document per image, byte-identical to ``json.dumps(annotation.json_repr(), indent=2)`` of the
+        annotations ``self(outputs)`` returns -- written straight from the packed detections by the C loop in
+        ``csrc/fastobj.c``, no ``ImageAnnotation`` / ``Object`` / ``Keypoint`` is built.
+
+        With ``img_sizes`` (one ``(w, h)`` per image) and ``net_size = (args.width, args.height)`` the documents are
+        those of the reference's ``detect`` loop (cli/detect.py:41-52): the annotation resized from the network input
+        to the original image, ``img_size`` and ``image_path`` set.  ``image_paths`` default to ``batch_<i>``."""
+        conf_thresh = self.args.conf_threshold if conf_thresh is None else conf_thresh
+        dist_thresh = self.args.decoder_dist_thresh if dist_thresh is None else dist_thresh
+        out_size, in_size = self._sizes(outputs)
+        packed = ops.decode_packed(outputs, self.max_objects, self.max_parts, conf_thresh, dist_thresh,
+                                   pre_activated=self._pre_activated)
+        return self._json_from_host(self._to_host(packed), conf_thresh, out_size, in_size, image_paths, img_sizes, net_size)
+
+    def _json_from_host(self, host, conf_thresh, out_size, in_size, image_paths=None, img_sizes=None, net_size=None):
+        B, K = host.anchor_out.shape[:2]
+        paths = [Path(f"batch_{b}") for b in range(B)] if image_paths is None else [Path(p) for p in image_paths]
+        sizes = [None] * B if img_sizes is None else list(img_sizes)
+        if len(paths) != B or len(sizes) != B:
+            raise ValueError(f"{B} images but {len(paths)} paths / {len(sizes)} image sizes")
+        if any(size is not None for size in sizes) and net_size is None:
+            raise ValueError("img_sizes need net_size = (args.width, args.height), the frame the decoder's coordinates are in")
+        # Keypoint.resize(in_size=net_size, out_size=img_size): x *= img_w / net_w (utils.py:19-26)
+        resize = [None if size is None else (size[0] / net_size[0], size[1] / net_size[1]) for size in sizes]
+        enc = lambda names: [None if name is None else json.dumps(name) for name in names]
+        return _fastobj.json_text(
+            host.anchor_out.contiguous().numpy(), host.part_out.contiguous().numpy(), host.assign.contiguous().numpy(), B, K,
+            host.part_out.shape[1], float(conf_thresh), in_size[0] / out_size[0], in_size[1] / out_size[1], resize,
+            enc(self._names(self.label_map)), enc(self._names(self.part_map)), json.dumps(self.anchor_name),
+            [json.dumps(str(path.expanduser().resolve())) for path in paths],
+            [json.dumps(None if size is None else list(size), indent=2).replace("\n", "\n  ") for size in sizes])
+
+    def save_detections_json(self, outputs, save_dir=None, **kwargs):
+        """``detections_json`` written like ``ImageAnnotation.save_json`` (utils.py:282-286): ``<save_dir>/<image stem>.json``."""
+        target = Path(save_dir or "detections/")
+        target.mkdir(parents=True, exist_ok=True)
+        paths = kwargs.get("image_paths")
+        texts = self.detections_json(outputs, **kwargs)
+        for b, text in enumerate(texts):
+            name = Path(paths[b] if paths is not None else f"batch_{b}").with_suffix(".json").name
+            (target / name).write_text(text)
+        return texts
+
     # reference: decoders.py:103-139
     def _assemble(self, host: ops.PackedDetections, conf_thresh, out_size, in_size):
         """Python objects from the packed rows, built by the C loop in ``csrc/fastobj.c``: float32 coordinates
@@ -171,11 +218,37 @@ class KeypointDecoder(_DecoderBase):
 class RawDecoder:
     """``RawDecoder(nb_hms)(raw)``: the network's raw ``(B, M+N+4, H, W)`` output with its first ``nb_hms``
     channels replaced by ``nms(clamped_sigmoid(.))`` -- what the reference bakes into its exported model
-    (reference: src/sdnet/cli/convert_coreml.py:12-19) and ``CoreMLDecoder`` then consumes."""
+    (reference: src/sdnet/cli/convert_coreml.py:12-19) and ``CoreMLDecoder`` then consumes.
+
+    float32: ONE kernel writes the baked heat maps straight into the first channels of the result
+    (``sdnet_suppress_into_launch``) and the four offset / embedding channels are copied behind them -- the reference's
+    sigmoid, clamp, max-pool, compare, multiply and ``torch.cat`` passes (12 reads / writes of the heat maps) become one
+    read and one write.  fp16 / bf16 go through a float32 intermediate of the heat maps only."""
 
     def __init__(self, nb_hms: int) -> None:
         self.nb_hms = nb_hms
 
     def __call__(self, input: torch.Tensor) -> torch.Tensor:
-        heatmaps = ops.suppress_maps(input[:, : self.nb_hms])
-        return torch.cat(tensors=(heatmaps, input[:, self.nb_hms:]), dim=1)
+        n = self.nb_hms
+        out = torch.empty(input.shape, dtype=input.dtype, device=input.device)
+        if input.dtype == torch.float32:
+            ops.suppress_into(input[:, :n], out[:, :n])
+        else:
+            out[:, :n] = ops.suppress_maps(input[:, :n])
+        out[:, n:] = input[:, n:]
+        return out
+
+
+class CoreMLModel(torch.nn.Module):
+    """``CoreMLModel(model, args)``: the network followed by ``RawDecoder`` as one module -- sigmoid + NMS fused onto the
+    head's output (reference: src/sdnet/cli/convert_coreml.py:21-29).  ``model`` is any module returning the raw
+    ``(B, M+N+4, H/4, W/4)`` tensor (the reference ``Network`` with ``raw_output=True``); ``forward`` returns that tensor
+    with the heat maps baked, i.e. what ``CoreMLDecoder`` decodes."""
+
+    def __init__(self, model: torch.nn.Module, args) -> None:
+        super().__init__()
+        self.model = model
+        self.decoder = RawDecoder(nb_hms=len(args.labels) + len(args.parts))
+
+    def forward(self, image: torch.Tensor) -> torch.Tensor:
+        return self.decoder(self.model(image))

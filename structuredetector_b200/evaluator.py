@@ -1,18 +1,19 @@
-"""Location metrics of the reference evaluator, computed on the device from the packed detections.
+"""The reference evaluator's metrics, computed on the device from the packed detections.
 
 Mirrors ``Evaluation`` / ``Evaluations`` / ``Evaluator`` of the reference (reference:
-src/sdnet/model/evaluator.py:13-120, 123-206, 209-334): same attribute and property names, same
-formulas, so tables and CSV code written against them keep working.  What moves to the GPU is the
-matching of ``eval_anchor`` (:244-284) and ``eval_part`` (:286-334) -- per image and label, detections in
-score order against their nearest ground truth -- through ``sdnet_match_launch`` on the tensors
-``sdnet_decode_launch`` wrote; no Python object is built for a prediction.  The CSI and classification
-tables (``eval_csi``, ``eval_classif``) are not covered; the objects our ``Decoder`` returns feed the
-reference's own ``Evaluator`` unchanged for those.
+src/sdnet/model/evaluator.py:13-120, 123-206, 209-646): same attribute and property names, same
+formulas, so tables and CSV code written against them keep working.  What moves to the GPU is the matching:
+``eval_anchor`` (:244-284) and ``eval_part`` (:286-334) -- per image and label, detections in score order
+against their nearest ground truth -- through ``sdnet_match_launch``; ``eval_csi`` with ``compute_csi``
+(:380-420, 539-581) and ``eval_classif`` (:429-474) -- predicted objects (anchor + grouped parts) against
+ground-truth objects -- through ``sdnet_match_objects_launch``; both straight on the tensors
+``sdnet_decode_launch`` wrote: no Python object is built for a prediction.
 """
 from __future__ import annotations
 
 import ctypes
 from functools import reduce
+from pathlib import Path
 
 import numpy as np
 import torch
@@ -82,9 +83,59 @@ class Evaluation:
         return (f"{self.npos}", f"{self.ndet}", f"{self.recall:.2%}", f"{self.precision:.2%}", f"{self.f1_score:.2%}",
                 f"{self.avg_acc:.4%}", f"{self.acc_err:.4%}")
 
+    COLUMNS = ("Gts.", "Preds.", "Rec.", "Prec.", "F1 Score", "L. Acc.", "L. Err.")
+
+    @staticmethod
+    def columns():
+        """Column headers of ``stats()`` (evaluator.py:88-98; ``rich`` Column objects when rich is installed)."""
+        try:
+            from rich.table import Column
+        except ImportError:
+            return Evaluation.COLUMNS
+        return tuple(Column(name, justify="right", **({"style": "green"} if name == "F1 Score" else {}))
+                     for name in Evaluation.COLUMNS)
+
+    def pretty_print(self):
+        single = Evaluations()
+        single.evals = {"": self}
+        _print_table(None, single)
+
+    def save_conf_matrix(self):
+        """One 10 x 10 (expected parts, predicted parts) count matrix per label, as ``conf_mat_<label>.npy``
+        (evaluator.py:107-113)."""
+        by_label = {}
+        for label, predicted, expected in self.count_errors:
+            by_label.setdefault(label, []).append((predicted, expected))
+        for label, pairs in by_label.items():
+            mat = np.zeros((10, 10))
+            for predicted, expected in pairs:
+                mat[expected, predicted] += 1
+            np.save(f"conf_mat_{label}.npy", mat)
+
     def __repr__(self):
         return (f"f1: {self.f1_score:.2%}, rec: {self.recall:.2%}, prec: {self.precision:.2%}, npos: {self.npos}, "
                 f"ndet: {self.ndet}, tp/fp/fn: {self.tp}/{self.fp}/{self.fn}, avg_acc: {self.avg_acc:.2}")
+
+
+def _print_table(title, evaluations):
+    """A ``rich`` table like the reference prints (evaluator.py:190-196, 583-604); plain text without rich."""
+    rows = [(label, *evaluation.stats()) for label, evaluation in evaluations.items()]
+    total = ("Total", *evaluations.reduce().stats()) if len(evaluations) > 1 else None
+    try:
+        from rich import print as rprint
+        from rich.table import Column, Table
+    except ImportError:
+        if title:
+            print(title)
+        for row in rows + ([total] if total else []):
+            print(" ", *row)
+        return
+    table = Table(Column("Label", style="bold"), *Evaluation.columns(), title=title)
+    for row in rows:
+        table.add_row(*row)
+    if total:
+        table.add_row(*total, style="bold")
+    rprint(table)
 
 
 class Evaluations:
@@ -130,8 +181,18 @@ class Evaluations:
         merged.evals.update({label: other[label] for label in other.labels - self.labels})
         return merged
 
+    def __ior__(self, other):
+        """In-place union (evaluator.py:180-185; the reference's version recurses into itself -- this does what it
+        is written to mean): labels only ``other`` has are adopted, shared labels are summed."""
+        for label, evaluation in other.items():
+            self.evals[label] = self.evals[label] + evaluation if label in self.evals else evaluation
+        return self
+
     def reduce(self):
         return reduce(Evaluation.__iadd__, self.evals.values(), Evaluation())
+
+    def pretty_print(self, table_name=None):
+        _print_table(table_name, self)
 
     def __repr__(self):
         lines = [f"total: {self.reduce()}"] if len(self) > 1 else []
@@ -158,10 +219,17 @@ class Evaluator:
     def reset(self):
         self.anchor_eval = Evaluations(self.labels)
         self.part_eval = Evaluations(self.kp_labels)
+        self.csi_eval = Evaluations(self.labels)
+        self.classification_eval = Evaluations(Evaluator.get_classification_labels())
 
     @property
     def kps_eval(self):
         return self.anchor_eval | self.part_eval
+
+    @staticmethod
+    def get_classification_labels():
+        """The reference's hard-coded (label, number of parts) classes (evaluator.py:422-427)."""
+        return [f"bean_{index}" for index in range(10)] + [f"maize_{index}" for index in range(10)]
 
     # -- ground truth -> tensors -------------------------------------------------------------
     def _pack_ground_truth(self, annotations, device):
@@ -169,6 +237,10 @@ class Evaluator:
                   for ann in annotations]
         rows_p = [[(kp.x, kp.y, self._part_index.get(kp.kind, -1)) for obj in ann.objects for kp in obj.parts]
                   for ann in annotations]
+
+        owners = [[j for j, obj in enumerate(ann.objects) for _ in obj.parts] for ann in annotations]
+        if any(len(obj.parts) > 64 for ann in annotations for obj in ann.objects):
+            raise ValueError("a ground-truth object has more than 64 parts; the object matcher tracks them in a 64-bit mask")
 
         def pack(rows):
             width = max(1, max((len(r) for r in rows), default=0))
@@ -186,21 +258,26 @@ class Evaluator:
             img_w, img_h = ann.img_size
             scale[b] = (img_w / self.args.width, img_h / self.args.height, min(ann.img_size) * self.args.dist_threshold,
                         min(ann.img_size))
-        return pack(rows_a), pack(rows_p), torch.from_numpy(scale).to(device)
+        owner = np.zeros((len(annotations), max(1, max((len(o) for o in owners), default=0))), dtype=np.int32)
+        for b, row in enumerate(owners):
+            owner[b, : len(row)] = row
+        return pack(rows_a), pack(rows_p), torch.from_numpy(scale).to(device), torch.from_numpy(owner).to(device)
 
     # -- the batched equivalent of accumulate(prediction, annotation, raw_parts) -------------------
-    def accumulate_packed(self, packed: ops.PackedDetections, annotations, out_size, conf_thresh=None):
+    def accumulate_packed(self, packed: ops.PackedDetections, annotations, out_size, conf_thresh=None, eval_csi=False,
+                          eval_classif=False):
         """Add one decoded batch.  ``packed`` = ``ops.decode_packed(...)`` (device tensors),
         ``annotations`` = the batch's ground truth (``ImageAnnotation`` with ``img_size``, coordinates in the
         network-input frame, as the reference's dataset yields them), ``out_size`` = (W, H) of the heat maps.
-        Equivalent to ``accumulate(prediction, annotation, raw_parts)`` of the reference per image."""
+        Equivalent to ``accumulate(prediction, annotation, raw_parts, eval_csi, eval_classif)`` of the reference per
+        image (evaluator.py:226-242; ``evaluate`` passes True, True: cli/evaluate.py:43-45)."""
         conf = self.args.conf_threshold if conf_thresh is None else conf_thresh
         B, K = packed.anchor_inds.shape
         P = packed.part_inds.shape[1]
         assert len(annotations) == B
         device = packed.anchor_out.device
         M, N = len(self._label_index), len(self._part_index)
-        (gt_a, n_a, wa), (gt_p, n_p, wp), scale = self._pack_ground_truth(annotations, device)
+        (gt_a, n_a, wa), (gt_p, n_p, wp), scale, owner = self._pack_ground_truth(annotations, device)
         a_stats = torch.empty(B, M, 3, dtype=torch.int32, device=device)
         p_stats = torch.empty(B, N, 3, dtype=torch.int32, device=device)
         a_acc = torch.empty(B, K, dtype=torch.float64, device=device)
@@ -225,6 +302,38 @@ class Evaluator:
         host = [t.cpu().numpy() for t in (a_stats, p_stats, a_acc, p_acc, a_cls, p_cls)]
         self._absorb(self.anchor_eval, self._label_names, host[0], host[2], host[4])
         self._absorb(self.part_eval, self._part_names, host[1], host[3], host[5])
+        if not (eval_csi or eval_classif):
+            return
+        # ---- object-level metrics: eval_csi / compute_csi and eval_classif (evaluator.py:380-474, 539-581)
+        groups = torch.tensor([{"bean": 0, "maize": 1}.get(self._label_names.get(i), -1) for i in range(M)], dtype=torch.int32,
+                              device=device)
+        c_stats = torch.empty(B, M, 3, dtype=torch.int32, device=device)
+        k_stats = torch.empty(B, 20, 3, dtype=torch.int32, device=device)
+        c_acc = torch.empty(B, K, dtype=torch.float64, device=device)
+        k_acc = torch.empty(B, K, dtype=torch.float64, device=device)
+        n_parts = torch.empty(B, K, dtype=torch.int32, device=device)
+        op = _native.SdnetObjectMatchParams()
+        op.struct_size = ctypes.sizeof(_native.SdnetObjectMatchParams)
+        op.B, op.M, op.N, op.K, op.P = B, M, N, K, P
+        op.max_gt_objects, op.max_gt_parts = wa, wp
+        op.conf, op.sx, op.sy = float(conf), in_w / out_w, in_h / out_h
+        op.csi_threshold = float(getattr(self.args, "csi_threshold", 0.75))
+        op.anchor_out, op.part_out, op.assign = packed.anchor_out.data_ptr(), packed.part_out.data_ptr(), packed.assign.data_ptr()
+        op.image_scale = scale.data_ptr()
+        op.gt_objects, op.n_gt_objects = gt_a.data_ptr(), n_a.data_ptr()
+        op.gt_parts, op.gt_part_owner, op.n_gt_parts = gt_p.data_ptr(), owner.data_ptr(), n_p.data_ptr()
+        op.cls_group = groups.data_ptr()
+        op.csi_stats, op.csi_acc = c_stats.data_ptr(), c_acc.data_ptr()
+        op.classif_stats, op.classif_acc, op.pred_parts = k_stats.data_ptr(), k_acc.data_ptr(), n_parts.data_ptr()
+        _native.check(self.lib.sdnet_match_objects_launch(ctypes.byref(op), ctypes.c_void_p(stream)), "sdnet_match_objects_launch")
+        c_stats, k_stats, c_acc, k_acc, n_parts = (t.cpu().numpy() for t in (c_stats, k_stats, c_acc, k_acc, n_parts))
+        if eval_csi:
+            self._absorb(self.csi_eval, self._label_names, c_stats, c_acc, host[4])
+        if eval_classif:
+            group_np = groups.cpu().numpy()
+            key = np.where((n_parts >= 0) & (n_parts <= 9), group_np[np.clip(host[4], 0, M - 1)] * 10 + n_parts, -1)
+            key = np.where(group_np[np.clip(host[4], 0, M - 1)] >= 0, key, -1)
+            self._absorb(self.classification_eval, dict(enumerate(Evaluator.get_classification_labels())), k_stats, k_acc, key)
 
     @staticmethod
     def _absorb(target: Evaluations, names, stats, acc, cls):
@@ -237,11 +346,27 @@ class Evaluator:
             hit = (cls == index) & ~np.isnan(acc)
             res.acc += acc[hit].tolist()  # image-major, slot (= score) order: the order the reference appends in
 
+    def _results(self):
+        return {"Anchor Location": self.anchor_eval, "Part Location": self.part_eval, "All Kps Location": self.kps_eval,
+                "CSI": self.csi_eval, "Classification": self.classification_eval}
+
     def pretty_print(self):
-        for title, evals in (("Anchor Location", self.anchor_eval), ("Part Location", self.part_eval),
-                             ("All Kps Location", self.kps_eval)):
-            print(title)
-            for label, evaluation in evals.items():
-                print(" ", label, *evaluation.stats())
+        for title, evals in self._results().items():
+            _print_table(title, evals)
+
+    def save_kps_csv(self, path):
+        """label, recall, precision, f1, average localisation error per keypoint label (evaluator.py:606-626)."""
+        evals = self.kps_eval
+        lines = [",".join((label, str(evals[label].recall), str(evals[label].precision), str(evals[label].f1_score),
+                           str(evals[label].avg_acc))) for label in sorted(evals.labels)]
+        Path(path).write_text("\n".join(lines))
+
+    def __repr__(self):
+        text = ""
+        for title, evals in self._results().items():
+            text += f"{title}\n"
             if len(evals) > 1:
-                print("  Total", *evals.reduce().stats())
+                text += f"  total: {evals.reduce()}\n"
+            for label, evaluation in sorted(evals.items(), key=lambda item: item[0]):
+                text += f"  {label}: {evaluation}\n"
+        return text

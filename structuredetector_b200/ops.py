@@ -21,7 +21,8 @@ PEAKS_PATHS = ("warp", "tile", "tile_row_pairs")  # SDNET_PATH_* in include/sdne
 from ._native import (FLAG_EXACT_SELECT, FLAG_NO_GROUPING, FLAG_PRE_ACTIVATED, FLAG_WARP_KERNEL, SdnetDecodeParams,
                       SdnetSchedule, SdnetTensor4)
 
-__all__ = ["decode_packed", "activate_maps", "DecodePlan", "PackedDetections", "gpu_launches_per_decode"]
+__all__ = ["decode_packed", "activate_maps", "suppress_maps", "suppress_into", "DecodePlan", "DecodePipeline",
+           "PackedDetections", "gpu_launches_per_decode"]
 
 # kernels launched by one sdnet_decode_launch: peaks, exact-select, tail (+ one memset node)
 _KERNELS_PER_DECODE = 3
@@ -345,6 +346,16 @@ def _(hm, radius):
     return hm.new_empty(hm.shape, dtype=torch.float32)
 
 
+@torch.library.custom_op("sdnet_b200::suppress_into", mutates_args=("out",), device_types="cuda")
+def _suppress_into_op(hm: torch.Tensor, out: torch.Tensor, radius: int) -> None:
+    B, C, H, W = hm.shape
+    view, oview = _view4(hm), _view4(out)
+    with torch.cuda.device(hm.device):
+        rc = _native.load().sdnet_suppress_into_launch(ctypes.byref(view), _DTYPES[hm.dtype], B, C, H, W, radius, ctypes.byref(oview),
+                                                       ctypes.c_void_p(torch.cuda.current_stream(hm.device).cuda_stream))
+    _native.check(rc, "sdnet_suppress_into_launch")
+
+
 def _unit_w_stride(t: torch.Tensor) -> torch.Tensor:
     # a layout fix on the device, not a fallback: the kernels need the innermost stride to be 1
     return t if t.stride(3) == 1 else t.contiguous()
@@ -409,6 +420,16 @@ def activate_maps(hm: torch.Tensor) -> torch.Tensor:
     _check_tensor("heat map", hm)
     out = _activate_op(_unit_w_stride(hm))  # fp32 storage of values exactly representable in hm.dtype
     return out if hm.dtype == torch.float32 else out.to(hm.dtype)
+
+
+def suppress_into(hm: torch.Tensor, out: torch.Tensor, radius: int = 2) -> torch.Tensor:
+    """``nms(clamped_sigmoid(hm))`` written into ``out``, a float32 ``(B, C, H, W)`` view with unit innermost stride
+    (e.g. the first channels of a wider tensor): no intermediate tensor, no ``torch.cat`` afterwards."""
+    _check_tensor("heat map", hm)
+    if out.dtype != torch.float32 or out.shape != hm.shape or out.device != hm.device or out.stride(3) != 1:
+        raise ValueError("out must be a float32 view of hm's shape on hm's device with unit innermost stride")
+    _suppress_into_op(_unit_w_stride(hm), out, int(radius))
+    return out
 
 
 def suppress_maps(hm: torch.Tensor, radius: int = 2) -> torch.Tensor:

@@ -13,6 +13,7 @@ from oracle import evaluator_oracle as EO
 GOLDEN = Path(__file__).parent / "golden"
 INDEX = json.loads((GOLDEN / "index.json").read_text())
 EVAL = json.loads((GOLDEN / "eval.json").read_text())
+EVAL_OBJECTS = json.loads((GOLDEN / "eval_objects.json").read_text())  # eval_csi + eval_classif of the same cases
 
 
 def _names(name):
@@ -31,14 +32,73 @@ def test_oracle_reproduces_reference_evaluator(name):
             assert acc == want["acc"], (name, key, label)  # same Python-float arithmetic: bit-exact
 
 
-def test_live_reference_evaluator_agrees_with_fixture():
+@pytest.mark.parametrize("script", ["make_golden_eval.py", "make_golden_eval_objects.py"])
+def test_live_reference_evaluator_agrees_with_fixture(script):
     ref = Path("/root/reference/src")
     if not ref.exists():
         pytest.skip("reference not present (GPU box)")
     import subprocess, sys
-    out = subprocess.run([sys.executable, str(GOLDEN / "make_golden_eval.py"), "--check"], capture_output=True, text=True,
+    out = subprocess.run([sys.executable, str(GOLDEN / script), "--check"], capture_output=True, text=True,
                          env={"PYTHONDONTWRITEBYTECODE": "1", "PATH": "/usr/bin:/bin"}, cwd=str(GOLDEN.parent.parent))
     assert out.returncode == 0, out.stderr[-2000:]
+
+
+def _object_case(name):
+    """eval.json's ground truth + eval_objects.json's thresholds and expected CSI / classification tables."""
+    return {**EVAL[name], "csi_threshold": EVAL_OBJECTS[name]["csi_threshold"]}, EVAL_OBJECTS[name]
+
+
+@pytest.mark.parametrize("name", sorted(EVAL_OBJECTS))
+def test_oracle_reproduces_reference_object_metrics(name):
+    """eval_csi / compute_csi / eval_classif (evaluator.py:380-474, 539-581) restated, against what the reference's own
+    Evaluator.accumulate(..., True, True) produced: counts and every accumulated value bit for bit."""
+    case, want = _object_case(name)
+    labels, _ = _names(name)
+    got = EO.evaluate_objects_batch(INDEX[name]["annotation"], case, labels, rename=want["rename"])
+    for key in ("csi", "classification"):
+        for label, w in want["result"][key].items():
+            tp, npos, ndet, acc = got[key][label]
+            assert (tp, npos, ndet) == (w["tp"], w["npos"], w["ndet"]), (name, key, label)
+            assert acc == w["acc"], (name, key, label)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(EVAL_OBJECTS))
+def test_cuda_object_matching_reproduces_reference_evaluator(cuda_device, name):
+    """sdnet_match_objects_launch on the packed detections against the reference's Decoder + Evaluator on CPU:
+    counts exact, CSI values exact ratios of small integers, localisation errors to 1e-9 relative."""
+    from structuredetector_b200 import ImageAnnotation, Keypoint, Object, ops
+    from structuredetector_b200.evaluator import Evaluator
+    from structuredetector_b200.synth import split_outputs
+    meta = INDEX[name]
+    case, want = _object_case(name)
+    rename = want["rename"]
+    _, m, n, h, w = meta["shape"]
+    labels, kinds = _names(name)
+    labels = [rename.get(l, l) for l in labels]
+    raw = torch.from_numpy(np.load(GOLDEN / f"{name}.npz")["raw"]).to(cuda_device)
+    packed = ops.decode_packed(split_outputs(raw, m, n), meta["K"], meta["P"], meta["conf"], meta["dist"])
+    args = SimpleNamespace(labels={l: i for i, l in enumerate(labels)}, parts={k: i for i, k in enumerate(kinds)},
+                           width=case["width"], height=case["height"], dist_threshold=case["dist_threshold"],
+                           conf_threshold=meta["conf"], down_ratio=meta["down_ratio"], csi_threshold=case["csi_threshold"])
+    anns = []
+    for image in case["images"]:
+        objs = [Object(rename.get(nm, nm), Keypoint("stem", x, y), [Keypoint(k, px, py) for k, px, py in kps]) for nm, x, y, kps in image["gt"]]
+        anns.append(ImageAnnotation("gt", objs, img_size=tuple(image["img_size"])))
+    ev = Evaluator(args)
+    ev.accumulate_packed(packed, anns, (w, h), eval_csi=True, eval_classif=True)
+    for key, evals in (("csi", ev.csi_eval), ("classification", ev.classification_eval)):
+        assert set(evals.labels) == set(want["result"][key])
+        for label, wnt in want["result"][key].items():
+            got = evals[label]
+            assert (got.tp, got.npos, got.ndet) == (wnt["tp"], wnt["npos"], wnt["ndet"]), (name, key, label)
+            np.testing.assert_allclose(got.acc, wnt["acc"], rtol=1e-9, atol=0)
+    # the location tables are unaffected by the extra flags
+    for key, evals in (("anchor", ev.anchor_eval), ("part", ev.part_eval)):
+        for label, wnt in EVAL[name]["result"][key].items():
+            label = rename.get(label, label)
+            assert (evals[label].tp, evals[label].npos, evals[label].ndet) == (wnt["tp"], wnt["npos"], wnt["ndet"])
+    assert "CSI" in repr(ev) and "Classification" in repr(ev)
 
 
 def _annotations(case):
@@ -150,6 +210,11 @@ def test_evaluation_classes_mirror_the_reference_formulas():
     parts["p0"] += Evaluation(tp=2, npos=2, ndet=3, acc=[0.2, 0.3])
     merged = both | parts
     assert set(merged.labels) == {"l0", "l1", "p0"} and merged.reduce().tp == 6
+    acc = Evaluations(["l0"])
+    acc["l0"] += Evaluation(tp=1, npos=1, ndet=1, acc=[0.4])
+    acc |= both          # in-place union: shared labels summed, new ones adopted (evaluator.py:180-185)
+    assert set(acc.labels) == {"l0", "l1"} and acc["l0"].tp == 4 and acc["l1"].tp == 1
+    assert [c if isinstance(c, str) else c.header for c in Evaluation.columns()] == list(Evaluation.COLUMNS)
     ref_src = Path("/root/reference/src")
     if ref_src.exists():
         import sys
@@ -185,7 +250,8 @@ def test_ground_truth_packing_host_logic():
                               Object("weed", Keypoint("stem", 5.0, 6.0), [Keypoint("flower", 7.0, 8.0)])], img_size=(2048, 1024)),
         ImageAnnotation("b", [], img_size=(1000, 3000)),
     ]
-    (gt_a, n_a, wa), (gt_p, n_p, wp), scale = ev._pack_ground_truth(anns, torch.device("cpu"))
+    (gt_a, n_a, wa), (gt_p, n_p, wp), scale, owner = ev._pack_ground_truth(anns, torch.device("cpu"))
+    assert owner.tolist() == [[0, 0, 1], [0, 0, 0]]  # object index of every ground-truth part (object order)
     assert (wa, wp) == (2, 3) and n_a.tolist() == [2, 0] and n_p.tolist() == [3, 0]
     assert gt_a[0].tolist() == [[10.0, 20.0, 1.0], [5.0, 6.0, -1.0]]
     assert gt_p[0].tolist() == [[1.0, 2.0, 0.0], [3.0, 4.0, 0.0], [7.0, 8.0, -1.0]]

@@ -5,7 +5,7 @@ import pytest
 import torch
 
 from oracle import torch_port as TP
-from structuredetector_b200 import CoreMLDecoder, Decoder, RawDecoder, ops
+from structuredetector_b200 import CoreMLDecoder, CoreMLModel, Decoder, RawDecoder, ops
 from structuredetector_b200.synth import CONFIGS, DecodeConfig, make_raw, split_outputs
 from tests.helpers import make_args, plain
 
@@ -48,3 +48,41 @@ def test_raw_decoder_feeds_coreml_decoder(cuda_device, name, mode):
     via_coreml = CoreMLDecoder(args)(split_outputs(baked, cfg.labels, cfg.parts))
     direct = Decoder(args)(split_outputs(raw, cfg.labels, cfg.parts))
     assert plain(via_coreml) == plain(direct)
+
+
+def test_coreml_model_wrapper_bakes_the_heat_maps(cuda_device):
+    """CoreMLModel(model, args) = the network followed by RawDecoder (convert_coreml.py:21-29): a stand-in head producing the raw
+    (B, M+N+4, H, W) tensor, checked against the reference's op sequence and decoded through CoreMLDecoder."""
+    from types import SimpleNamespace
+
+    cfg = CONFIGS["cfg3"]
+    raw = make_raw(cfg, "blobs", batch=2).to(cuda_device)
+
+    class Head(torch.nn.Module):  # plays the network: returns the stored raw output whatever the image
+        def forward(self, image):
+            return raw
+
+    args = make_args(cfg)
+    args.labels, args.parts = {"bean": 0, "maize": 1}, {"leaf": 0}
+    module = CoreMLModel(Head(), args)
+    baked = module(torch.zeros(2, 3, 8, 8, device=cuda_device))
+    nb = cfg.labels + cfg.parts
+    assert torch.equal(baked[:, :nb], _reference_maps(raw[:, :nb])) and torch.equal(baked[:, nb:], raw[:, nb:])
+    assert plain(CoreMLDecoder(args)(split_outputs(baked, cfg.labels, cfg.parts))) == plain(Decoder(args)(split_outputs(raw, cfg.labels, cfg.parts)))
+
+
+@pytest.mark.parametrize("path", ["tile", "w"])
+def test_suppress_into_strided_output(cuda_device, path, monkeypatch):
+    """sdnet_suppress_into_launch: the result lands in the first channels of a wider tensor (strided output), on both kernels
+    (the per-lane one is forced through a 4-byte-misaligned input view)."""
+    cfg = DecodeConfig("supinto", 3, 3, 2, 70, 132, 1, 1, cfg_id=33)
+    raw = make_raw(cfg, "noise").to(cuda_device)
+    if path == "w":
+        wide = torch.zeros(3, 9, 70, 133, device=cuda_device)
+        wide[..., 1:] = raw
+        raw_in = wide[..., 1:]  # rows start 4 bytes off a 16-byte boundary: TMA cannot describe them
+    else:
+        raw_in = raw
+    out = torch.full((3, 9, 70, 132), -7.0, device=cuda_device)
+    ops.suppress_into(raw_in[:, :5], out[:, :5])
+    assert torch.equal(out[:, :5], _reference_maps(raw[:, :5])) and bool((out[:, 5:] == -7.0).all())

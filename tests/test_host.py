@@ -178,3 +178,35 @@ def test_c_object_assembly_matches_the_oracle(conf):
     assert clone.objects[0].anchor.x == x0 / 2 and first.anchor.x == x0
     first.parts.append(Keypoint("part0", 1.0, 2.0, 0.5))
     assert first.nb_parts >= 1
+
+
+@pytest.mark.parametrize("with_sizes", [False, True])
+def test_packed_json_writer_equals_json_repr(tmp_path, with_sizes):
+    """Decoder._json_from_host (csrc/fastobj.c json_text): the documents `detect` saves (cli/detect.py:41-52 ->
+    utils.py:275-286), straight from the packed rows, byte for byte what json.dumps(annotation.json_repr(), indent=2)
+    gives for the assembled (and, with image sizes, resized) annotations -- empty images, non-ASCII names included."""
+    from types import SimpleNamespace
+
+    from structuredetector_b200 import Decoder
+
+    rng = np.random.default_rng(21)
+    B, K, P, M, N = 4, 17, 23, 2, 2
+    conf = 0.4
+    host = _random_packed(rng, B, K, P, M, N, conf)
+    host.anchor_out.numpy()[1, :, 2] = 0.1  # an image without objects: "objects": []
+    host.anchor_out.numpy()[2, 0, :2] = (1e-7, 123456789.0)  # float repr corner cases
+    labels, kinds = {0: "bean", 1: 'ma"ïze'}, {0: "leaf", 1: "feuille\\n"}
+    dec = Decoder(SimpleNamespace(_r_labels=labels, _r_parts=kinds, anchor_name="stem", down_ratio=4.0, max_objects=K,
+                                  max_parts=P, conf_threshold=conf, decoder_dist_thresh=0.1))
+    out_size, in_size = (612, 512), (2448, 2048)
+    paths = [tmp_path / f"img_{b}.jpg" for b in range(B)] if with_sizes else None
+    sizes = [(4000 + 13 * b, 3000 + 7 * b) for b in range(B)] if with_sizes else None
+    texts = dec._json_from_host(host, conf, out_size, in_size, paths, sizes, in_size if with_sizes else None)
+    anns = dec._assemble(host, conf, out_size, in_size)
+    for b, (ann, text) in enumerate(zip(anns, texts)):
+        if with_sizes:  # what detect.py does with the decoder's annotation
+            ann.resize(in_size, sizes[b])
+            ann.img_size = sizes[b]
+            ann.image_path = paths[b]
+        assert text == json.dumps(ann.json_repr(), indent=2), f"image {b}"
+        assert json.loads(text)["objects"] == ann.json_repr()["objects"]
