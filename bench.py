@@ -62,7 +62,7 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--pipeline", type=int, default=0,
                     help="decodes in flight: consecutive steps alternate between this many plans/streams; 0 = auto "
-                         "(2 for shards of >= 512 images, 4 for smaller ones)")
+                         "(3 for shards of >= 512 images, 4 down to 161, 6 for smaller ones)")
     ap.add_argument("--gather", choices=("fused", "nccl"), default="fused",
                     help="N > 1: tail kernel stores into every peer (symmetric memory) + barrier, or ncclAllGather")
     return ap.parse_args()
@@ -354,7 +354,10 @@ def main():
     # Software pipeline over batches: consecutive steps alternate between `depth` plans (own workspace,
     # own outputs, own gather buffer) on `depth` streams, so one batch's tail kernel and gather overlap
     # the next batch's peaks kernel.  --pipeline 1 = strictly one decode at a time.
-    depth = args.pipeline if args.pipeline > 0 else (2 if shard >= 512 else 4)
+    # measured on one B200 (profiles/r02_pipeline_depth.log): 1024 images 0.806 / 0.784 / 0.774 ms per step at depth 1 / 2 / 3;
+    # 128 images 0.139 / 0.122 / 0.117 ms at 2 / 4 / 6 -- consecutive kernels overlap at their ends, and a small shard's
+    # kernel is all warm-up at its start and all streaming at its end, so more of them in flight mix those phases
+    depth = args.pipeline if args.pipeline > 0 else (3 if shard >= 512 else (4 if shard > 160 else 6))
     pipe = None
     if depth > 1:
         if fused is not None:

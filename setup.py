@@ -13,6 +13,9 @@ class BuildWithCuda(build_py):
         mod = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(mod)
         mod.build(force=False)
+        # the public C header travels with the package data, so an installed copy can rebuild its libraries
+        root = Path(__file__).parent
+        (root / "structuredetector_b200" / "csrc" / "sdnet_decode.h").write_bytes((root / "include" / "sdnet_decode.h").read_bytes())
         super().run()
 
 

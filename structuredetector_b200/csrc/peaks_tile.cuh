@@ -35,7 +35,7 @@ constexpr int kTileNG = SDNET_X_NG;   // ring slots (tiles) per warp: a group re
 #ifndef SDNET_X_FLUSH_AT
 #define SDNET_X_FLUSH_AT 16
 #endif
-constexpr int kWork = 128;   // per-warp work list: one byte per (row of the group, lane) whose 16-byte word holds a pixel above the floor
+constexpr int kWork = 256;   // per-warp work list: one byte per (row of the group, run of four columns) that holds a pixel above the floor
 constexpr int kFlushAt = SDNET_X_FLUSH_AT;  // buffered candidates that trigger a flush once the plane has a floor
 // S = rows per TMA row (see the kernel).  Under S = 2 a tile arrives as two 2-row boxes and a TMA
 // destination must be 128-byte aligned: the second box sits at +1152 and a slot takes 2304 bytes.
@@ -88,6 +88,8 @@ struct TileMax<SDNET_DTYPE_F32> {
   static __device__ __forceinline__ float group(const uint4& a, const uint4& b, const uint4& c, const uint4& d) {
     return fmaxf(fmaxf(word(a), word(b)), fmaxf(word(c), word(d)));
   }
+  static __device__ __forceinline__ float half_lo(const uint4& a) { return word(a); }  // (fp32 words are not split)
+  static __device__ __forceinline__ float half_hi(const uint4& a) { return word(a); }
   static __device__ __forceinline__ float elem(u32 addr) {
     float v;
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
@@ -104,6 +106,8 @@ struct TileMax<SDNET_DTYPE_F16> {
   static __device__ __forceinline__ __half2 word2(const uint4& a) { return __hmax2(__hmax2(h2(a.x), h2(a.y)), __hmax2(h2(a.z), h2(a.w))); }
   static __device__ __forceinline__ float fold(__half2 m) { return __half2float(__hmax(__low2half(m), __high2half(m))); }
   static __device__ __forceinline__ float word(const uint4& a) { return fold(word2(a)); }
+  static __device__ __forceinline__ float half_lo(const uint4& a) { return fold(__hmax2(h2(a.x), h2(a.y))); }  // pixels 0..3
+  static __device__ __forceinline__ float half_hi(const uint4& a) { return fold(__hmax2(h2(a.z), h2(a.w))); }  // pixels 4..7
   static __device__ __forceinline__ float group(const uint4& a, const uint4& b, const uint4& c, const uint4& d) {
     return fold(__hmax2(__hmax2(word2(a), word2(b)), __hmax2(word2(c), word2(d))));
   }
@@ -130,6 +134,8 @@ struct TileMax<SDNET_DTYPE_BF16> {
   static __device__ __forceinline__ __nv_bfloat162 word2(const uint4& a) { return __hmax2(__hmax2(h2(a.x), h2(a.y)), __hmax2(h2(a.z), h2(a.w))); }
   static __device__ __forceinline__ float fold(__nv_bfloat162 m) { return __bfloat162float(__hmax(__low2bfloat16(m), __high2bfloat16(m))); }
   static __device__ __forceinline__ float word(const uint4& a) { return fold(word2(a)); }
+  static __device__ __forceinline__ float half_lo(const uint4& a) { return fold(__hmax2(h2(a.x), h2(a.y))); }
+  static __device__ __forceinline__ float half_hi(const uint4& a) { return fold(__hmax2(h2(a.z), h2(a.w))); }
   static __device__ __forceinline__ float group(const uint4& a, const uint4& b, const uint4& c, const uint4& d) {
     return fold(__hmax2(__hmax2(word2(a), word2(b)), __hmax2(word2(c), word2(d))));
   }
@@ -159,15 +165,24 @@ __device__ __forceinline__ u32 ring_row_off(u32 rr) {
   return (rr >> 2) * tile_slot_bytes(2) + (rr & 1u) * (kOddBoxOff + kOddShiftB) + ((rr >> 1) & 1u) * kTilePitchB;
 }
 
+#ifndef SDNET_X_TRACE
+#define SDNET_X_TRACE 0
+#endif
+#ifndef SDNET_X_WARMPOLL
+#define SDNET_X_WARMPOLL 1  // poll the published floor every group, synchronously, while this warp has none
+#endif
+#ifndef SDNET_X_EARLYFLUSH
+#define SDNET_X_EARLYFLUSH 0  // 1: flush after every group while the plane has no floor (the pre-early-histogram rule)
+#endif
 #ifndef SDNET_X_QUICK
 #define SDNET_X_QUICK 1  // settle_entries: reject flank pixels on their four direct neighbours before the full window
 #endif
 #ifndef SDNET_X_EARLYHIST
 #define SDNET_X_EARLYHIST 1  // count a candidate in the plane-wide histogram when it is found, not when it is flushed
 #endif
-// Settle the work list of one 4-row group.  Entry e = (row in group << 5) | lane names one 16-byte
-// word of centre pixels holding at least one pixel above the floor; kPx consecutive lanes take the
-// pixels of an entry, so records leave in (row, column) = index order.  A lane whose pixel beats the
+// Settle the work list of one 4-row group.  Entry e = (row in group << 6) | q names FOUR consecutive centre
+// pixels (columns 4 q .. 4 q + 3 of the panel: a 16-byte word of fp32, half a word of fp16 / bf16) holding at
+// least one pixel above the floor; four consecutive lanes take the pixels of an entry.  A lane whose pixel beats the
 // floor reads the pixel's (2R+1)^2 window from the ring with scalar loads (columns and rows outside
 // the image hold NaN or -inf and never win a max), classifies it like classify_row and appends a
 // (logit, index) record to the warp's candidate buffer.
@@ -181,11 +196,11 @@ __device__ __forceinline__ void settle_entries(UnitState& st, const unsigned cha
                   kHiZone2 = Num<DT>::kHi2;
   constexpr u32 kRingRows = kTileNG * kGroupRows;
   constexpr int kPx = TileGeom<DT>::kPx, kEsz = TileGeom<DT>::kEsz;
-  const int nslots = kPx * nent;
+  const int nslots = 4 * nent;
   for (int base = 0; base < nslots; base += 32) {  // warp-uniform
     const int slot = base + lane;
-    const u32 e = slot < nslots ? work[slot / kPx] : 0u;
-    const u32 i = e >> 5, colp = kPx * (e & 31u) + (u32)(slot % kPx);
+    const u32 e = slot < nslots ? work[slot >> 2] : 0u;
+    const u32 i = e >> 6, colp = 4u * (e & 63u) + (u32)(slot & 3);
     const u32 col_addr = ring_s + (kPx + colp - R) * kEsz;  // first column of the window
     // byte offsets of the window's rows.  Plain rows: a multiply.  Row pairs: the slot layout makes that
     // eight instructions per row, so lane k keeps the offset of ring row k (row_tab) and a shuffle looks it up
@@ -407,6 +422,15 @@ __device__ __forceinline__ void tile_fix_edges(u32 slot_s, int x0, int W, int la
 // at pitch + x - 4 (a box has to start on a 16-byte boundary, measured: anything else is an illegal
 // instruction) -- and lands in its slot as rows 0, 2 | 1, 3 with the odd rows 8 bytes further right.
 // At the image edges such a box reads across the row boundary; tile_fix_edges repairs that after the wait.
+#if SDNET_X_TRACE  // diagnostics builds only (tools/xbuild.sh -DSDNET_X_TRACE=1): per-warp timeline of the last launch
+__device__ unsigned long long g_tile_trace[8192 * 4];  // [warp]: start, first tile landed, end (globaltimer ns), groups << 32 | units
+__device__ __forceinline__ unsigned long long trace_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#endif
+
 template <int R, int DT, int S>
 __global__ void __launch_bounds__(kTileWarps * 32, kTileMinCtas)
 sdnet_peaks_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_constant__ CUtensorMap tm_anchor,
@@ -451,11 +475,18 @@ sdnet_peaks_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_cons
   auto step_pos = [&](u32& slot, u32& par) {
     if (++slot == (u32)NG) { slot = 0; par ^= 1u; }
   };
+#if SDNET_X_TRACE
+  const unsigned long long tr_start = trace_now();
+  unsigned long long tr_first = 0, tr_groups = 0, tr_units = 0;
+#endif
   for (;;) {
     u32 unit = 0;
     if (lane == 0) unit = atomicAdd(p.sched, 1u);
     unit = __shfl_sync(0xffffffffu, unit, 0);
     if (unit >= (u32)p.units) break;
+#if SDNET_X_TRACE
+    ++tr_units;
+#endif
     // the unit's piece of the line of groups; it is walked one column segment at a time
     u32 pos, pos_end;
     if (unit < (u32)p.tier1_units) {
@@ -530,11 +561,23 @@ sdnet_peaks_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_cons
     constexpr int poll_mask = 3;  // measured at 128-row strips: polling every group 0.179 ms, every 4th 0.136 ms, every 8th 0.146 ms
     u32 idx0 = (u32)(r_begin * W + panel * kPanel);  // flat index of the group's row 0, panel column 0
     wait_tile(cur_slot, cur_par);
+#if SDNET_X_TRACE
+    if (!tr_first) tr_first = trace_now();
+    tr_groups += (unsigned long long)groups_out;
+#endif
     for (int g = 0; g < groups_out; ++g, idx0 += (u32)(kGroupRows * W)) {
       // cur_* = the tile holding the group's first window row, nxt_* = the one after it
       u32 nxt_slot = cur_slot, nxt_par = cur_par;
       step_pos(nxt_slot, nxt_par);
       if (R == 2 || g + 1 < groups) wait_tile(nxt_slot, nxt_par);
+#if SDNET_X_WARMPOLL
+      if (gfloor_seen <= 0 && g > 0) {
+        // The plane has no floor that this warp knows of: every pixel it looks at goes through the slow path, so a
+        // fresh look at the published floor is worth its latency (one L2 round trip) -- every group, applied at once.
+        gfloor_seen = __ldcg(gfloor_ptr);
+        st.floorx = fmaxf(st.floorx, shared_floor<DT>(gfloor_seen, xscale));
+      } else
+#endif
       if ((g & poll_mask) == 0) {
         // every 16 rows: apply the plane-wide floor fetched one period ago
         // and start the next fetch.  The load writes straight into the register it will be read
@@ -580,17 +623,28 @@ sdnet_peaks_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_cons
 #pragma unroll
           for (int i = 0; i < kGroupRows; ++i) {
             const uint4 ci = i == 0 ? c0 : (i == 1 ? c1 : (i == 2 ? c2 : c3));
-            const bool mine = TileMax<DT>::word(ci) > floorx && i < rows_here;
-            const u32 bm = __ballot_sync(0xffffffffu, mine);
-            if (mine) work[nent + __popc(bm & lt)] = (unsigned char)((i << 5) | lane);
-            nent += __popc(bm);
+            if (DT == SDNET_DTYPE_F32) {
+              const bool mine = TileMax<DT>::word(ci) > floorx && i < rows_here;
+              const u32 bm = __ballot_sync(0xffffffffu, mine);
+              if (mine) work[nent + __popc(bm & lt)] = (unsigned char)((i << 6) | lane);
+              nent += __popc(bm);
+            } else {  // 8 pixels per lane: list the two halves of the word separately, so that a pass settles 8 entries, not 4
+              const bool lo = TileMax<DT>::half_lo(ci) > floorx && i < rows_here, hi = TileMax<DT>::half_hi(ci) > floorx && i < rows_here;
+              const u32 bl = __ballot_sync(0xffffffffu, lo), bh = __ballot_sync(0xffffffffu, hi);
+              if (lo) work[nent + __popc(bl & lt)] = (unsigned char)((i << 6) | (2 * lane));
+              nent += __popc(bl);
+              if (hi) work[nent + __popc(bh & lt)] = (unsigned char)((i << 6) | (2 * lane + 1));
+              nent += __popc(bh);
+            }
           }
           __syncwarp();
           settle_entries<R, DT, S>(st, work, nent, ring_s, row0, row_tab, floorx, idx0, W, pre, buf, hist, minx, sf, count_ptr, list,
                                    p.cap, K, lane, xscale, satx);
         }
         // while the plane has no floor yet, publish early and often; later only in batches
-        if (st.nbuf >= kFlushAt || (st.nbuf > 0 && gfloor_seen <= 0)) {
+        // (candidates are counted in the plane-wide histogram when they are found, so a flush is no longer what
+        // publishes them: while the plane has no floor, flushing after every group only added its latency)
+        if (st.nbuf >= kFlushAt || (SDNET_X_EARLYFLUSH && st.nbuf > 0 && gfloor_seen <= 0)) {
           __syncwarp();
           flush_candidates<DT, !SDNET_X_EARLYHIST>(st, buf, hist, minx, sf, count_ptr, list, p.cap, K, lane, pre, xscale, satx);
         }
@@ -613,6 +667,15 @@ sdnet_peaks_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_cons
     }
     }  // segments of the unit
   }
+#if SDNET_X_TRACE
+  if (lane == 0) {
+    const u32 w = blockIdx.x * kTileWarps + warp;
+    if (w < 8192) {
+      g_tile_trace[4 * w + 0] = tr_start; g_tile_trace[4 * w + 1] = tr_first; g_tile_trace[4 * w + 2] = trace_now();
+      g_tile_trace[4 * w + 3] = (tr_groups << 32) | tr_units;
+    }
+  }
+#endif
 }
 
 

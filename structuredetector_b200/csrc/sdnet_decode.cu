@@ -308,6 +308,11 @@ cudaError_t plan_peaks(const SdnetDecodeParams* p, PeaksParams& pp, PeaksPlan& p
     cudaError_t err = cudaSuccess;
     pl.ctas_per_sm = tile_ctas_per_sm(pl.tile_kern, p->dtype, pl.tile_s, p->radius, pl.smem, &err);
     if (pl.ctas_per_sm <= 0) return err != cudaSuccess ? err : cudaErrorUnknown;
+    static const int occ_cap = [] {  // tuning knob, read once: SDNET_PEAKS_OCC = resident CTAs per SM one launch may take
+      const char* e = getenv("SDNET_PEAKS_OCC");
+      return e ? atoi(e) : 0;
+    }();
+    if (occ_cap > 0 && occ_cap < pl.ctas_per_sm) pl.ctas_per_sm = occ_cap;
     pp.panels = (p->W + panel_cols - 1) / panel_cols;
     // The work is a line of `columns` x G groups of four rows (a column = one panel of one plane, top to
     // bottom), cut into units handed out in order by an atomic counter.  Long units prune best (a unit
@@ -514,6 +519,13 @@ int sdnet_decode_peaks_path(const SdnetDecodeParams* params) {
   int tile_s = 0;
   return select_peaks_path(params, &a, &b, &tile_s);
 }
+
+#if SDNET_X_TRACE
+// diagnostics builds only: copy out the per-warp timeline of the last fp32 tile-kernel launch (4 u64 per warp)
+int sdnet_debug_trace(unsigned long long* out, int n_warps) {
+  return (int)cudaMemcpyFromSymbol(out, g_tile_trace, sizeof(unsigned long long) * 4 * (size_t)n_warps);
+}
+#endif
 
 int sdnet_decode_schedule(const SdnetDecodeParams* params, SdnetSchedule* out) {
   const int rc = validate(params);
