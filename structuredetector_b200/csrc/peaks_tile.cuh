@@ -35,7 +35,7 @@ constexpr int kTileNG = SDNET_X_NG;   // ring slots (tiles) per warp: a group re
 #ifndef SDNET_X_FLUSH_AT
 #define SDNET_X_FLUSH_AT 16
 #endif
-constexpr int kWork = 256;   // per-warp work list: one byte per (row of the group, run of four columns) that holds a pixel above the floor
+constexpr int kWork = 128;   // per-warp work list: one byte per (row of the group, lane) whose 16-byte word holds a pixel above the floor
 constexpr int kFlushAt = SDNET_X_FLUSH_AT;  // buffered candidates that trigger a flush once the plane has a floor
 // S = rows per TMA row (see the kernel).  Under S = 2 a tile arrives as two 2-row boxes and a TMA
 // destination must be 128-byte aligned: the second box sits at +1152 and a slot takes 2304 bytes.
@@ -88,8 +88,6 @@ struct TileMax<SDNET_DTYPE_F32> {
   static __device__ __forceinline__ float group(const uint4& a, const uint4& b, const uint4& c, const uint4& d) {
     return fmaxf(fmaxf(word(a), word(b)), fmaxf(word(c), word(d)));
   }
-  static __device__ __forceinline__ float half_lo(const uint4& a) { return word(a); }  // (fp32 words are not split)
-  static __device__ __forceinline__ float half_hi(const uint4& a) { return word(a); }
   static __device__ __forceinline__ float elem(u32 addr) {
     float v;
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
@@ -106,8 +104,6 @@ struct TileMax<SDNET_DTYPE_F16> {
   static __device__ __forceinline__ __half2 word2(const uint4& a) { return __hmax2(__hmax2(h2(a.x), h2(a.y)), __hmax2(h2(a.z), h2(a.w))); }
   static __device__ __forceinline__ float fold(__half2 m) { return __half2float(__hmax(__low2half(m), __high2half(m))); }
   static __device__ __forceinline__ float word(const uint4& a) { return fold(word2(a)); }
-  static __device__ __forceinline__ float half_lo(const uint4& a) { return fold(__hmax2(h2(a.x), h2(a.y))); }  // pixels 0..3
-  static __device__ __forceinline__ float half_hi(const uint4& a) { return fold(__hmax2(h2(a.z), h2(a.w))); }  // pixels 4..7
   static __device__ __forceinline__ float group(const uint4& a, const uint4& b, const uint4& c, const uint4& d) {
     return fold(__hmax2(__hmax2(word2(a), word2(b)), __hmax2(word2(c), word2(d))));
   }
@@ -134,8 +130,6 @@ struct TileMax<SDNET_DTYPE_BF16> {
   static __device__ __forceinline__ __nv_bfloat162 word2(const uint4& a) { return __hmax2(__hmax2(h2(a.x), h2(a.y)), __hmax2(h2(a.z), h2(a.w))); }
   static __device__ __forceinline__ float fold(__nv_bfloat162 m) { return __bfloat162float(__hmax(__low2bfloat16(m), __high2bfloat16(m))); }
   static __device__ __forceinline__ float word(const uint4& a) { return fold(word2(a)); }
-  static __device__ __forceinline__ float half_lo(const uint4& a) { return fold(__hmax2(h2(a.x), h2(a.y))); }
-  static __device__ __forceinline__ float half_hi(const uint4& a) { return fold(__hmax2(h2(a.z), h2(a.w))); }
   static __device__ __forceinline__ float group(const uint4& a, const uint4& b, const uint4& c, const uint4& d) {
     return fold(__hmax2(__hmax2(word2(a), word2(b)), __hmax2(word2(c), word2(d))));
   }
@@ -180,9 +174,10 @@ __device__ __forceinline__ u32 ring_row_off(u32 rr) {
 #ifndef SDNET_X_EARLYHIST
 #define SDNET_X_EARLYHIST 1  // count a candidate in the plane-wide histogram when it is found, not when it is flushed
 #endif
-// Settle the work list of one 4-row group.  Entry e = (row in group << 6) | q names FOUR consecutive centre
-// pixels (columns 4 q .. 4 q + 3 of the panel: a 16-byte word of fp32, half a word of fp16 / bf16) holding at
-// least one pixel above the floor; four consecutive lanes take the pixels of an entry.  A lane whose pixel beats the
+// Settle the work list of one 4-row group.  Entry e = (row in group << 5) | lane names one 16-byte
+// word of centre pixels holding at least one pixel above the floor; kPx consecutive lanes take the
+// pixels of an entry.  (Listing the two halves of a fp16 / bf16 word separately -- twice the ballots, half the
+// passes -- measured 2-3 % slower: 0.656 / 0.775 ms against 0.639 / 0.757 ms.)  A lane whose pixel beats the
 // floor reads the pixel's (2R+1)^2 window from the ring with scalar loads (columns and rows outside
 // the image hold NaN or -inf and never win a max), classifies it like classify_row and appends a
 // (logit, index) record to the warp's candidate buffer.
@@ -196,11 +191,11 @@ __device__ __forceinline__ void settle_entries(UnitState& st, const unsigned cha
                   kHiZone2 = Num<DT>::kHi2;
   constexpr u32 kRingRows = kTileNG * kGroupRows;
   constexpr int kPx = TileGeom<DT>::kPx, kEsz = TileGeom<DT>::kEsz;
-  const int nslots = 4 * nent;
+  const int nslots = kPx * nent;
   for (int base = 0; base < nslots; base += 32) {  // warp-uniform
     const int slot = base + lane;
-    const u32 e = slot < nslots ? work[slot >> 2] : 0u;
-    const u32 i = e >> 6, colp = 4u * (e & 63u) + (u32)(slot & 3);
+    const u32 e = slot < nslots ? work[slot / kPx] : 0u;
+    const u32 i = e >> 5, colp = kPx * (e & 31u) + (u32)(slot % kPx);
     const u32 col_addr = ring_s + (kPx + colp - R) * kEsz;  // first column of the window
     // byte offsets of the window's rows.  Plain rows: a multiply.  Row pairs: the slot layout makes that
     // eight instructions per row, so lane k keeps the offset of ring row k (row_tab) and a shuffle looks it up
@@ -610,8 +605,11 @@ sdnet_peaks_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_cons
         //   many (the first groups of a unit, before the plane has a floor worth the name): the whole maximum filter
         //   of the group once, in registers (settle_dense_f32);
         //   otherwise: list the hot 16-byte words, one ballot per row, and give every pixel of a listed word a
-        //   lane (settle_entries).  (Measured and dropped: giving every pixel of a hot lane's 4-row block a lane
-        //   without building the list -- more, emptier passes: 0.72 / 0.78 ms against 0.69 / 0.75 ms.)
+        //   lane (settle_entries).
+        // Measured and dropped (noise / blobs, 1024 images, against 0.69 / 0.74 ms): giving every pixel of a hot lane's
+        // 4-row block a lane without building the list -- more, emptier passes: 0.72 / 0.78 ms; parking the hot pixels
+        // of sparse groups and testing their windows 32 at a time from global memory (L2) -- the warp stalls on the
+        // scattered loads longer than the saved passes cost: 0.91 / 1.01 ms.
         const int nhot = __popc(hot), rows_here = nrows - g * kGroupRows;
         const float floorx = st.floorx;
         bool settled = false;
@@ -623,19 +621,10 @@ sdnet_peaks_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_cons
 #pragma unroll
           for (int i = 0; i < kGroupRows; ++i) {
             const uint4 ci = i == 0 ? c0 : (i == 1 ? c1 : (i == 2 ? c2 : c3));
-            if (DT == SDNET_DTYPE_F32) {
-              const bool mine = TileMax<DT>::word(ci) > floorx && i < rows_here;
-              const u32 bm = __ballot_sync(0xffffffffu, mine);
-              if (mine) work[nent + __popc(bm & lt)] = (unsigned char)((i << 6) | lane);
-              nent += __popc(bm);
-            } else {  // 8 pixels per lane: list the two halves of the word separately, so that a pass settles 8 entries, not 4
-              const bool lo = TileMax<DT>::half_lo(ci) > floorx && i < rows_here, hi = TileMax<DT>::half_hi(ci) > floorx && i < rows_here;
-              const u32 bl = __ballot_sync(0xffffffffu, lo), bh = __ballot_sync(0xffffffffu, hi);
-              if (lo) work[nent + __popc(bl & lt)] = (unsigned char)((i << 6) | (2 * lane));
-              nent += __popc(bl);
-              if (hi) work[nent + __popc(bh & lt)] = (unsigned char)((i << 6) | (2 * lane + 1));
-              nent += __popc(bh);
-            }
+            const bool mine = TileMax<DT>::word(ci) > floorx && i < rows_here;
+            const u32 bm = __ballot_sync(0xffffffffu, mine);
+            if (mine) work[nent + __popc(bm & lt)] = (unsigned char)((i << 5) | lane);
+            nent += __popc(bm);
           }
           __syncwarp();
           settle_entries<R, DT, S>(st, work, nent, ring_s, row0, row_tab, floorx, idx0, W, pre, buf, hist, minx, sf, count_ptr, list,
