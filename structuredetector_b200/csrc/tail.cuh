@@ -434,7 +434,17 @@ __global__ void __launch_bounds__(2 * kTeamThreads, 3) sdnet_tail_kernel(const _
       store_out(p, p.diag + ((size_t)b * C + c) * 2 + 1, p.exact_flags[(size_t)b * C + c]);
     }
   }
+#ifndef SDNET_X_TAILFENCE
+#define SDNET_X_TAILFENCE 1
+#endif
+#if SDNET_X_TAILFENCE == 1
   if (p.n_dest) __threadfence_system();  // peer stores performed before the kernel retires
+#elif SDNET_X_TAILFENCE == 2
+  if (p.n_dest) {  // one fence per CTA, after everybody's stores: fences are cumulative over what the barrier ordered
+    __syncthreads();
+    if (threadIdx.x == 0) __threadfence_system();
+  }
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------
