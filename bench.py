@@ -342,8 +342,10 @@ def main():
             from structuredetector_b200.parallel import FusedGatherPlan
 
             fused = FusedGatherPlan(device, cfg.batch, M, N, H, W, K, P, dtype=tdtype)
-            gather_kind = ("fused: tail kernel stores each rank's packed detections into every peer's copy "
-                           "(symmetric memory, st.global over NVLink) + one symmetric-memory barrier; results double-buffered")
+            how = ("one multimem.st per value to the blob's NVSwitch multicast mapping" if fused.stores == "multicast"
+                   else "one st.global per peer over NVLink")
+            gather_kind = (f"fused: tail kernel stores each rank's packed detections into every rank's copy (symmetric memory, {how}) "
+                           "+ one symmetric-memory barrier; results double-buffered")
         except Exception as exc:  # noqa: BLE001
             print(f"[bench] symmetric memory unavailable ({exc!r}); falling back to ncclAllGather", file=sys.stderr)
             fused = None
@@ -410,10 +412,13 @@ def main():
             ev1.record()
             fence()
         ms_total = ev0.elapsed_time(ev1)
+        by_rank = None
         if world > 1:
             t = torch.tensor([ms_total], dtype=torch.float64, device=device)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms_total = float(t.item())
+            every = torch.empty(world, dtype=torch.float64, device=device)
+            dist.all_gather_into_tensor(every, t)
+            by_rank = [round(v / args.steps, 5) for v in every.tolist()]
+            ms_total = max(every.tolist())  # the job's time is the slowest rank's
         ms_per_step = ms_total / args.steps
 
         # ---- one more (untimed) step through the timed objects, then look at what they produced
@@ -470,7 +475,7 @@ def main():
             kernel_ms["tail_storing_to_peers"] = statistics.mean(k[2] for k in fk)
             fence()
         per_mode[mode] = {
-            "value": cfg.batch / (ms_per_step * 1e-3), "ms_per_step": ms_per_step, "kernel_ms": kernel_ms,
+            "value": cfg.batch / (ms_per_step * 1e-3), "ms_per_step": ms_per_step, "ms_per_step_by_rank": by_rank, "kernel_ms": kernel_ms,
             "peaks_achieved_gbs": achieved, "peaks_frac": achieved / peak_gbs,
             "parity": parity, "gather_bit_exact": gather_ok, "clocks": clocks.summary(),
             "detections": {"anchors_above_conf": counts[0], "parts_above_conf": counts[1],

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SDNET_ABI_VERSION 7
+#define SDNET_ABI_VERSION 8
 
 /* element types of the four input tensors */
 #define SDNET_DTYPE_F32 0
@@ -53,6 +53,8 @@ extern "C" {
 #define SDNET_MAX_TOPK 1024
 #define SDNET_MAX_CHANNELS 255
 #define SDNET_MAX_DEST 16
+#define SDNET_DEST_PEER_STORES 0 /* SdnetDecodeParams.dest_mode: one st.global per destination */
+#define SDNET_DEST_MULTICAST 1   /* one multimem.st to the multicast address of the destination blob */
 
 /* A strided NCHW view.  Strides are in ELEMENTS.  The decoder consumes the channel-slice
  * views produced by the reference network (src/sdnet/model/network.py:79-84), which are
@@ -90,9 +92,12 @@ typedef struct SdnetDecodeParams {
    * (char*)ptr + dest_delta[j].  With the outputs placed in a symmetric (peer-mapped) allocation,
    * dest_delta[j] = peer_base[j] - local_base makes the tail kernel store each rank's detections
    * straight into every peer's copy over NVLink; one cross-GPU barrier afterwards replaces the
-   * all-gather.  Include 0 in dest_delta to also keep the local copy.  n_dest = 0: plain local stores. */
+   * all-gather.  Include 0 in dest_delta to also keep the local copy.  n_dest = 0: plain local stores.
+   * dest_mode = SDNET_DEST_MULTICAST (with n_dest = 1): dest_delta[0] = multicast_base - local_base, where
+   * multicast_base is the NVSwitch multicast mapping of the same symmetric allocation; every value is then
+   * stored ONCE with multimem.st and the switch replicates it into every GPU's copy (the local one included). */
   int32_t n_dest;
-  int32_t reserved0;
+  int32_t dest_mode; /* SDNET_DEST_* */
   int64_t dest_delta[SDNET_MAX_DEST];
 } SdnetDecodeParams;
 

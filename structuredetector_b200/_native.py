@@ -13,7 +13,8 @@ import os as _os
 
 # SDNET_DECODE_LIB: load another build of the same library (kernel experiments, tools/xbuild.sh)
 LIB_PATH = Path(_os.environ.get("SDNET_DECODE_LIB") or Path(__file__).resolve().parent / "csrc" / "libsdnet_decode.so").resolve()
-ABI_VERSION = 7
+ABI_VERSION = 8
+DEST_PEER_STORES, DEST_MULTICAST = 0, 1  # SdnetDecodeParams.dest_mode
 
 FLAG_PRE_ACTIVATED = 1
 FLAG_NO_GROUPING = 2
@@ -84,7 +85,7 @@ class SdnetDecodeParams(ctypes.Structure):
         ("workspace", ctypes.c_void_p),
         ("workspace_bytes", ctypes.c_size_t),
         ("n_dest", ctypes.c_int32),
-        ("reserved0", ctypes.c_int32),
+        ("dest_mode", ctypes.c_int32),
         ("dest_delta", ctypes.c_int64 * MAX_DEST),
     ]
 

@@ -22,11 +22,14 @@ constexpr int kGroupRows = 4;                                // output rows per 
 constexpr int kTileCols = kPanelW + 8;
 constexpr int kTilePitchB = kTileCols * 4;                   // 544 B per ring row
 constexpr int kTileBytes = kGroupRows * kTilePitchB;         // 2176 B per TMA tile (17 x 128 B)
-constexpr int kTileWarps = 4;
-#ifndef SDNET_X_CTAS
-#define SDNET_X_CTAS 6
+#ifndef SDNET_X_WARPS
+#define SDNET_X_WARPS 4
 #endif
-constexpr int kTileMinCtas = SDNET_X_CTAS;  // resident CTAs per SM the register allocation aims for
+constexpr int kTileWarps = SDNET_X_WARPS;  // warps per CTA; they never talk to each other (no __syncthreads in the kernel)
+#ifndef SDNET_X_CTAS
+#define SDNET_X_CTAS (24 / SDNET_X_WARPS)
+#endif
+constexpr int kTileMinCtas = SDNET_X_CTAS;  // resident CTAs per SM the register allocation aims for (24 warps)
 constexpr int kMinChunkGroups = 8;  // shortest tier-2 unit (32 rows)
 #ifndef SDNET_X_NG
 #define SDNET_X_NG 3

@@ -102,6 +102,8 @@ int validate(const SdnetDecodeParams* p) {
   if (p->K > SDNET_MAX_TOPK || p->P > SDNET_MAX_TOPK || p->M + p->N > SDNET_MAX_CHANNELS) return SDNET_E_SHAPE;
   if (p->radius != 1 && p->radius != 2) return SDNET_E_RADIUS;
   if (p->n_dest < 0 || p->n_dest > SDNET_MAX_DEST) return SDNET_E_SHAPE;
+  if (p->dest_mode != SDNET_DEST_PEER_STORES && p->dest_mode != SDNET_DEST_MULTICAST) return SDNET_E_SHAPE;
+  if (p->dest_mode == SDNET_DEST_MULTICAST && p->n_dest != 1) return SDNET_E_SHAPE;
   const bool no_group = (p->flags & SDNET_FLAG_NO_GROUPING) != 0;
   if (!p->anchor_hm.data || !p->part_hm.data || !p->offsets.data || (!no_group && !p->embeddings.data)) return SDNET_E_NULL;
   if (!p->anchor_out || !p->part_out || !p->anchor_inds || !p->part_inds || !p->assign || !p->counts) return SDNET_E_NULL;
@@ -439,6 +441,7 @@ int launch_decode(const SdnetDecodeParams* p, cudaStream_t stream, cudaEvent_t* 
   tp.exact_flags = reinterpret_cast<const int*>(base + ws.off_flags);
   tp.ghist = pp.ghist;
   tp.n_dest = p->n_dest;
+  tp.dest_multicast = p->dest_mode == SDNET_DEST_MULTICAST ? 1 : 0;
   for (int j = 0; j < SDNET_MAX_DEST; ++j) tp.dest_delta[j] = j < p->n_dest ? p->dest_delta[j] : 0;
   if (p->dtype == SDNET_DTYPE_F16) launch_pdl(sdnet_tail_kernel<SDNET_DTYPE_F16>, dim3((unsigned)p->B), dim3(2 * kTeamThreads), stream, tp);
   else if (p->dtype == SDNET_DTYPE_BF16) launch_pdl(sdnet_tail_kernel<SDNET_DTYPE_BF16>, dim3((unsigned)p->B), dim3(2 * kTeamThreads), stream, tp);

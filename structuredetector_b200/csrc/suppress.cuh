@@ -149,7 +149,7 @@ constexpr int kSupTileSmemPerWarp = (kTileNG * kTileBytes + 32 + 127) / 128 * 12
 constexpr int kSupTileSmem = kTileWarps * kSupTileSmemPerWarp;
 
 template <int R>
-__global__ void __launch_bounds__(kTileWarps * 32, 6)
+__global__ void __launch_bounds__(kTileWarps * 32, 24 / kTileWarps)
 sdnet_suppress_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_constant__ CUtensorMap tm, const View4 outv) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int NG = kTileNG;

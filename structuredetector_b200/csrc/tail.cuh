@@ -25,15 +25,33 @@ struct TailParams {
   const int* exact_flags;  // [planes] 1 if the exact select rewrote the list
   const u32* ghist;        // [planes][kFineBins] logit histogram of the recorded candidates (peaks kernels)
   int n_dest;              // fused gather: every output is stored n_dest times, at ptr + dest_delta[j]
+  int dest_multicast;      // ... or once, with multimem.st, at the multicast address ptr + dest_delta[0]
   long long dest_delta[SDNET_MAX_DEST];
 };
 
 // Store one output value locally (n_dest == 0) or into every destination copy of the output blob
-// (fused detection gather: peer-mapped symmetric memory, plain st.global over NVLink).
+// (fused detection gather: peer-mapped symmetric memory).  Two forms: plain st.global to each peer's
+// address, n_dest stores per value; or -- dest_multicast -- ONE multimem.st to the NVSwitch multicast
+// address of the blob (dest_delta[0] = multicast_base - local_base), which the switch replicates into
+// every GPU's copy, the local one included: 1/n_dest of the store instructions and of the NVLink egress.
+__device__ __forceinline__ void mc_store(void* a, const float4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void mc_store(void* a, const float2& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1, %2};" ::"l"(a), "f"(v.x), "f"(v.y) : "memory");
+}
+__device__ __forceinline__ void mc_store(void* a, const long long& v) {
+  asm volatile("multimem.st.relaxed.sys.global.b64 [%0], %1;" ::"l"(a), "l"(v) : "memory");
+}
+__device__ __forceinline__ void mc_store(void* a, const int& v) {
+  asm volatile("multimem.st.relaxed.sys.global.b32 [%0], %1;" ::"l"(a), "r"(v) : "memory");
+}
 template <typename T>
 __device__ __forceinline__ void store_out(const TailParams& p, T* ptr, const T& v) {
   if (p.n_dest == 0) {
     *ptr = v;
+  } else if (p.dest_multicast) {
+    mc_store(reinterpret_cast<char*>(ptr) + p.dest_delta[0], v);
   } else {
     for (int j = 0; j < p.n_dest; ++j) *reinterpret_cast<T*>(reinterpret_cast<char*>(ptr) + p.dest_delta[j]) = v;
   }

@@ -8,10 +8,12 @@ tests) is plumbing only.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.distributed as dist
 
-from . import ops
+from . import _native, ops
 
 __all__ = ["shard_bounds", "shard_sizes", "all_gather_packed", "merge_packed", "ShardedDecoder", "FusedGatherPlan"]
 
@@ -76,8 +78,9 @@ class ShardedDecoder:
 
 class FusedGatherPlan:
     """Decode + gather in one pass: the tail kernel stores every rank's packed detections straight
-    into EVERY rank's copy of the global result (peer-mapped symmetric memory, plain stores over
-    NVLink / NVSwitch), and one cross-GPU barrier replaces the all-gather collective.
+    into EVERY rank's copy of the global result (peer-mapped symmetric memory; one ``multimem.st`` per
+    value through the NVSwitch multicast mapping when there is one, else a plain store per peer over
+    NVLink), and one cross-GPU barrier replaces the all-gather collective.
 
     The global result is one packed blob for the whole batch (``ops._carve`` layout); rank r owns the
     image rows ``shard_bounds(B, world, r)`` of every field.  ``dest_delta[j] = peer_base[j] -
@@ -116,12 +119,28 @@ class FusedGatherPlan:
         self._mine = [ops.PackedDetections(
             r.anchor_out[lo:hi], r.part_out[lo:hi], r.anchor_inds[lo:hi], r.part_inds[lo:hi], r.part_emb[lo:hi],
             r.assign[lo:hi], r.counts[lo:hi], r.diag[lo * C:hi * C], None) for r in self.results]
-        # ... and every store is replicated into the peers' copies
+        # ... and every store reaches every rank's copy: ONE multimem.st to the blob's NVSwitch multicast mapping when
+        # the fabric offers one (the switch replicates it, the local copy included), else one st.global per peer
         ptrs = list(self.handle.buffer_ptrs)
         prm = self.plan.params
-        prm.n_dest = self.world
-        for j in range(self.world):
-            prm.dest_delta[j] = int(ptrs[j]) - int(ptrs[self.rank])
+        mc = int(getattr(self.handle, "multicast_ptr", 0) or 0)
+        want = os.environ.get("SDNET_GATHER_STORES", "auto")  # auto | multicast | peer
+        if want not in ("auto", "multicast", "peer"):
+            raise ValueError(f"SDNET_GATHER_STORES={want!r}: expected auto, multicast or peer")
+        if want == "multicast" and mc == 0:
+            raise RuntimeError("SDNET_GATHER_STORES=multicast but the symmetric allocation has no multicast mapping")
+        self.stores = "multicast" if (mc != 0 and want != "peer") else "peer"
+        if self.stores == "multicast":
+            prm.n_dest, prm.dest_mode = 1, _native.DEST_MULTICAST
+            prm.dest_delta[0] = mc - int(ptrs[self.rank])
+        else:
+            prm.n_dest, prm.dest_mode = self.world, _native.DEST_PEER_STORES
+            for j in range(self.world):
+                prm.dest_delta[j] = int(ptrs[j]) - int(ptrs[self.rank])
+        # timing diagnostics only (results are wrong or unsafe): "local" = no remote stores, "nobarrier" = no barrier
+        self._diag = os.environ.get("SDNET_GATHER_DIAG", "")
+        if "local" in self._diag:
+            prm.n_dest, prm.dest_mode = 0, _native.DEST_PEER_STORES
         self.handle.barrier()  # everyone is mapped before the first remote store
 
     def run(self, anchor_hm, part_hm, offsets, embeddings, conf_f32, dist_abs_f32, radius=2, flags=0,
@@ -134,7 +153,8 @@ class FusedGatherPlan:
         self._runs += 1
         self.plan._bind_outputs(self._mine[k])
         self.plan.run(anchor_hm, part_hm, offsets, embeddings, conf_f32, dist_abs_f32, radius, flags, stream=stream)
-        with torch.cuda.stream(stream):
-            self.handle.barrier()
+        if "nobarrier" not in self._diag:
+            with torch.cuda.stream(stream):
+                self.handle.barrier()
         self.result = self.results[k]
         return self.result
