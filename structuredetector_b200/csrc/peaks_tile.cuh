@@ -613,6 +613,10 @@ sdnet_peaks_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_cons
         // 4-row block a lane without building the list -- more, emptier passes: 0.72 / 0.78 ms; parking the hot pixels
         // of sparse groups and testing their windows 32 at a time from global memory (L2) -- the warp stalls on the
         // scattered loads longer than the saved passes cost: 0.91 / 1.01 ms.
+        // Also measured and dropped: loading the NEXT segment's first tiles into the ring slots a segment's last groups
+        // free (unit fetched from the counter three groups early): 0.704 / 0.753 ms against 0.684 / 0.729 ms in the same
+        // run -- with HBM the shared limit, one warp's cold ring is bandwidth the other warps use; and one warp per CTA
+        // (24 CTAs per SM, so that a finished warp's slot is refilled at once): 0.707 / 0.765 against 0.699 / 0.774 ms.
         const int nhot = __popc(hot), rows_here = nrows - g * kGroupRows;
         const float floorx = st.floorx;
         bool settled = false;

@@ -11,3 +11,4 @@ EXTRA=--no-parity run local SDNET_GATHER_DIAG=local
 EXTRA=--no-parity run nobar SDNET_GATHER_DIAG=nobarrier
 EXTRA=--no-parity run solo SDNET_GATHER_DIAG=local,nobarrier
 EXTRA="--no-parity --pipeline 8" run auto_p8 X=1
+python -m torch.distributed.run --nnodes=1 --nproc-per-node $NP --master-addr 127.0.0.1 --master-port 29531 tools/host_rate.py 128 6 2>&1 | grep "img x" | sort | head -20
