@@ -613,6 +613,15 @@ sdnet_peaks_tile_kernel(const __grid_constant__ PeaksParams p, const __grid_cons
         // 4-row block a lane without building the list -- more, emptier passes: 0.72 / 0.78 ms; parking the hot pixels
         // of sparse groups and testing their windows 32 at a time from global memory (L2) -- the warp stalls on the
         // scattered loads longer than the saved passes cost: 0.91 / 1.01 ms.
+        // Also measured and dropped (r02, same-run pairs): settling a hot lane's 4 x 4 block by the whole warp (one LDS.64
+        // per lane of the 8 x 8 window region, separable 5-maxima by shuffles: ~35 instructions against ~160 for list +
+        // pass) for groups with up to 1 / 3 / 6 hot lanes: 0.706 / 0.725 / 0.734 ms against 0.691 (noise), 0.767 / 0.768 /
+        // 0.819 against 0.733 (blobs) -- nine dependent shuffles are a longer chain than the pass's independent loads,
+        // and a warp's pace is set by dependent latency (10 cycles per issued instruction on average at 6 warps per
+        // scheduler), not by issue slots; one out-of-line copy of the flush instead of four inlined ones (the kernel is
+        // 4,872 SASS instructions = 78 KB, 3,512 with the call; no_instruction stalls 0.8 cycles per instruction): 0.707 /
+        // 0.750 against 0.690 / 0.734 ms, fp16 0.709 against 0.640 -- the call's register shuffling costs more than the
+        // instruction fetches it saves.
         // Also measured and dropped: loading the NEXT segment's first tiles into the ring slots a segment's last groups
         // free (unit fetched from the counter three groups early): 0.704 / 0.753 ms against 0.684 / 0.729 ms in the same
         // run -- with HBM the shared limit, one warp's cold ring is bandwidth the other warps use; and one warp per CTA
