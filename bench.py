@@ -62,7 +62,7 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--pipeline", type=int, default=0,
                     help="decodes in flight: consecutive steps alternate between this many plans/streams; 0 = auto "
-                         "(3 for shards of >= 512 images, 4 down to 161, 6 for smaller ones)")
+                         "(3 for shards of >= 512 images, 4 down to 161, 8 for smaller ones)")
     ap.add_argument("--gather", choices=("fused", "nccl"), default="fused",
                     help="N > 1: tail kernel stores into every peer (symmetric memory) + barrier, or ncclAllGather")
     return ap.parse_args()
@@ -344,8 +344,10 @@ def main():
             fused = FusedGatherPlan(device, cfg.batch, M, N, H, W, K, P, dtype=tdtype)
             how = ("one multimem.st per value to the blob's NVSwitch multicast mapping" if fused.stores == "multicast"
                    else "one st.global per peer over NVLink")
-            gather_kind = (f"fused: tail kernel stores each rank's packed detections into every rank's copy (symmetric memory, {how}) "
-                           "+ one symmetric-memory barrier; results double-buffered")
+            sync = ("the tail kernel's last CTA releases the rank's completion flag into every copy, a one-CTA wait kernel spins on the local flags"
+                    if fused.sync == "flags" else "one symmetric-memory barrier")
+            gather_kind = (f"fused: tail kernel stores each rank's packed detections into every rank's copy (symmetric memory, {how}); "
+                           f"{sync}; results double-buffered")
         except Exception as exc:  # noqa: BLE001
             print(f"[bench] symmetric memory unavailable ({exc!r}); falling back to ncclAllGather", file=sys.stderr)
             fused = None
@@ -359,7 +361,8 @@ def main():
     # measured on one B200 (profiles/r02_pipeline_depth.log): 1024 images 0.806 / 0.784 / 0.774 ms per step at depth 1 / 2 / 3;
     # 128 images 0.139 / 0.122 / 0.117 ms at 2 / 4 / 6 -- consecutive kernels overlap at their ends, and a small shard's
     # kernel is all warm-up at its start and all streaming at its end, so more of them in flight mix those phases
-    depth = args.pipeline if args.pipeline > 0 else (3 if shard >= 512 else (4 if shard > 160 else 6))
+    # (8 GPUs x 128 images, profiles/r02_gather_n8.log: 0.131 ms per step at depth 6, 0.128 at 8)
+    depth = args.pipeline if args.pipeline > 0 else (3 if shard >= 512 else (4 if shard > 160 else 8))
     pipe = None
     if depth > 1:
         if fused is not None:

@@ -99,6 +99,14 @@ typedef struct SdnetDecodeParams {
   int32_t n_dest;
   int32_t dest_mode; /* SDNET_DEST_* */
   int64_t dest_delta[SDNET_MAX_DEST];
+  /* Completion flag of the fused gather (optional, n_dest > 0 only): when done_flag is not NULL, the last CTA of the
+   * tail kernel to finish -- after every CTA's output stores and a system-scope fence -- stores done_value to
+   * (char*)done_flag + dest_delta[j] in every destination copy (release, system scope; one multimem.st under
+   * SDNET_DEST_MULTICAST).  With done_flag = &flags[rank] of a per-rank flag array inside the symmetric allocation and
+   * done_value counting this rank's decodes, sdnet_gather_wait_launch on flags replaces the cross-GPU barrier. */
+  uint32_t* done_flag;
+  uint32_t done_value;
+  uint32_t reserved1;
 } SdnetDecodeParams;
 
 /* Library / ABI identification. */
@@ -162,6 +170,11 @@ int sdnet_suppress_launch(const SdnetTensor4* in, int dtype, int B, int C, int H
  * reference's RawDecoder / CoreMLModel (src/sdnet/cli/convert_coreml.py:12-29) -- needs no torch.cat pass. */
 int sdnet_suppress_into_launch(const SdnetTensor4* in, int dtype, int B, int C, int H, int W, int radius, const SdnetTensor4* out,
                                void* stream);
+
+/* The consumer side of the fused gather's completion flags: enqueue, on `stream`, a wait until flags[j] >= value for
+ * every j < world (acquire loads, system scope; one tiny CTA that spins).  Everything enqueued on `stream` after it
+ * sees every rank's detections of decode number `value`.  Replaces the all-gather's implicit synchronisation. */
+int sdnet_gather_wait_launch(const uint32_t* flags, int world, uint32_t value, void* stream);
 
 /* Same as sdnet_decode_launch but the four input tensors live in (pinned) HOST memory: the heat-map
  * planes are copied to `staging` (device, >= B*(M+N)*H*W*elem bytes, 256-byte aligned) with one strided

@@ -37,6 +37,7 @@ EXPORTS = (
     "sdnet_decode_peaks_path",
     "sdnet_decode_schedule",
     "sdnet_match_launch",
+    "sdnet_gather_wait_launch",
     "sdnet_match_objects_launch",
     "sdnet_activate_launch",
     "sdnet_suppress_launch",
@@ -87,6 +88,9 @@ class SdnetDecodeParams(ctypes.Structure):
         ("n_dest", ctypes.c_int32),
         ("dest_mode", ctypes.c_int32),
         ("dest_delta", ctypes.c_int64 * MAX_DEST),
+        ("done_flag", ctypes.c_void_p),
+        ("done_value", ctypes.c_uint32),
+        ("reserved1", ctypes.c_uint32),
     ]
 
 
@@ -161,6 +165,8 @@ def load_from(path) -> ctypes.CDLL:
     lib.sdnet_decode_workspace_bytes.argtypes = [ctypes.c_int] * 8 + [ctypes.POINTER(ctypes.c_size_t)]
     lib.sdnet_decode_launch.restype = ctypes.c_int
     lib.sdnet_decode_launch.argtypes = [ctypes.POINTER(SdnetDecodeParams), ctypes.c_void_p]
+    lib.sdnet_gather_wait_launch.restype = ctypes.c_int
+    lib.sdnet_gather_wait_launch.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32, ctypes.c_void_p]
     lib.sdnet_match_launch.restype = ctypes.c_int
     lib.sdnet_match_launch.argtypes = [ctypes.POINTER(SdnetMatchParams), ctypes.c_void_p]
     lib.sdnet_match_objects_launch.restype = ctypes.c_int

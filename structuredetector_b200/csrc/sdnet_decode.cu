@@ -442,6 +442,9 @@ int launch_decode(const SdnetDecodeParams* p, cudaStream_t stream, cudaEvent_t* 
   tp.ghist = pp.ghist;
   tp.n_dest = p->n_dest;
   tp.dest_multicast = p->dest_mode == SDNET_DEST_MULTICAST ? 1 : 0;
+  tp.done_flag = p->n_dest > 0 ? p->done_flag : nullptr;
+  tp.done_value = p->done_value;
+  tp.ticket = pp.sched + 1;  // second word of the scheduler block, zeroed with it
   for (int j = 0; j < SDNET_MAX_DEST; ++j) tp.dest_delta[j] = j < p->n_dest ? p->dest_delta[j] : 0;
   if (p->dtype == SDNET_DTYPE_F16) launch_pdl(sdnet_tail_kernel<SDNET_DTYPE_F16>, dim3((unsigned)p->B), dim3(2 * kTeamThreads), stream, tp);
   else if (p->dtype == SDNET_DTYPE_BF16) launch_pdl(sdnet_tail_kernel<SDNET_DTYPE_BF16>, dim3((unsigned)p->B), dim3(2 * kTeamThreads), stream, tp);
@@ -478,6 +481,13 @@ int sdnet_decode_workspace_bytes(int B, int M, int N, int H, int W, int K, int P
   if ((long long)H * W >= (1ll << 24)) return SDNET_E_SHAPE;
   *out_bytes = plan_workspace(B, M, N, H, W, K, P).total;
   return 0;
+}
+
+int sdnet_gather_wait_launch(const uint32_t* flags, int world, uint32_t value, void* stream) {
+  if (!flags) return SDNET_E_NULL;
+  if (world <= 0 || world > SDNET_MAX_DEST) return SDNET_E_SHAPE;
+  sdnet_gather_wait_kernel<<<dim3(1), dim3(32), 0, static_cast<cudaStream_t>(stream)>>>(flags, world, value);
+  return (int)cudaGetLastError();
 }
 
 int sdnet_match_launch(const SdnetMatchParams* p, void* stream) {

@@ -26,6 +26,9 @@ struct TailParams {
   const u32* ghist;        // [planes][kFineBins] logit histogram of the recorded candidates (peaks kernels)
   int n_dest;              // fused gather: every output is stored n_dest times, at ptr + dest_delta[j]
   int dest_multicast;      // ... or once, with multimem.st, at the multicast address ptr + dest_delta[0]
+  u32* done_flag;          // fused gather: completion flag of this rank (nullptr = none), stored like an output by the last CTA
+  u32 done_value;
+  u32* ticket;             // workspace counter (zeroed per launch): CTAs that have finished their stores
   long long dest_delta[SDNET_MAX_DEST];
 };
 
@@ -452,17 +455,39 @@ __global__ void __launch_bounds__(2 * kTeamThreads, 3) sdnet_tail_kernel(const _
       store_out(p, p.diag + ((size_t)b * C + c) * 2 + 1, p.exact_flags[(size_t)b * C + c]);
     }
   }
-#ifndef SDNET_X_TAILFENCE
-#define SDNET_X_TAILFENCE 1
-#endif
-#if SDNET_X_TAILFENCE == 1
-  if (p.n_dest) __threadfence_system();  // peer stores performed before the kernel retires
-#elif SDNET_X_TAILFENCE == 2
-  if (p.n_dest) {  // one fence per CTA, after everybody's stores: fences are cumulative over what the barrier ordered
-    __syncthreads();
-    if (threadIdx.x == 0) __threadfence_system();
+  if (p.n_dest) {
+    if (p.done_flag == nullptr) {
+      __threadfence_system();  // peer stores performed before the kernel retires (a barrier follows on the stream)
+    } else {
+      // Completion flag: every thread's stores are ordered before the CTA barrier, thread 0's system fence after it is
+      // cumulative over them, then the CTA takes a ticket; the CTA that takes the last one knows every other CTA has
+      // fenced, fences once more (acquire side of the ticket chain) and releases the flag into every copy.
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        __threadfence_system();
+        if (atomicAdd(p.ticket, 1u) == gridDim.x - 1) {
+          __threadfence_system();
+          if (p.dest_multicast) {
+            asm volatile("multimem.st.release.sys.global.u32 [%0], %1;" ::"l"(reinterpret_cast<char*>(p.done_flag) + p.dest_delta[0]), "r"(p.done_value) : "memory");
+          } else {
+            for (int j = 0; j < p.n_dest; ++j)
+              asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(reinterpret_cast<char*>(p.done_flag) + p.dest_delta[j]), "r"(p.done_value) : "memory");
+          }
+        }
+      }
+    }
   }
-#endif
+}
+
+// The consumer side: wait until every rank's completion flag has reached `value`.
+__global__ void sdnet_gather_wait_kernel(const u32* flags, int world, u32 value) {
+  const int j = threadIdx.x;
+  if (j < world) {
+    u32 v;
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + j) : "memory");
+    } while ((int)(v - value) < 0);  // wrap-safe "v < value"
+  }
 }
 
 // ---------------------------------------------------------------------------------------------

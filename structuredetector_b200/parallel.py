@@ -8,6 +8,7 @@ tests) is plumbing only.
 """
 from __future__ import annotations
 
+import ctypes
 import os
 
 import torch
@@ -87,13 +88,17 @@ class FusedGatherPlan:
     local_base`` (``SdnetDecodeParams.dest_delta``) is all the kernel needs, because symmetric buffers
     share one layout.  Requires equal per-field offsets on all ranks, i.e. the same (B, K, P, C).
 
+    Arrival: the last CTA of a rank's tail kernel releases that rank's completion flag (= its run count)
+    into every copy, and ``run`` ends with a one-CTA wait kernel that spins on the local flags until all
+    ranks have completed this run (``SDNET_GATHER_SYNC=barrier``: torch's symmetric-memory barrier instead).
+
     Write-after-read safety across ranks: the plan owns TWO result buffers and alternates between them.
-    Run i stores into buffer i % 2 on every rank, then passes the barrier.  A rank can only start the
-    remote stores of run i + 2 (the next writer of the same buffer) after it has passed the barrier of
-    run i + 1, i.e. after every peer has reached that barrier on its own stream -- which that peer
-    enqueued after whatever it did with result i.  So: consume (or copy) a result ON THE RUN STREAM, or
-    make the run stream wait for your consumer, before calling ``run`` again; the tensors returned by run
-    i stay valid until run i + 2 is enqueued.  No extra barrier is needed.
+    Run i stores into buffer i % 2 on every rank, then waits.  A rank can only start the remote stores of
+    run i + 2 (the next writer of the same buffer) after it has passed the wait of run i + 1, i.e. after
+    every peer has finished the tail kernel of ITS run i + 1 -- which that peer enqueued after whatever
+    it did with result i.  So: consume (or copy) a result ON THE RUN STREAM, or make the run stream wait
+    for your consumer, before calling ``run`` again; the tensors returned by run i stay valid until run
+    i + 2 is enqueued.  No extra barrier is needed.
     """
 
     def __init__(self, device, global_batch: int, M: int, N: int, H: int, W: int, K: int, P: int, group=None,
@@ -106,8 +111,11 @@ class FusedGatherPlan:
         self.lo, self.hi = shard_bounds(global_batch, self.world, self.rank)
         C = M + N
         nbytes = (ops.packed_nbytes(global_batch, K, P, C) + 255) // 256 * 256
-        self.blob = symm.empty(2 * nbytes, dtype=torch.uint8, device=device)
+        # two result buffers + one completion flag per rank (a 256-byte line of its own)
+        self.blob = symm.empty(2 * nbytes + 256, dtype=torch.uint8, device=device)
+        self.blob[2 * nbytes:].zero_()
         self.handle = symm.rendezvous(self.blob, self.group)
+        self._flags = self.blob[2 * nbytes:2 * nbytes + 4 * self.world].view(torch.int32)  # flags[j] = decodes rank j has completed
         # the gathered detections of run i live in results[i % 2]
         self.results = [ops._carve(self.blob[k * nbytes:(k + 1) * nbytes], global_batch, K, P, C) for k in range(2)]
         self.result = self.results[0]  # what the most recent run() returned
@@ -137,11 +145,21 @@ class FusedGatherPlan:
             prm.n_dest, prm.dest_mode = self.world, _native.DEST_PEER_STORES
             for j in range(self.world):
                 prm.dest_delta[j] = int(ptrs[j]) - int(ptrs[self.rank])
-        # timing diagnostics only (results are wrong or unsafe): "local" = no remote stores, "nobarrier" = no barrier
+        # How a rank learns that every rank's rows have arrived: "flags" (default) = the last CTA of each rank's tail
+        # kernel releases that rank's completion flag into every copy and a one-CTA wait kernel spins on the local flags
+        # (one-sided: no handshake, no round trip over NVLink); "barrier" = torch's symmetric-memory barrier kernel.
+        self.sync = os.environ.get("SDNET_GATHER_SYNC", "flags")
+        if self.sync not in ("flags", "barrier"):
+            raise ValueError(f"SDNET_GATHER_SYNC={self.sync!r}: expected flags or barrier")
+        if self.sync == "flags":
+            prm.done_flag = self._flags.data_ptr() + 4 * self.rank
+        # timing diagnostics only (results are wrong or unsafe): "local" = no remote stores, "nobarrier" = no barrier / wait
         self._diag = os.environ.get("SDNET_GATHER_DIAG", "")
         if "local" in self._diag:
-            prm.n_dest, prm.dest_mode = 0, _native.DEST_PEER_STORES
-        self.handle.barrier()  # everyone is mapped before the first remote store
+            prm.n_dest, prm.dest_mode, prm.done_flag = 0, _native.DEST_PEER_STORES, None
+            self.sync = "barrier"
+        torch.cuda.synchronize(self.plan.device)  # the flags are zero ...
+        self.handle.barrier()  # ... and everyone is mapped before the first remote store
 
     def run(self, anchor_hm, part_hm, offsets, embeddings, conf_f32, dist_abs_f32, radius=2, flags=0,
             stream: torch.cuda.Stream | None = None) -> ops.PackedDetections:
@@ -152,8 +170,16 @@ class FusedGatherPlan:
         k = self._runs % 2
         self._runs += 1
         self.plan._bind_outputs(self._mine[k])
+        self.plan.params.done_value = self._runs & 0xFFFFFFFF
         self.plan.run(anchor_hm, part_hm, offsets, embeddings, conf_f32, dist_abs_f32, radius, flags, stream=stream)
-        if "nobarrier" not in self._diag:
+        if "nobarrier" in self._diag:
+            pass
+        elif self.sync == "flags":
+            raw = getattr(stream, "cuda_stream", stream)
+            rc = self.plan.lib.sdnet_gather_wait_launch(ctypes.c_void_p(self._flags.data_ptr()), self.world,
+                                                        ctypes.c_uint32(self._runs & 0xFFFFFFFF), ctypes.c_void_p(raw))
+            _native.check(rc, "sdnet_gather_wait_launch")
+        else:
             with torch.cuda.stream(stream):
                 self.handle.barrier()
         self.result = self.results[k]

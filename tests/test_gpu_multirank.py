@@ -13,6 +13,7 @@ from structuredetector_b200.synth import CONFIGS, make_raw, split_outputs
 pytestmark = pytest.mark.gpu
 BATCH = 10  # uneven over 4 ranks, even over 2
 FUSED_RUNS = 5
+FUSED_VARIANTS = (('flags', 'auto'), ('barrier', 'auto'), ('flags', 'peer'))  # (SDNET_GATHER_SYNC, SDNET_GATHER_STORES)
 
 
 def _worker(rank, world, port, out_dir):
@@ -32,24 +33,30 @@ def _worker(rank, world, port, out_dir):
         # the fused path: tail kernel stores into every peer's copy + one barrier
         from structuredetector_b200 import ops
 
-        fp = parallel.FusedGatherPlan(f"cuda:{rank}", BATCH, cfg.labels, cfg.parts, cfg.height, cfg.width,
-                                      cfg.max_objects, cfg.max_parts)
         # Repeated runs reuse the plan's two symmetric result buffers.  Every run decodes DIFFERENT inputs
         # and its result is read (copied on the run stream) before the next run is enqueued, with no host
         # synchronisation in between and rank 1 deliberately slowed down: a missing write-after-read guard
         # would let the fast rank's next run overwrite rows the slow rank has not copied yet.
+        # Every way of getting the rows across (one multimem.st per value / one store per peer) and of knowing they
+        # have arrived (completion flags / symmetric-memory barrier) has to give the same bits.
         keys = ("anchor_out", "part_out", "anchor_inds", "part_inds", "assign")
-        copies = []
-        for it in range(FUSED_RUNS):
-            raw_it = make_raw(cfg, "noise", batch=BATCH, seed=500 + it)
-            o = split_outputs(raw_it[lo:hi].to(f"cuda:{rank}"), cfg.labels, cfg.parts)
-            res = fp.run(o["anchor_hm"], o["part_hm"], o["offsets"], o["embeddings"],
-                         ops._f32(cfg.conf_threshold), ops._f32(cfg.dist_thresh * min(cfg.width, cfg.height)))
-            if rank == 1:
-                torch.cuda._sleep(20_000_000)  # ~10 ms of device time before this rank reads its copy
-            copies.append({k: getattr(res, k).clone() for k in keys})
-        torch.cuda.synchronize()
-        torch.save([{k: v.cpu() for k, v in c.items()} for c in copies], os.path.join(out_dir, f"fused{rank}.pt"))
+        for variant, (sync, stores) in enumerate(FUSED_VARIANTS):
+            os.environ.update(SDNET_GATHER_SYNC=sync, SDNET_GATHER_STORES=stores)
+            fp = parallel.FusedGatherPlan(f"cuda:{rank}", BATCH, cfg.labels, cfg.parts, cfg.height, cfg.width,
+                                          cfg.max_objects, cfg.max_parts)
+            assert fp.sync == sync and (stores == "auto" or fp.stores == stores)
+            copies = []
+            for it in range(FUSED_RUNS):
+                raw_it = make_raw(cfg, "noise", batch=BATCH, seed=500 + it)
+                o = split_outputs(raw_it[lo:hi].to(f"cuda:{rank}"), cfg.labels, cfg.parts)
+                res = fp.run(o["anchor_hm"], o["part_hm"], o["offsets"], o["embeddings"],
+                             ops._f32(cfg.conf_threshold), ops._f32(cfg.dist_thresh * min(cfg.width, cfg.height)))
+                if rank == 1:
+                    torch.cuda._sleep(20_000_000)  # ~10 ms of device time before this rank reads its copy
+                copies.append({k: getattr(res, k).clone() for k in keys})
+            torch.cuda.synchronize()
+            torch.save([{k: v.cpu() for k, v in c.items()} for c in copies], os.path.join(out_dir, f"fused{variant}_{rank}.pt"))
+            dist.barrier()
     finally:
         dist.destroy_process_group()
 
@@ -78,8 +85,9 @@ def test_sharded_decode_equals_single_gpu(cuda_device, tmp_path, world):
         got = torch.load(os.path.join(tmp_path, f"rank{rank}.pt"))
         for key, val in got.items():
             assert torch.equal(val, getattr(want, key).cpu()), f"nccl gather, rank {rank}: {key}"
-        runs = torch.load(os.path.join(tmp_path, f"fused{rank}.pt"))
-        assert len(runs) == FUSED_RUNS
-        for it, (g, w) in enumerate(zip(runs, want_runs)):
-            for key, val in g.items():
-                assert torch.equal(val, w[key]), f"fused gather, rank {rank}, run {it}: {key}"
+        for variant, names in enumerate(FUSED_VARIANTS):
+            runs = torch.load(os.path.join(tmp_path, f"fused{variant}_{rank}.pt"))
+            assert len(runs) == FUSED_RUNS
+            for it, (g, w) in enumerate(zip(runs, want_runs)):
+                for key, val in g.items():
+                    assert torch.equal(val, w[key]), f"fused gather {names}, rank {rank}, run {it}: {key}"
