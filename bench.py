@@ -398,6 +398,7 @@ def main():
     peaks_bytes = shard * (M + N) * H * W * esize  # algorithmic bytes of the dominant kernel: heat maps read once
 
     per_mode = {}
+    align = torch.zeros(1, device=device)
     for mode in modes:
         rot = outs_of[mode]
         for i in range(max(3, args.warmup)):
@@ -407,6 +408,11 @@ def main():
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with ClockSampler(physical_gpu_index(local_rank)) as clocks:
             fence()
+            if world > 1:
+                # start the clock at the same moment on every GPU: a stream-ordered collective right before the first
+                # event, so a rank whose host reaches this line late delays everybody's start instead of being waited
+                # for inside the others' timed regions (a 3 ms host skew is 12 % of a 200-step region at 8 GPUs)
+                dist.all_reduce(align)
             ev0.record()
             for i in range(args.steps):
                 step(rot[i % len(rot)])
