@@ -72,8 +72,9 @@ __device__ __forceinline__ u64 make_comp(u64 rec, int c_local) {
 // barrier.  They meet once, before the grouping.
 constexpr int kTeamThreads = 256;
 constexpr float kNearField = 1e5f;   // see the grouping pass
-constexpr int kRankSortMax = 192;     // up to this many collected composites are sorted by counting ranks (<= kTeamThreads)
-constexpr int kHistCollectMax = 512;  // a histogram cut-off that collects more than this falls back to the radix refinement
+constexpr int kRankPerThread = 4;     // composites a thread ranks at once
+constexpr int kRankSortMax = kRankPerThread * kTeamThreads;  // up to this many collected composites are sorted by counting ranks
+constexpr int kHistCollectSlack = 412;  // a histogram cut-off that collects more than want + this falls back to the radix refinement
 
 struct Team {
   int tid;    // thread index inside the team
@@ -173,8 +174,15 @@ __device__ int select_group(const Team& tm, const TailParams& p, int b, int c0, 
   for (int attempt = 0; attempt < 2; ++attempt) {
     if (by_hist) {
       for (int bin = tid; bin < kFineBins; bin += kTeamThreads) {
+        const u32* col = p.ghist + ((size_t)b * C + c0) * kFineBins + bin;
         u32 sum = 0;
-        for (int c = 0; c < nc; ++c) sum += __ldcg(p.ghist + ((size_t)b * C + c0 + c) * kFineBins + bin);
+        int c = 0;
+        for (; c + 4 <= nc; c += 4) {  // four planes' loads in flight (20 planes at cfg4: one L2 round trip each otherwise)
+          const u32 h0 = __ldcg(col + (size_t)c * kFineBins), h1 = __ldcg(col + (size_t)(c + 1) * kFineBins),
+                    h2 = __ldcg(col + (size_t)(c + 2) * kFineBins), h3 = __ldcg(col + (size_t)(c + 3) * kFineBins);
+          sum += (h0 + h1) + (h2 + h3);
+        }
+        for (; c < nc; ++c) sum += __ldcg(col + (size_t)c * kFineBins);
         s_hist[bin] = sum;
       }
       tm.sync();
@@ -240,16 +248,25 @@ __device__ int select_group(const Team& tm, const TailParams& p, int b, int c0, 
     for (int c = 0; c < nc; ++c) {
       const int n = min(p.counts[(size_t)b * C + c0 + c], p.cap);
       const u64* list = p.lists + ((size_t)b * C + c0 + c) * p.cap;
-      for (int i = tid; i < n; i += kTeamThreads) {
-        const u64 v = make_comp(list[i], c);
-        if ((u32)(v >> 32) >= floor_key && (bits == 0 || (v >> (64 - bits)) >= prefix)) {
-          const int slot = atomicAdd(&s_misc[1], 1);
-          if (slot < kSortN) s_sel[slot] = v;
+      for (int i0 = tid; i0 < n; i0 += 4 * kTeamThreads) {  // four records per thread in flight: the pass is L2-latency-bound
+        u64 rec[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int i = i0 + e * kTeamThreads;
+          rec[e] = i < n ? __ldcg(list + i) : 0ull;
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const u64 v = make_comp(rec[e], c);
+          if (i0 + e * kTeamThreads < n && (u32)(v >> 32) >= floor_key && (bits == 0 || (v >> (64 - bits)) >= prefix)) {
+            const int slot = atomicAdd(&s_misc[1], 1);
+            if (slot < kSortN) s_sel[slot] = v;
+          }
         }
       }
     }
     tm.sync();
-    if (!by_hist || s_misc[1] <= kHistCollectMax) break;
+    if (!by_hist || s_misc[1] <= min(kSortN, want + kHistCollectSlack)) break;
     // the histogram's superset is too large to sort cheaply (heavily tied scores): refine by radix instead
     tm.sync();
     if (tid == 0) s_misc[1] = 0;
@@ -259,15 +276,31 @@ __device__ int select_group(const Team& tm, const TailParams& p, int b, int c0, 
   }
   const int got = min(s_misc[1], kSortN);
   if (got <= kRankSortMax) {
-    // The usual case (want plus a few dozen): every thread ranks its own composite by counting the larger ones --
-    // got broadcast reads per thread, no barrier in the loop; composites are pairwise distinct (they end in the
-    // pixel index and the class), so the ranks are a permutation.
-    const u64 mine = tid < got ? s_sel[tid] : 0ull;
-    int rank = 0;
-    if (tid < got)
-      for (int j = 0; j < got; ++j) rank += s_sel[j] > mine ? 1 : 0;
+    // The usual case (want plus a few dozen; a few hundred more at K = 500): every thread ranks its own composites -- up
+    // to four of them -- by counting the larger ones: got broadcast reads per thread, no barrier in the loop;
+    // composites are pairwise distinct (they end in the pixel index and the class), so the ranks are a permutation.
+    u64 mine[kRankPerThread];
+    int rank[kRankPerThread];
+#pragma unroll
+    for (int e = 0; e < kRankPerThread; ++e) {
+      const int i = tid + e * kTeamThreads;
+      mine[e] = i < got ? s_sel[i] : 0ull;
+      rank[e] = 0;
+    }
+    if (got <= kTeamThreads) {  // one composite per thread: the short loop
+      if (tid < got)
+        for (int j = 0; j < got; ++j) rank[0] += s_sel[j] > mine[0] ? 1 : 0;
+    } else {
+      for (int j = 0; j < got; ++j) {
+        const u64 o = s_sel[j];
+#pragma unroll
+        for (int e = 0; e < kRankPerThread; ++e) rank[e] += o > mine[e] ? 1 : 0;
+      }
+    }
     tm.sync();
-    if (tid < got) s_sel[rank] = mine;
+#pragma unroll
+    for (int e = 0; e < kRankPerThread; ++e)
+      if (tid + e * kTeamThreads < got) s_sel[rank[e]] = mine[e];
     tm.sync();
     return min(got, want);
   }
