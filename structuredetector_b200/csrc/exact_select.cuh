@@ -10,7 +10,14 @@ namespace {
 // index-ordered emission pass that keeps every score above the K-th and the lowest-index
 // members of the K-th score's tie run.  Rewrites the plane's list with <= K records.
 // ---------------------------------------------------------------------------------------------
-constexpr int kExactThreads = 512;
+// A THIN CTA on purpose: 128 threads x <= 80 registers is exactly the footprint of one peaks-kernel CTA, so the CTAs of
+// the usual pass-through ("nothing overflowed": one look at the counts, exit) drop into whatever slot is free.  The
+// 512-thread, 116-register CTA this kernel used to have needs a whole SM's register file: the block scheduler drained
+// SM after SM of the next decode's peaks CTAs to place it, which cost 2.6 % of the step at 1024 images and 4-10 % at 128
+// with several decodes in flight (measured by skipping the launch).  Six thin CTAs per SM hold more threads than one
+// fat one, so a batch of saturated planes is not slower either; a single overflowed plane takes ~4x longer.
+constexpr int kExactThreads = 128;
+constexpr int kExactCtasPerSm = 6;
 
 struct ExactParams {
   View4 anchor, part;
@@ -88,7 +95,7 @@ __device__ void pick_digit(const u32* s_hist, int nbins, int need, int* s_out) {
 }
 
 template <int DT>
-__global__ void __launch_bounds__(kExactThreads) sdnet_exact_select_kernel(const __grid_constant__ ExactParams p) {
+__global__ void __launch_bounds__(kExactThreads, kExactCtasPerSm) sdnet_exact_select_kernel(const __grid_constant__ ExactParams p) {
   __shared__ u32 s_hist[2048];
   __shared__ int s_out[2];
   __shared__ int s_warp[kExactThreads / 32][2];
