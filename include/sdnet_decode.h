@@ -39,6 +39,10 @@ extern "C" {
 #define SDNET_FLAG_NO_GROUPING 2u   /* skip part->anchor grouping: decoders.py:345-423 (KeypointDecoder) */
 #define SDNET_FLAG_EXACT_SELECT 4u  /* route every plane through the bounded-memory exact select (testing) */
 #define SDNET_FLAG_WARP_KERNEL 8u   /* use the any-alignment per-warp peaks kernel even when the TMA one applies (testing) */
+#define SDNET_FLAG_WORKSPACE_CLEAN 16u /* the caller promises that the last thing that touched `workspace` was a completed
+                                          decode of the same shape (every decode leaves the workspace header zeroed behind
+                                          it), so the per-call cudaMemsetAsync of the header is skipped: one stream
+                                          operation less per decode.  Never set it for a fresh or reused-elsewhere buffer. */
 
 /* argument errors */
 #define SDNET_E_NULL -1      /* a required pointer is NULL */

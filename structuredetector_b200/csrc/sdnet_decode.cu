@@ -374,8 +374,10 @@ int launch_decode(const SdnetDecodeParams* p, cudaStream_t stream, cudaEvent_t* 
   PeaksPlan pl;
   cudaError_t err = plan_peaks(p, pp, pl);
   if (err != cudaSuccess) return (int)err;
-  err = cudaMemsetAsync(base, 0, ws.off_lists, stream);
-  if (err != cudaSuccess) return (int)err;
+  if (!(p->flags & SDNET_FLAG_WORKSPACE_CLEAN)) {  // else: the previous decode's tail kernel left the header zeroed
+    err = cudaMemsetAsync(base, 0, ws.off_lists, stream);
+    if (err != cudaSuccess) return (int)err;
+  }
   if (marks) cudaEventRecord(marks[0], stream);
 
   if (pl.tile_kern) {
@@ -448,6 +450,11 @@ int launch_decode(const SdnetDecodeParams* p, cudaStream_t stream, cudaEvent_t* 
   tp.done_flag = p->n_dest > 0 ? p->done_flag : nullptr;
   tp.done_value = p->done_value;
   tp.ticket = pp.sched + 1;  // second word of the scheduler block, zeroed with it
+  tp.ws_counts = pp.counts;
+  tp.ws_flags = reinterpret_cast<int*>(base + ws.off_flags);
+  tp.ws_gfloor = pp.gfloor;
+  tp.ws_ghist = pp.ghist;
+  tp.ws_sched = pp.sched;
   for (int j = 0; j < SDNET_MAX_DEST; ++j) tp.dest_delta[j] = j < p->n_dest ? p->dest_delta[j] : 0;
   if (p->dtype == SDNET_DTYPE_F16) launch_pdl(sdnet_tail_kernel<SDNET_DTYPE_F16>, dim3((unsigned)p->B), dim3(2 * kTeamThreads), stream, tp);
   else if (p->dtype == SDNET_DTYPE_BF16) launch_pdl(sdnet_tail_kernel<SDNET_DTYPE_BF16>, dim3((unsigned)p->B), dim3(2 * kTeamThreads), stream, tp);

@@ -29,6 +29,12 @@ struct TailParams {
   u32* done_flag;          // fused gather: completion flag of this rank (nullptr = none), stored like an output by the last CTA
   u32 done_value;
   u32* ticket;             // workspace counter (zeroed per launch): CTAs that have finished their stores
+  // the workspace header, to be left zeroed for the next decode (SDNET_FLAG_WORKSPACE_CLEAN)
+  int* ws_counts;
+  int* ws_flags;
+  int* ws_gfloor;
+  u32* ws_ghist;
+  u32* ws_sched;
   long long dest_delta[SDNET_MAX_DEST];
 };
 
@@ -488,6 +494,20 @@ __global__ void __launch_bounds__(2 * kTeamThreads, 3) sdnet_tail_kernel(const _
       store_out(p, p.diag + ((size_t)b * C + c) * 2 + 1, p.exact_flags[(size_t)b * C + c]);
     }
   }
+  // Leave the workspace header as a fresh memset would: this image's planes (counts, flags, floors, histograms -- all
+  // consumed above) and, once, the unit counter (the peaks kernel is long complete: pdl_wait).
+  __syncthreads();
+  {
+    const int C = p.M + p.N;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      p.ws_counts[(size_t)b * C + c] = 0;
+      p.ws_flags[(size_t)b * C + c] = 0;
+      p.ws_gfloor[(size_t)b * C + c] = 0;
+    }
+    uint4* gh = reinterpret_cast<uint4*>(p.ws_ghist + (size_t)b * C * kFineBins);
+    for (int i = threadIdx.x; i < C * kFineBins / 4; i += blockDim.x) gh[i] = make_uint4(0, 0, 0, 0);
+    if (b == 0 && threadIdx.x == 0) p.ws_sched[0] = 0;
+  }
   if (p.n_dest) {
     if (p.done_flag == nullptr) {
       __threadfence_system();  // peer stores performed before the kernel retires (a barrier follows on the stream)
@@ -499,6 +519,7 @@ __global__ void __launch_bounds__(2 * kTeamThreads, 3) sdnet_tail_kernel(const _
       if (threadIdx.x == 0) {
         __threadfence_system();
         if (atomicAdd(p.ticket, 1u) == gridDim.x - 1) {
+          *p.ticket = 0;  // for the next decode
           __threadfence_system();
           if (p.dest_multicast) {
             asm volatile("multimem.st.release.sys.global.u32 [%0], %1;" ::"l"(reinterpret_cast<char*>(p.done_flag) + p.dest_delta[0]), "r"(p.done_value) : "memory");

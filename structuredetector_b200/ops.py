@@ -18,7 +18,8 @@ import torch
 
 from . import _native
 PEAKS_PATHS = ("warp", "tile", "tile_row_pairs")  # SDNET_PATH_* in include/sdnet_decode.h
-from ._native import (FLAG_EXACT_SELECT, FLAG_NO_GROUPING, FLAG_PRE_ACTIVATED, FLAG_WARP_KERNEL, SdnetDecodeParams,
+from ._native import (FLAG_EXACT_SELECT, FLAG_NO_GROUPING, FLAG_PRE_ACTIVATED, FLAG_WARP_KERNEL, FLAG_WORKSPACE_CLEAN,
+                      SdnetDecodeParams,
                       SdnetSchedule, SdnetTensor4)
 
 __all__ = ["decode_packed", "activate_maps", "suppress_maps", "suppress_into", "DecodePlan", "DecodePipeline",
@@ -125,6 +126,16 @@ class DecodePlan:
         p.workspace = self.workspace.data_ptr()
         p.workspace_bytes = self.workspace_bytes
         self._bind_outputs(self.out)
+        self._clean = False  # True once a decode has run on this workspace: its tail kernel leaves the header zeroed
+
+    def _launch(self, fn, *args) -> None:
+        """Call a launch entry point; after the first successful decode the per-call memset of the workspace header is
+        skipped (SDNET_FLAG_WORKSPACE_CLEAN: every decode zeroes the header behind itself)."""
+        if self._clean:
+            self.params.flags |= FLAG_WORKSPACE_CLEAN
+        rc = fn(ctypes.byref(self.params), *args)
+        self._clean = rc == 0
+        _native.check(rc, fn.__name__)
 
     def _bind_outputs(self, out: PackedDetections):
         p = self.params
@@ -167,8 +178,7 @@ class DecodePlan:
         if stream is None:
             stream = torch.cuda.current_stream(self.device)
         stream = getattr(stream, "cuda_stream", stream)  # a torch.cuda.Stream or a raw cudaStream_t
-        rc = self.lib.sdnet_decode_launch(ctypes.byref(self.params), ctypes.c_void_p(stream))
-        _native.check(rc, "sdnet_decode_launch")
+        self._launch(self.lib.sdnet_decode_launch, ctypes.c_void_p(stream))
         return self.out
 
     def peaks_path(self, anchor_hm, part_hm, offsets, embeddings, radius=2, flags=0) -> str:
@@ -196,8 +206,7 @@ class DecodePlan:
         self._bind_inputs(anchor_hm, part_hm, offsets, embeddings, conf_f32, dist_abs_f32, radius, flags)
         ms = (ctypes.c_float * 3)()
         stream = torch.cuda.current_stream(self.device).cuda_stream
-        rc = self.lib.sdnet_decode_launch_timed(ctypes.byref(self.params), ctypes.c_void_p(stream), ms)
-        _native.check(rc, "sdnet_decode_launch_timed")
+        self._launch(self.lib.sdnet_decode_launch_timed, ctypes.c_void_p(stream), ms)
         return tuple(float(x) for x in ms)
 
     def run_host(self, anchor_hm, part_hm, offsets, embeddings, conf_f32, dist_abs_f32, staging: torch.Tensor,
@@ -207,10 +216,8 @@ class DecodePlan:
         if stream is None:
             stream = torch.cuda.current_stream(self.device)
         stream = getattr(stream, "cuda_stream", stream)
-        rc = self.lib.sdnet_decode_host_launch(ctypes.byref(self.params), ctypes.c_void_p(staging.data_ptr()),
-                                               ctypes.c_size_t(staging.numel() * staging.element_size()),
-                                               ctypes.c_void_p(stream))
-        _native.check(rc, "sdnet_decode_host_launch")
+        self._launch(self.lib.sdnet_decode_host_launch, ctypes.c_void_p(staging.data_ptr()),
+                     ctypes.c_size_t(staging.numel() * staging.element_size()), ctypes.c_void_p(stream))
         return self.out
 
 
