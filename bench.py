@@ -63,6 +63,9 @@ def parse_args():
     ap.add_argument("--pipeline", type=int, default=0,
                     help="decodes in flight: consecutive steps alternate between this many plans/streams; 0 = auto "
                          "(3 for shards of >= 512 images, 4 down to 161, 8 for smaller ones)")
+    ap.add_argument("--gather-wait", choices=("lazy", "step"), default="lazy",
+                    help="fused gather: wait for every rank's rows after each step, or only before a result buffer is "
+                         "written again (two runs later) and at the end of the timed region")
     ap.add_argument("--gather", choices=("fused", "nccl"), default="fused",
                     help="N > 1: tail kernel stores into every peer (symmetric memory) + barrier, or ncclAllGather")
     return ap.parse_args()
@@ -342,12 +345,15 @@ def main():
             from structuredetector_b200.parallel import FusedGatherPlan
 
             fused = FusedGatherPlan(device, cfg.batch, M, N, H, W, K, P, dtype=tdtype)
+            fused.lazy = args.gather_wait == "lazy"
             how = ("one multimem.st per value to the blob's NVSwitch multicast mapping" if fused.stores == "multicast"
                    else "one st.global per peer over NVLink")
             sync = ("the tail kernel's last CTA releases the rank's completion flag into every copy, a one-CTA wait kernel spins on the local flags"
                     if fused.sync == "flags" else "one symmetric-memory barrier")
+            when = ("arrival is waited for before a result buffer is written again (two runs later) and at the end of the timed region"
+                    if fused.lazy and fused.sync == "flags" else "arrival is waited for after every step")
             gather_kind = (f"fused: tail kernel stores each rank's packed detections into every rank's copy (symmetric memory, {how}); "
-                           f"{sync}; results double-buffered")
+                           f"{sync}; {when}; results double-buffered")
         except Exception as exc:  # noqa: BLE001
             print(f"[bench] symmetric memory unavailable ({exc!r}); falling back to ncclAllGather", file=sys.stderr)
             fused = None
@@ -367,6 +373,8 @@ def main():
     if depth > 1:
         if fused is not None:
             extra = [FusedGatherPlan(device, cfg.batch, M, N, H, W, K, P, dtype=tdtype) for _ in range(depth - 1)]
+            for e in extra:
+                e.lazy = fused.lazy
             pipe = ops.DecodePipeline(device, depth, lambda i: fused if i == 0 else extra[i - 1])
         elif world == 1:
             pipe = ops.DecodePipeline(device, depth, lambda i: plan if i == 0 else ops.DecodePlan(device, shard, M, N, H, W, K, P, tdtype))
@@ -417,7 +425,9 @@ def main():
             for i in range(args.steps):
                 step(rot[i % len(rot)])
             if pipe is not None:
-                pipe.drain()
+                pipe.drain()  # fused gather in lazy mode: includes the wait for every rank's rows of each plan's last run
+            elif fused is not None:
+                fused.wait_arrival()
             ev1.record()
             fence()
         ms_total = ev0.elapsed_time(ev1)
@@ -434,6 +444,7 @@ def main():
         o = rot[0]
         if fused is not None:
             res = fused.run(o["anchor_hm"], o["part_hm"], o["offsets"], o["embeddings"], conf32, dist32)
+            fused.wait_arrival()
         else:
             res = plan.run(o["anchor_hm"], o["part_hm"], o["offsets"], o["embeddings"], conf32, dist32)
         fence()

@@ -267,7 +267,10 @@ class DecodePipeline:
     def drain(self, stream: torch.cuda.Stream | None = None):
         """Make ``stream`` (default: the current one) wait for everything submitted so far."""
         stream = stream if stream is not None else torch.cuda.current_stream(self.device)
-        for st in self.streams:
+        for plan, st in zip(self.plans, self.streams):
+            arrived = getattr(plan, "wait_arrival", None)  # parallel.FusedGatherPlan in lazy mode: the gather's arrival
+            if arrived is not None:
+                arrived(st)
             stream.wait_stream(st)
 
 

@@ -120,6 +120,8 @@ class FusedGatherPlan:
         self.results = [ops._carve(self.blob[k * nbytes:(k + 1) * nbytes], global_batch, K, P, C) for k in range(2)]
         self.result = self.results[0]  # what the most recent run() returned
         self._runs = 0
+        self._waited = 0  # highest run number whose arrival has been waited for on the run stream
+        self.lazy = False
         shard = self.hi - self.lo
         self.plan = ops.DecodePlan(device, shard, M, N, H, W, K, P, dtype)
         # this rank's rows of each global buffer: where the plan's outputs point ...
@@ -161,26 +163,48 @@ class FusedGatherPlan:
         torch.cuda.synchronize(self.plan.device)  # the flags are zero ...
         self.handle.barrier()  # ... and everyone is mapped before the first remote store
 
+    def _enqueue_wait(self, value: int, stream) -> None:
+        """Everything enqueued on ``stream`` after this sees every rank's rows of run number ``value`` (and earlier)."""
+        if value <= self._waited or "nobarrier" in self._diag:
+            return
+        if self.sync == "flags":
+            raw = getattr(stream, "cuda_stream", stream)
+            rc = self.plan.lib.sdnet_gather_wait_launch(ctypes.c_void_p(self._flags.data_ptr()), self.world,
+                                                        ctypes.c_uint32(value & 0xFFFFFFFF), ctypes.c_void_p(raw))
+            _native.check(rc, "sdnet_gather_wait_launch")
+        else:  # a barrier cannot wait for the past: lazy mode degenerates to one barrier per run
+            with torch.cuda.stream(stream):
+                self.handle.barrier()
+        self._waited = value
+
     def run(self, anchor_hm, part_hm, offsets, embeddings, conf_f32, dist_abs_f32, radius=2, flags=0,
             stream: torch.cuda.Stream | None = None) -> ops.PackedDetections:
-        """Enqueue decode + remote stores + the barrier on ``stream`` (default: the current one); returns
-        the global result.  Every rank must call its plans in the same order."""
+        """Enqueue decode + remote stores + the arrival wait on ``stream`` (default: the current one); returns
+        the global result.  Every rank must call its plans in the same order, and a plan must stay on one stream.
+
+        ``self.lazy = True`` (completion flags only) defers the arrival wait: ``run`` then only waits -- before its own
+        stores -- for the run before the previous one's successor, which is what write-after-read safety of the two
+        result buffers needs, and the caller asks for arrival with ``wait_arrival`` when it wants to read a result.
+        Ranks then drift apart by up to two runs per plan instead of meeting after every run."""
         if stream is None:
             stream = torch.cuda.current_stream(self.plan.device)
         k = self._runs % 2
         self._runs += 1
+        run_no = self._runs
+        lazy = self.lazy and self.sync == "flags"
+        if lazy and run_no >= 3:
+            self._enqueue_wait(run_no - 1, stream)  # every peer is past its run (run_no - 1): it has consumed result (run_no - 2)
         self.plan._bind_outputs(self._mine[k])
-        self.plan.params.done_value = self._runs & 0xFFFFFFFF
+        self.plan.params.done_value = run_no & 0xFFFFFFFF
         self.plan.run(anchor_hm, part_hm, offsets, embeddings, conf_f32, dist_abs_f32, radius, flags, stream=stream)
-        if "nobarrier" in self._diag:
-            pass
-        elif self.sync == "flags":
-            raw = getattr(stream, "cuda_stream", stream)
-            rc = self.plan.lib.sdnet_gather_wait_launch(ctypes.c_void_p(self._flags.data_ptr()), self.world,
-                                                        ctypes.c_uint32(self._runs & 0xFFFFFFFF), ctypes.c_void_p(raw))
-            _native.check(rc, "sdnet_gather_wait_launch")
-        else:
-            with torch.cuda.stream(stream):
-                self.handle.barrier()
+        if not lazy:
+            self._enqueue_wait(run_no, stream)
         self.result = self.results[k]
         return self.result
+
+    def wait_arrival(self, stream: torch.cuda.Stream | None = None) -> None:
+        """Lazy mode: make ``stream`` (the plan's run stream) wait until every rank's rows of the most recent run
+        have arrived.  A no-op when that has been waited for already."""
+        if stream is None:
+            stream = torch.cuda.current_stream(self.plan.device)
+        self._enqueue_wait(self._runs, stream)

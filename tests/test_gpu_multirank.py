@@ -13,7 +13,8 @@ from structuredetector_b200.synth import CONFIGS, make_raw, split_outputs
 pytestmark = pytest.mark.gpu
 BATCH = 10  # uneven over 4 ranks, even over 2
 FUSED_RUNS = 5
-FUSED_VARIANTS = (('flags', 'auto'), ('barrier', 'auto'), ('flags', 'peer'))  # (SDNET_GATHER_SYNC, SDNET_GATHER_STORES)
+# (SDNET_GATHER_SYNC, SDNET_GATHER_STORES, lazy arrival waits)
+FUSED_VARIANTS = (('flags', 'auto', False), ('barrier', 'auto', False), ('flags', 'peer', False), ('flags', 'auto', True))
 
 
 def _worker(rank, world, port, out_dir):
@@ -40,11 +41,12 @@ def _worker(rank, world, port, out_dir):
         # Every way of getting the rows across (one multimem.st per value / one store per peer) and of knowing they
         # have arrived (completion flags / symmetric-memory barrier) has to give the same bits.
         keys = ("anchor_out", "part_out", "anchor_inds", "part_inds", "assign")
-        for variant, (sync, stores) in enumerate(FUSED_VARIANTS):
+        for variant, (sync, stores, lazy) in enumerate(FUSED_VARIANTS):
             os.environ.update(SDNET_GATHER_SYNC=sync, SDNET_GATHER_STORES=stores)
             fp = parallel.FusedGatherPlan(f"cuda:{rank}", BATCH, cfg.labels, cfg.parts, cfg.height, cfg.width,
                                           cfg.max_objects, cfg.max_parts)
             assert fp.sync == sync and (stores == "auto" or fp.stores == stores)
+            fp.lazy = lazy  # the reader then asks for arrival itself, on the run stream, before it copies
             copies = []
             for it in range(FUSED_RUNS):
                 raw_it = make_raw(cfg, "noise", batch=BATCH, seed=500 + it)
@@ -53,6 +55,7 @@ def _worker(rank, world, port, out_dir):
                              ops._f32(cfg.conf_threshold), ops._f32(cfg.dist_thresh * min(cfg.width, cfg.height)))
                 if rank == 1:
                     torch.cuda._sleep(20_000_000)  # ~10 ms of device time before this rank reads its copy
+                fp.wait_arrival()
                 copies.append({k: getattr(res, k).clone() for k in keys})
             torch.cuda.synchronize()
             torch.save([{k: v.cpu() for k, v in c.items()} for c in copies], os.path.join(out_dir, f"fused{variant}_{rank}.pt"))
