@@ -62,7 +62,7 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=4)
     ap.add_argument("--pipeline", type=int, default=0,
                     help="decodes in flight: consecutive steps alternate between this many plans/streams; 0 = auto "
-                         "(3 for shards of >= 512 images, 4 down to 161, 8 for smaller ones)")
+                         "(3 for shards of >= 512 images, 4 down to 161, 12 for smaller ones)")
     ap.add_argument("--gather-wait", choices=("lazy", "step"), default="lazy",
                     help="fused gather: wait for every rank's rows after each step, or only before a result buffer is "
                          "written again (two runs later) and at the end of the timed region")
@@ -367,8 +367,9 @@ def main():
     # measured on one B200 (profiles/r02_pipeline_depth.log): 1024 images 0.806 / 0.784 / 0.774 ms per step at depth 1 / 2 / 3;
     # 128 images 0.139 / 0.122 / 0.117 ms at 2 / 4 / 6 -- consecutive kernels overlap at their ends, and a small shard's
     # kernel is all warm-up at its start and all streaming at its end, so more of them in flight mix those phases
-    # (8 GPUs x 128 images, profiles/r02_gather_n8.log: 0.131 ms per step at depth 6, 0.128 at 8)
-    depth = args.pipeline if args.pipeline > 0 else (3 if shard >= 512 else (4 if shard > 160 else 8))
+    # (8 GPUs x 128 images, profiles/r02_gather_n8.log: 0.131 ms per step at depth 6, 0.128 at 8; with lazy arrival waits
+    # 0.1199 at 8, 0.1188 at 12)
+    depth = args.pipeline if args.pipeline > 0 else (3 if shard >= 512 else (4 if shard > 160 else 12))
     pipe = None
     if depth > 1:
         if fused is not None:
