@@ -81,7 +81,7 @@ class FusedGatherPlan:
     """Decode + gather in one pass: the tail kernel stores every rank's packed detections straight
     into EVERY rank's copy of the global result (peer-mapped symmetric memory; one ``multimem.st`` per
     value through the NVSwitch multicast mapping when there is one, else a plain store per peer over
-    NVLink), and one cross-GPU barrier replaces the all-gather collective.
+    NVLink), and per-rank completion flags replace the all-gather collective and its synchronisation.
 
     The global result is one packed blob for the whole batch (``ops._carve`` layout); rank r owns the
     image rows ``shard_bounds(B, world, r)`` of every field.  ``dest_delta[j] = peer_base[j] -
@@ -98,7 +98,8 @@ class FusedGatherPlan:
     every peer has finished the tail kernel of ITS run i + 1 -- which that peer enqueued after whatever
     it did with result i.  So: consume (or copy) a result ON THE RUN STREAM, or make the run stream wait
     for your consumer, before calling ``run`` again; the tensors returned by run i stay valid until run
-    i + 2 is enqueued.  No extra barrier is needed.
+    i + 2 is enqueued.  No extra barrier is needed.  ``lazy = True`` moves the wait from the end of a run to the
+    point where it is needed (see ``run`` / ``wait_arrival``).
     """
 
     def __init__(self, device, global_batch: int, M: int, N: int, H: int, W: int, K: int, P: int, group=None,
@@ -123,6 +124,9 @@ class FusedGatherPlan:
         self._waited = 0  # highest run number whose arrival has been waited for on the run stream
         self.lazy = False
         shard = self.hi - self.lo
+        if min(self.sizes) == 0:
+            raise ValueError(f"global batch {global_batch} leaves a rank of {self.world} without images: every rank "
+                             "takes part in the completion flags, so every rank needs at least one image")
         self.plan = ops.DecodePlan(device, shard, M, N, H, W, K, P, dtype)
         # this rank's rows of each global buffer: where the plan's outputs point ...
         lo, hi = self.lo, self.hi
