@@ -42,6 +42,38 @@ def test_struct_layout_matches_the_header():
     assert "struct_size" in _native.error_string(-7)
 
 
+def test_every_field_offset_matches_the_header_under_gcc(tmp_path):
+    """The ctypes mirror of every struct of the C ABI, field by field: a C program that includes the public header
+    prints sizeof and offsetof as the C compiler sees them."""
+    import shutil
+    import subprocess
+
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    structs = {n: getattr(_native, n) for n in
+               ("SdnetTensor4", "SdnetDecodeParams", "SdnetSchedule", "SdnetMatchParams", "SdnetObjectMatchParams")}
+    src = ["#include <stdio.h>", "#include <stddef.h>", '#include "sdnet_decode.h"', "int main(void) {"]
+    for name, struct in structs.items():
+        src.append(f'printf("{name} %zu\\n", sizeof({name}));')
+        src += [f'printf("{name}.{field} %zu\\n", offsetof({name}, {field}));' for field, _ in struct._fields_]
+    src.append("return 0; }")
+    (tmp_path / "layout.c").write_text("\n".join(src))
+    subprocess.run([cc, "-std=c99", "-Wall", "-Werror", f"-I{ROOT / 'include'}", str(tmp_path / "layout.c"), "-o", str(tmp_path / "layout")],
+                   check=True)
+    out = subprocess.run([str(tmp_path / "layout")], check=True, capture_output=True, text=True).stdout.split("\n")
+    seen = 0
+    for line in filter(None, out):
+        name, value = line.split()
+        if "." in name:
+            struct, field = name.split(".")
+            assert getattr(structs[struct], field).offset == int(value), name
+        else:
+            assert ctypes.sizeof(structs[name]) == int(value), name
+        seen += 1
+    assert seen == sum(len(s._fields_) + 1 for s in structs.values())
+
+
 def test_argument_errors_are_reported_before_any_launch():
     lib = _native.load()
     p = _native.SdnetDecodeParams()
@@ -56,6 +88,18 @@ def test_argument_errors_are_reported_before_any_launch():
     p.dtype, p.radius = 0, 3
     assert lib.sdnet_decode_launch(ctypes.byref(p), None) == -6
     assert lib.sdnet_decode_launch(None, None) == -1
+    # fused-gather destinations: unknown mode, multicast with more than its one (multicast) destination, too many peers
+    p.radius = 2
+    p.dest_mode, p.n_dest = 2, 1
+    assert lib.sdnet_decode_launch(ctypes.byref(p), None) == -2
+    p.dest_mode, p.n_dest = _native.DEST_MULTICAST, 2
+    assert lib.sdnet_decode_launch(ctypes.byref(p), None) == -2
+    p.dest_mode, p.n_dest = _native.DEST_PEER_STORES, _native.MAX_DEST + 1
+    assert lib.sdnet_decode_launch(ctypes.byref(p), None) == -2
+    assert lib.sdnet_gather_wait_launch(None, 2, 1, None) == -1
+    flag_words = (ctypes.c_uint32 * 16)()
+    assert lib.sdnet_gather_wait_launch(flag_words, 0, 1, None) == -2
+    assert lib.sdnet_gather_wait_launch(flag_words, _native.MAX_DEST + 1, 1, None) == -2
     out = ctypes.c_size_t(0)
     assert lib.sdnet_decode_workspace_bytes(1, 2, 1, 4096, 4096, 10, 10, 0, ctypes.byref(out)) == -2  # H*W >= 2^24
     # per-plane candidate lists hold 8 max(K, P) + 8192 records, but never less than the exact select's bitmap needs
