@@ -215,3 +215,34 @@ def test_pipeline_of_decodes_matches_serial(cuda_device):
         torch.cuda.synchronize()
         n = blob.numel() - want.diag.numel() * 4  # everything but the trailing diagnostics is deterministic
         assert torch.equal(blob[:n], want.blob[:n])
+
+
+def test_workspace_is_left_clean_between_decodes(cuda_device):
+    """From its second run on a DecodePlan skips the per-call memset (SDNET_FLAG_WORKSPACE_CLEAN): every decode has to
+    leave the workspace header as a memset would.  One plan whose workspace starts as garbage decodes different inputs
+    run after run -- among them a batch whose planes overflow into the exact select, and forced exact selects -- and
+    every run has to equal what a one-off decode of the same inputs gives."""
+    cfg = DecodeConfig("clean", 3, 2, 1, 96, 160, 50, 50, cfg_id=11)
+    sat = make_raw(cfg, "noise", seed=77)
+    sat[:, 0] = 3.0 + 0.0 * sat[:, 0]
+    sat[1, 2, 8:70, 16:150] = 25.0
+    runs = [(make_raw(cfg, "noise", seed=71), 0), (make_raw(cfg, "blobs", seed=72), 0), (sat, 0),
+            (make_raw(cfg, "ties", seed=73), 0), (make_raw(cfg, "noise", seed=74), ops.FLAG_EXACT_SELECT),
+            (make_raw(cfg, "ladder", seed=75), 0), (make_raw(cfg, "noise", seed=71), 0)]
+    conf32, dist32 = ops._f32(cfg.conf_threshold), ops._f32(cfg.dist_thresh * min(cfg.width, cfg.height))
+    plan = ops.DecodePlan(cuda_device, cfg.batch, cfg.labels, cfg.parts, cfg.height, cfg.width, cfg.max_objects, cfg.max_parts)
+    plan.workspace.fill_(0xA5)
+    for it, (raw, flags) in enumerate(runs):
+        o = split_outputs(raw.to(cuda_device), cfg.labels, cfg.parts)
+        got = {k: v.clone() for k, v in plan.run(o["anchor_hm"], o["part_hm"], o["offsets"], o["embeddings"], conf32, dist32,
+                                                 flags=flags).as_dict().items()}
+        assert plan._clean and bool(plan.params.flags & ops.FLAG_WORKSPACE_CLEAN) == (it > 0)
+        once = ops.DecodePlan(cuda_device, cfg.batch, cfg.labels, cfg.parts, cfg.height, cfg.width, cfg.max_objects, cfg.max_parts)
+        want = once.run(o["anchor_hm"], o["part_hm"], o["offsets"], o["embeddings"], conf32, dist32, flags=flags)
+        torch.cuda.synchronize()
+        for key, val in want.as_dict().items():  # field by field: the blob has alignment padding nobody writes
+            if key != "diag":  # candidates per plane depend on timing
+                assert torch.equal(got[key], val), f"run {it}: {key}"
+        assert torch.equal(got["diag"][:, 1], want.diag[:, 1]), f"run {it}: which planes went through the exact select"
+    planes = cfg.batch * (cfg.labels + cfg.parts)
+    assert int(plan.workspace.view(torch.int32)[:planes].abs().sum()) == 0, "candidate counts left behind"
