@@ -509,19 +509,23 @@ def main():
     o = outs_of[head][0]
     raw = buffers[head][0]
     sched = plan.schedule(o["anchor_hm"], o["part_hm"], o["offsets"], o["embeddings"])
-    traffic = None
+    # DRAM bytes per launch of the peaks kernel from the ncu capture of the same case (images per rank, input mode,
+    # dtype), when profiles/ holds one; null otherwise
+    traffic = traffic_source = None
     traffic_path = ROOT / "profiles" / "peaks_kernel_traffic.json"
-    if traffic_path.exists() and args.dtype == "f32" and args.workload == "cfg5":
+    if traffic_path.exists() and args.workload == "cfg5":
         try:
-            traffic = json.loads(traffic_path.read_text()).get(f"n{world}", {}).get("dram_bytes_per_launch")
+            for cap in json.loads(traffic_path.read_text()).get("captures", []):
+                if (cap.get("images"), cap.get("mode"), cap.get("dtype")) == (shard, head, args.dtype):
+                    traffic, traffic_source = cap["dram_bytes_per_launch"], cap.get("source")
         except Exception:  # noqa: BLE001
-            traffic = None
+            traffic = traffic_source = None
     step_s = ms_per_step * 1e-3
     roofline = {
         "bound": "hbm",
         "kernel": {"tile": "sdnet_peaks_tile_kernel (TMA tiles)", "tile_row_pairs": "sdnet_peaks_tile_kernel (TMA tiles over row pairs)",
                    "warp": "sdnet_peaks_kernel (per-lane feed)"}[sched["path"]],
-        "achieved": hm["peaks_achieved_gbs"], "peak": peak_gbs, "unit": "GB/s", "frac": hm["peaks_frac"], "traffic": traffic,
+        "achieved": hm["peaks_achieved_gbs"], "peak": peak_gbs, "unit": "GB/s", "frac": hm["peaks_frac"], "traffic": traffic, "traffic_source": traffic_source,
         "peak_source": peak_src, "mode": head, "kernel_ms": kernel_ms,
         "kernel_share_of_step": kernel_ms["peaks"] / (kernel_ms["peaks"] + kernel_ms["exact_select"] + kernel_ms["tail"]),
         "algorithmic_bytes_per_launch": peaks_bytes,

@@ -8,13 +8,13 @@ tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
 out, prof = Path("gpurun_out"), Path("profiles")
 BENCH = ("bench_n1", "bench_ref", "bench_n1_serial", "bench_n1_f16", "bench_n1_bf16", "bench_n1_gb128", "bench_cfg2", "bench_cfg3",
          "bench_cfg4")
-CAPTURES = (  # (report suffix, what was captured)
-    ("kernels_n1", "cfg5, 1024 images, fp32, noise: `python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline --no-objects --no-parity --pipeline 1 --mode noise`"),
-    ("kernels_n1_blobs", "same, `--mode blobs`"),
-    ("kernels_n1_gb128", "the 8-GPU shard: `--mode blobs --global-batch 128`"),
-    ("peaks_f16", "peaks kernel, `--mode noise --dtype f16` (row-pair tiles)"),
-    ("peaks_bf16", "peaks kernel, `--mode noise --dtype bf16` (row-pair tiles)"),
-    ("suppress", "`python tools/time_suppress.py 256` (dense sigmoid + NMS maps, 256 cfg5 images, fp32)"),
+CAPTURES = (  # (report suffix, what was captured, (images per rank, input mode, dtype) of a cfg5 peaks-kernel capture)
+    ("kernels_n1", "cfg5, 1024 images, fp32, noise: `python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline --no-objects --no-parity --pipeline 1 --mode noise`", (1024, "noise", "f32")),
+    ("kernels_n1_blobs", "same, `--mode blobs`", (1024, "blobs", "f32")),
+    ("kernels_n1_gb128", "the 8-GPU shard: `--mode blobs --global-batch 128`", (128, "blobs", "f32")),
+    ("peaks_f16", "peaks kernel, `--mode noise --dtype f16` (row-pair tiles)", (1024, "noise", "f16")),
+    ("peaks_bf16", "peaks kernel, `--mode noise --dtype bf16` (row-pair tiles)", (1024, "noise", "bf16")),
+    ("suppress", "`python tools/time_suppress.py 256` (dense sigmoid + NMS maps, 256 cfg5 images, fp32)", None),
 )
 SCALE = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1, "ms": 1e3,
          "byte/block": 1, "Kbyte/block": 1e3, "Mbyte/block": 1e6}
@@ -70,16 +70,17 @@ md = [f"# {tag}: ncu `--set full --clock-control none --import-source on` captur
       "plain run.  Columns: registers per thread, dynamic shared memory per CTA, DRAM bytes per launch, executed warp",
       "instructions, issue-slot utilisation, achieved occupancy, L2 hit rate.", ""]
 all_traffic = {}
-for suffix, what in CAPTURES:
+for suffix, what, case in CAPTURES:
     rep = out / f"{tag}_{suffix}.ncu-rep"
     if not rep.exists():
         continue
     lines, traffic = table(rep)
     md += [f"## {suffix} — {what}", ""] + lines + [""]
-    if traffic:
+    if traffic and case:
         traffic["source"] = f"profiles/{tag}_kernels.md section {suffix}"
+        traffic["images"], traffic["mode"], traffic["dtype"] = case
         all_traffic[suffix] = traffic
 (prof / f"{tag}_kernels.md").write_text("\n".join(md))
-if "kernels_n1" in all_traffic:
-    (prof / "peaks_kernel_traffic.json").write_text(json.dumps({"n1": all_traffic["kernels_n1"], **{k: v for k, v in all_traffic.items() if k != "kernels_n1"}}, indent=1))
+if all_traffic:  # bench.py looks its (images per rank, mode, dtype) up in this list
+    (prof / "peaks_kernel_traffic.json").write_text(json.dumps({"captures": list(all_traffic.values())}, indent=1))
 print("\n".join(md))
